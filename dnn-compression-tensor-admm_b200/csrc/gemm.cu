@@ -1,0 +1,172 @@
+// Batched fp32 GEMM with general operand strides: C = (A * B) .* colscale.
+// Used for the projection side of every truncated SVD (carry = U_r^T A, core = A V_r / sigma:
+// ttd.py:21-26), the tt2ten reconstruction chain (ttd.py:39-40) and the Tucker mode products
+// (tensorly multi_mode_dot behind admm.py:116-117).  One launch covers all layers of a step: the
+// tile list of every task is concatenated and grid-strided.
+#include "tta_common.cuh"
+
+namespace tta {
+
+constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kGemmMaxTasks = 192;
+
+struct GemmTable {
+  int n_tasks;
+  int total;
+  int start[kGemmMaxTasks + 1];
+};
+
+__global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task* __restrict__ tasks,
+                                                           const __grid_constant__ GemmTable tab) {
+  __shared__ __align__(16) float As[kGemmBK][kGemmBM + 4];
+  __shared__ __align__(16) float Bs[kGemmBK][kGemmBN + 4];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  for (int item = blockIdx.x; item < tab.total; item += gridDim.x) {
+    int lo = 0, hi = tab.n_tasks;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (tab.start[mid] <= item) lo = mid; else hi = mid;
+    }
+    const tta_gemm_task tk = tasks[lo];
+    const int tiles_n = (tk.N + kGemmBN - 1) / kGemmBN;
+    const int local = item - tab.start[lo];
+    const int m0 = (local / tiles_n) * kGemmBM;
+    const int n0 = (local % tiles_n) * kGemmBN;
+    const bool a_kfast = (tk.sak == 1);
+    const bool b_jfast = (tk.sbj == 1);
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < tk.K; k0 += kGemmBK) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = q * kGemmThreads + tid;  // 0..1023
+        int ar, ak;
+        if (a_kfast) { ar = e >> 4; ak = e & 15; } else { ak = e >> 6; ar = e & 63; }
+        const int gi = m0 + ar, gk = k0 + ak;
+        float v = 0.f;
+        if (gi < tk.M && gk < tk.K) v = __ldg(tk.a + (int64_t)gi * tk.sai + (int64_t)gk * tk.sak);
+        As[ak][ar] = v;
+        int bk, bj;
+        if (b_jfast) { bk = e >> 6; bj = e & 63; } else { bj = e >> 4; bk = e & 15; }
+        const int gj = n0 + bj, gkb = k0 + bk;
+        float vb = 0.f;
+        if (gj < tk.N && gkb < tk.K) vb = __ldg(tk.b + (int64_t)gkb * tk.sbk + (int64_t)gj * tk.sbj);
+        Bs[bk][bj] = vb;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kGemmBK; ++kk) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float a[4] = {av.x, av.y, av.z, av.w};
+        const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = m0 + ty * 4 + i;
+      if (gi >= tk.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gj = n0 + tx * 4 + j;
+        if (gj >= tk.N) continue;
+        float v = acc[i][j];
+        if (tk.colscale) v *= __ldg(tk.colscale + gj);
+        tk.c[(int64_t)gi * tk.ldc + gj] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sqnorm_kernel(const tta_sqnorm_task* __restrict__ tasks,
+                                                    double* __restrict__ out) {
+  __shared__ double s_part[8];
+  const tta_sqnorm_task tk = tasks[blockIdx.y];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tk.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)tk.x[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < 8 ? s_part[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, t);
+  }
+}
+
+}  // namespace tta
+
+extern "C" {
+
+int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
+                     void* stream) {
+  using namespace tta;
+  if (n_tasks < 0 || (n_tasks > 0 && (!tasks_dev || !tasks_host))) {
+    set_error("gemm: bad task table");
+    return TTA_E_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int first = 0; first < n_tasks; first += kGemmMaxTasks) {
+    const int cnt = (n_tasks - first) < kGemmMaxTasks ? (n_tasks - first) : kGemmMaxTasks;
+    GemmTable tab;
+    tab.n_tasks = cnt;
+    int64_t total = 0;
+    for (int t = 0; t < cnt; ++t) {
+      const tta_gemm_task& tk = tasks_host[first + t];
+      if (tk.M < 0 || tk.N < 0 || tk.K < 0 || (tk.M > 0 && tk.N > 0 && (!tk.c || (tk.K > 0 && (!tk.a || !tk.b))))) {
+        set_error("gemm: task %d invalid (M=%d N=%d K=%d)", first + t, tk.M, tk.N, tk.K);
+        return TTA_E_INVALID;
+      }
+      tab.start[t] = (int)total;
+      total += (int64_t)((tk.M + kGemmBM - 1) / kGemmBM) * ((tk.N + kGemmBN - 1) / kGemmBN);
+      if (total > 0x7fffffff) {
+        set_error("gemm: too many tiles");
+        return TTA_E_INVALID;
+      }
+    }
+    tab.start[cnt] = (int)total;
+    tab.total = (int)total;
+    if (total == 0) continue;
+    const int grid = total < (int64_t)kNumSMs * 16 ? (int)total : kNumSMs * 16;
+    gemm_kernel<<<grid, kGemmThreads, 0, st>>>(tasks_dev + first, tab);
+    TTA_CHECK_LAUNCH("gemm launch");
+  }
+  return TTA_OK;
+}
+
+int tta_sqnorm_batched(const tta_sqnorm_task* tasks_dev, const tta_sqnorm_task* tasks_host, int n_tasks,
+                       double* out_dev, void* stream) {
+  using namespace tta;
+  if (n_tasks <= 0) return TTA_OK;
+  if (!tasks_dev || !tasks_host || !out_dev) {
+    set_error("sqnorm: null argument");
+    return TTA_E_INVALID;
+  }
+  int64_t mx = 0;
+  for (int t = 0; t < n_tasks; ++t) mx = tasks_host[t].n > mx ? tasks_host[t].n : mx;
+  int gx = (int)((mx + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > kNumSMs * 4) gx = kNumSMs * 4;
+  dim3 grid(gx, n_tasks);
+  sqnorm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tasks_dev, out_dev);
+  TTA_CHECK_LAUNCH("sqnorm launch");
+  return TTA_OK;
+}
+}

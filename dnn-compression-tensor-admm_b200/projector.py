@@ -1,0 +1,257 @@
+"""Host-side plans for the batched low-rank projections (Z-update of admm.py:42-69).
+
+A plan is built once per (model, hp table): it owns the workspaces, precomputes every kernel's task
+table for every "wave" (TT step i over all layers at once -- the layers are independent, admm.py:43)
+and then replays them through the C ABI (`tta_runtime`) on each `run()`.
+
+TT-SVD of one layer (ttd.py:10-31) per step, with A the (r_i*s_i) x n unfolding of the carry:
+    m <= n :  G = A A^T  --eigh-->  E = top-r eigenvectors (rows),  core = E^T,  carry' = E A
+    m >  n :  G = A^T A  --eigh-->  E = V_r^T, sigma;  core = A E^T diag(1/sigma),  carry' = diag(sigma) E
+(the reference computes the same objects from a full LAPACK SVD; only the dominant r-dimensional
+singular subspace enters the reconstruction, and that subspace is the dominant eigenspace of G).
+Reconstruction (ttd.py:34-43) is the left-to-right chain of GEMMs, its last product written straight
+into Z (through the (O,KK,I)->(O,I,KK) fold for k x k convolutions, admm.py:99).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+import tta_runtime as rt
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _prod(xs):
+    p = 1
+    for v in xs:
+        p *= int(v)
+    return p
+
+
+def clip_tt_ranks(shapes, ranks):
+    """The in-place clip of ttd.py:18-19, resolved statically: r_{i+1} <- min(r_{i+1}, m, n)."""
+    ranks = list(ranks)
+    d = len(shapes)
+    for i in range(d - 1):
+        m = ranks[i] * shapes[i]
+        n = _prod(shapes[i + 1:])
+        ranks[i + 1] = min(ranks[i + 1], m, n)
+    return ranks
+
+
+def eig_geometry(k):
+    """Column-state geometry of the Jacobi solver for a k x k Gram matrix."""
+    ld = _round_up(k, 4)
+    bw = 16 if 2 * 16 * ld * 4 <= 200 * 1024 else 8
+    return ld, _round_up(k, bw), bw
+
+
+def gram_splits(k, red_len):
+    tiles = (k + 63) // 64
+    pairs = tiles * (tiles + 1) // 2
+    return max(1, min((red_len + 511) // 512, (296 + pairs - 1) // pairs))
+
+
+def tt_step_flops(shapes, ranks):
+    """SURVEY 8(d) accounting: (gram, proj, eig, recon) FLOPs of one layer (used for LPT sharding)."""
+    ranks = clip_tt_ranks(shapes, ranks)
+    d = len(shapes)
+    gram = proj = eig = recon = 0
+    for i in range(d - 1):
+        m = ranks[i] * shapes[i]
+        n = _prod(shapes[i + 1:])
+        k, big = min(m, n), max(m, n)
+        r = ranks[i + 1]
+        gram += 2 * k * k * big
+        proj += 2 * r * m * n * (2 if m > n else 1)
+        eig += 9 * k ** 3
+    for i in range(1, d):
+        recon += 2 * _prod(shapes[:i]) * ranks[i] * shapes[i] * ranks[i + 1]
+    return gram, proj, eig, recon
+
+
+class _Buf:
+    """fp32/fp64 workspace tensor + raw address."""
+
+    def __init__(self, numel, device, dtype=torch.float32):
+        self.t = torch.empty(max(int(numel), 1), dtype=dtype, device=device)
+        self.ptr = self.t.data_ptr()
+
+
+class TTLayer:
+    """Static description of one layer's projection.
+
+    kind: 'conv'   4-D weight (O, I, kh, kw) viewed as (O, KK, I) (admm.py:96)
+          'matrix' 2-D weight, tensorised row-major straight to `shapes` (admm.py:107)
+    """
+
+    def __init__(self, name, weight_shape, shapes, ranks):
+        self.name = name
+        self.weight_shape = tuple(int(v) for v in weight_shape)
+        self.numel = _prod(self.weight_shape)
+        if len(self.weight_shape) == 4:
+            o, i, kh, kw = self.weight_shape
+            self.O, self.I, self.KK = o, i, kh * kw
+        elif len(self.weight_shape) == 2:
+            self.O, self.I, self.KK = self.weight_shape[0], self.weight_shape[1], 1
+        else:
+            raise Exception('ERROR: unsupported layer in ADMM!')
+        self.shapes = [int(s) for s in shapes]
+        if _prod(self.shapes) != self.numel:
+            raise ValueError('tt_shapes {} do not factor weight {} of {}'.format(self.shapes, self.weight_shape, name))
+        if len(ranks) != len(self.shapes) + 1:
+            raise ValueError('need len(ranks) == len(tt_shapes) + 1 for {}'.format(name))
+        self.ranks = clip_tt_ranks(self.shapes, [int(r) for r in ranks])
+        self.d = len(self.shapes)
+
+
+class TTProjectionPlan:
+    """Batched TT-SVD projection of a list of layers: Z_l = Proj_TT(W_l + U_l)."""
+
+    def __init__(self, layers, device, tol=5e-7, max_sweeps=40):
+        self.layers = list(layers)
+        self.device = torch.device(device)
+        self.tol = float(tol)
+        self.max_sweeps = int(max_sweeps)
+        self.sweeps = {}
+        self._bound = None
+        self._alloc()
+
+    # -- workspace ---------------------------------------------------------------------------------
+    def _alloc(self):
+        dev = self.device
+        self.ws = []
+        for L in self.layers:
+            w = {'T': _Buf(L.numel, dev), 'steps': [], 'acc': {}}
+            carry = w['T']
+            for i in range(L.d - 1):
+                m = L.ranks[i] * L.shapes[i]
+                n = _prod(L.shapes[i + 1:])
+                k = min(m, n)
+                r = L.ranks[i + 1]
+                ld, kpad, bw = eig_geometry(k)
+                nsplit = gram_splits(k, max(m, n))
+                st = dict(m=m, n=n, k=k, r=r, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, A=carry,
+                          X=_Buf(ld * kpad, dev), part=_Buf(nsplit * k * k, dev, torch.float64),
+                          E=_Buf(r * k, dev), core=_Buf(m * r, dev), carry=_Buf(r * n, dev))
+                if m > n:
+                    st['sigma'] = _Buf(r, dev)
+                    st['isigma'] = _Buf(r, dev)
+                w['steps'].append(st)
+                carry = st['carry']
+            # reconstruction accumulators acc_j, j = 1..d-1 ; acc_0 is core_0
+            for j in range(1, L.d):
+                rows = _prod(L.shapes[:j + 1])
+                w['acc'][j] = _Buf(rows * L.ranks[j + 1], dev)
+            self.ws.append(w)
+        n_eig = max((sum(1 for L in self.layers if L.d - 1 > i) for i in range(self.max_order() - 1)), default=0)
+        self._n_eig_max = n_eig
+
+    def max_order(self):
+        return max((L.d for L in self.layers), default=0)
+
+    # -- task tables -------------------------------------------------------------------------------
+    def bind(self, w_list, u_list, z_list):
+        """(Re)build the task tables for concrete W / U / Z tensors (raw pointers are baked in)."""
+        key = tuple((w.data_ptr(), (u.data_ptr() if u is not None else 0), z.data_ptr())
+                    for w, u, z in zip(w_list, u_list, z_list))
+        if key == self._bound:
+            return
+        dev = self.device
+        for t in list(w_list) + [u for u in u_list if u is not None] + list(z_list):
+            rt.require_device(t)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise rt.TtaError('W/U/Z must be contiguous fp32 tensors')
+        nL = len(self.layers)
+
+        unfold = np.zeros(nL, dtype=rt.FOLD_TASK)
+        for li, (L, w) in enumerate(zip(self.layers, self.ws)):
+            unfold[li] = (w_list[li].data_ptr(), u_list[li].data_ptr() if u_list[li] is not None else 0,
+                          w['T'].ptr, 0, L.O, L.I, L.KK, 0)
+        self.t_unfold = rt.TaskTable(unfold, dev)
+
+        self.waves = []
+        for i in range(self.max_order() - 1):
+            idx = [li for li, L in enumerate(self.layers) if L.d - 1 > i]
+            g = np.zeros(len(idx), dtype=rt.GRAM_TASK)
+            e = np.zeros(len(idx), dtype=rt.EIG_TASK)
+            s = np.zeros(len(idx), dtype=rt.SELECT_TASK)
+            mm = np.zeros(len(idx), dtype=rt.GEMM_TASK)
+            for q, li in enumerate(idx):
+                st = self.ws[li]['steps'][i]
+                m, n, k, r = st['m'], st['n'], st['k'], st['r']
+                a = st['A'].ptr
+                if m <= n:   # row Gram A A^T
+                    g[q] = (a, st['part'].ptr, st['X'].ptr, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'])
+                    s[q] = (st['X'].ptr, st['E'].ptr, st['core'].ptr, 0, 0, 0, k, st['ld'], r, 0)
+                    # carry' (r x n) = E (r x m) * A (m x n)
+                    mm[q] = (st['E'].ptr, a, st['carry'].ptr, 0, m, 1, n, 1, n, r, n, m, 0)
+                else:        # column Gram A^T A
+                    g[q] = (a, st['part'].ptr, st['X'].ptr, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'])
+                    s[q] = (st['X'].ptr, st['E'].ptr, 0, st['carry'].ptr, st['sigma'].ptr, st['isigma'].ptr,
+                            k, st['ld'], r, 0)
+                    # core (m x r) = A (m x n) * E^T (n x r) * diag(1/sigma)
+                    mm[q] = (a, st['E'].ptr, st['core'].ptr, st['isigma'].ptr, n, 1, 1, n, r, m, r, n, 0)
+                e[q] = (st['X'].ptr, k, st['ld'], st['kpad'], st['bw'])
+            wave = dict(idx=idx, gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev),
+                        select=rt.TaskTable(s, dev), gemm=rt.TaskTable(mm, dev))
+            nbytes = rt.jacobi_scratch_bytes(wave['eig'])
+            wave['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
+            self.waves.append(wave)
+
+        # reconstruction chain: recon wave j multiplies acc_{j-1} by core_j (or the last carry)
+        self.recon = []
+        fold = []
+        for j in range(1, self.max_order()):
+            idx = [li for li, L in enumerate(self.layers) if L.d > j]
+            mm = np.zeros(len(idx), dtype=rt.GEMM_TASK)
+            for q, li in enumerate(idx):
+                L, w = self.layers[li], self.ws[li]
+                rows = _prod(L.shapes[:j])
+                rj, rj1, sj = L.ranks[j], L.ranks[j + 1], L.shapes[j]
+                left = w['steps'][0]['core'].ptr if j == 1 else w['acc'][j - 1].ptr
+                last = (j == L.d - 1)
+                right = w['steps'][j - 1]['carry'].ptr if last else w['steps'][j]['core'].ptr
+                out = w['acc'][j].ptr
+                if last and L.KK == 1:
+                    out = z_list[li].data_ptr()      # no fold needed: (O, 1, I) == (O, I)
+                ncols = sj * rj1
+                mm[q] = (left, right, out, 0, rj, 1, ncols, 1, ncols, rows, ncols, rj, 0)
+                if last and L.KK != 1:
+                    fold.append((0, 0, w['acc'][j].ptr, z_list[li].data_ptr(), L.O, L.I, L.KK, 0))
+            self.recon.append(rt.TaskTable(mm, dev))
+        self.t_fold = rt.TaskTable(np.array(fold, dtype=rt.FOLD_TASK) if fold else np.zeros(0, dtype=rt.FOLD_TASK), dev)
+        self._bound = key
+
+    # -- execution ---------------------------------------------------------------------------------
+    def run(self, w_list, u_list, z_list):
+        self.bind(w_list, u_list, z_list)
+        rt.unfold_add(self.t_unfold)
+        for wave in self.waves:
+            rt.gram(wave['gram'])
+            sw = rt.jacobi_eigh(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
+            for q, li in enumerate(wave['idx']):
+                self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
+            rt.select(wave['select'])
+            rt.gemm(wave['gemm'])
+        for tab in self.recon:
+            rt.gemm(tab)
+        if self.t_fold.n:
+            rt.fold_store(self.t_fold)
+
+    def cores(self, li):
+        """Cores of layer `li` after `run()` as tensors shaped (r_i, s_i, r_{i+1}) (ten2tt's return)."""
+        L, w = self.layers[li], self.ws[li]
+        out = []
+        for i in range(L.d - 1):
+            st = w['steps'][i]
+            out.append(st['core'].t[:st['m'] * st['r']].view(L.ranks[i], L.shapes[i], L.ranks[i + 1]))
+        last = w['steps'][-1]['carry'] if L.d > 1 else w['T']
+        out.append(last.t[:L.ranks[L.d - 1] * L.shapes[L.d - 1] * L.ranks[L.d]]
+                   .view(L.ranks[L.d - 1], L.shapes[L.d - 1], L.ranks[L.d]))
+        return out

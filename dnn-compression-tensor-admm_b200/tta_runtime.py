@@ -1,0 +1,210 @@
+"""ctypes binding of libtta.so (include/tta.h) -- the only bridge between the Python host code and
+the sm_100a kernels.  No torch types cross the boundary: raw device pointers, sizes and the current
+CUDA stream handle.
+
+There is NO CPU fallback: if libtta.so is missing or the device is not sm_100, every entry point
+raises.  (tests/ may inject an emulator of the C ABI through `set_backend_for_tests` to exercise the
+host-side index logic on a box without a GPU; product code never does.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtta.so')
+
+# ---- struct layouts (must mirror include/tta.h; checked by tests/test_abi.py against the header) ----
+P = np.uint64  # pointers
+EW_TASK = np.dtype([('w', P), ('z', P), ('u', P), ('g', P), ('numel', np.int64)], align=True)
+FOLD_TASK = np.dtype([('w', P), ('u', P), ('t', P), ('z', P), ('O', np.int32), ('I', np.int32),
+                      ('KK', np.int32), ('pad_', np.int32)], align=True)
+GRAM_TASK = np.dtype([('a', P), ('part', P), ('x', P), ('si', np.int64), ('sb', np.int64), ('sc', np.int64),
+                      ('k', np.int32), ('nb', np.int32), ('nc', np.int32), ('nsplit', np.int32),
+                      ('ld', np.int32), ('kpad', np.int32)], align=True)
+EIG_TASK = np.dtype([('x', P), ('k', np.int32), ('ld', np.int32), ('kpad', np.int32), ('bw', np.int32)],
+                    align=True)
+SELECT_TASK = np.dtype([('x', P), ('e', P), ('et', P), ('se', P), ('sigma', P), ('isigma', P),
+                        ('k', np.int32), ('ld', np.int32), ('r', np.int32), ('pad_', np.int32)], align=True)
+GEMM_TASK = np.dtype([('a', P), ('b', P), ('c', P), ('colscale', P), ('sai', np.int64), ('sak', np.int64),
+                      ('sbk', np.int64), ('sbj', np.int64), ('ldc', np.int64), ('M', np.int32),
+                      ('N', np.int32), ('K', np.int32), ('pad_', np.int32)], align=True)
+SQNORM_TASK = np.dtype([('x', P), ('n', np.int64)], align=True)
+
+STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.itemsize,
+                'tta_gram_task': GRAM_TASK.itemsize, 'tta_eig_task': EIG_TASK.itemsize,
+                'tta_select_task': SELECT_TASK.itemsize, 'tta_gemm_task': GEMM_TASK.itemsize,
+                'tta_sqnorm_task': SQNORM_TASK.itemsize}
+
+EXPORTS = ['tta_last_error', 'tta_version', 'tta_check_device', 'tta_dual_update_multi',
+           'tta_penalty_fwd_multi', 'tta_penalty_bwd_multi', 'tta_unfold_add_batched',
+           'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
+           'tta_jacobi_scratch_bytes', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched']
+
+
+class TtaError(RuntimeError):
+    pass
+
+
+_LIB = None
+_FAKE = None
+_CHECKED_DEVICES = set()
+
+
+def set_backend_for_tests(fake):
+    """tests/ only: route the C-ABI calls to an emulator operating on host memory."""
+    global _FAKE
+    _FAKE = fake
+
+
+def backend_is_emulated():
+    return _FAKE is not None
+
+
+def _load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.isfile(LIB_PATH):
+        raise TtaError('libtta.so not found at {} -- build it with `python -c "import __graft_entry__ as g; '
+                       'g.build()"` (nvcc, sm_100a). There is no CPU fallback.'.format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+    lib.tta_last_error.restype = ctypes.c_char_p
+    lib.tta_last_error.argtypes = []
+    lib.tta_version.restype = ci
+    lib.tta_check_device.argtypes = [ci]
+    lib.tta_dual_update_multi.argtypes = [vp, vp, ci, vp, vp]
+    lib.tta_penalty_fwd_multi.argtypes = [vp, vp, ci, cf, vp, vp]
+    lib.tta_penalty_bwd_multi.argtypes = [vp, vp, ci, cf, vp, ci, vp]
+    lib.tta_unfold_add_batched.argtypes = [vp, vp, ci, vp]
+    lib.tta_fold_store_batched.argtypes = [vp, vp, ci, vp]
+    lib.tta_gram_batched.argtypes = [vp, vp, ci, vp]
+    lib.tta_jacobi_eigh_batched.argtypes = [vp, vp, ci, cf, ci, vp, cs, vp, vp]
+    lib.tta_jacobi_scratch_bytes.argtypes = [vp, ci]
+    lib.tta_jacobi_scratch_bytes.restype = cs
+    lib.tta_select_batched.argtypes = [vp, vp, ci, vp]
+    lib.tta_gemm_batched.argtypes = [vp, vp, ci, vp]
+    lib.tta_sqnorm_batched.argtypes = [vp, vp, ci, vp, vp]
+    for name in EXPORTS:
+        if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes'):
+            getattr(lib, name).restype = ci
+    _LIB = lib
+    return lib
+
+
+def lib():
+    return _FAKE if _FAKE is not None else _load()
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().tta_last_error()
+        if isinstance(msg, bytes):
+            msg = msg.decode()
+        raise TtaError('{} failed (rc={}): {}'.format(what, rc, msg))
+
+
+def require_device(t):
+    """Fail loudly unless `t` lives on an sm_100 GPU (or the tests' emulator is active)."""
+    if _FAKE is not None:
+        return
+    if not t.is_cuda:
+        raise TtaError('tensor on {}: this implementation runs on B200 (sm_100a) only; there is no CPU path'
+                       .format(t.device))
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _CHECKED_DEVICES:
+        _check(lib().tta_check_device(idx), 'tta_check_device')
+        _CHECKED_DEVICES.add(idx)
+
+
+def stream_handle():
+    if _FAKE is not None:
+        return None
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class TaskTable:
+    """A task table: numpy structured array (host copy) + its device mirror."""
+
+    def __init__(self, host, device):
+        self.host = np.ascontiguousarray(host)
+        self.n = int(self.host.shape[0])
+        if self.n == 0:
+            self.dev = None
+        elif _FAKE is not None:
+            self.dev = None  # emulator reads the host copy
+        else:
+            self.dev = torch.from_numpy(self.host.view(np.uint8).reshape(-1).copy()).to(device)
+
+    @property
+    def host_ptr(self):
+        return ctypes.c_void_p(self.host.ctypes.data) if self.n else None
+
+    @property
+    def dev_ptr(self):
+        if self.n == 0:
+            return None
+        if _FAKE is not None:
+            return ctypes.c_void_p(self.host.ctypes.data)
+        return ctypes.c_void_p(self.dev.data_ptr())
+
+
+# ---- thin call wrappers -------------------------------------------------------------------------
+def dual_update(tab, sqnorm_out=None):
+    p = ctypes.c_void_p(sqnorm_out.data_ptr()) if sqnorm_out is not None else None
+    _check(lib().tta_dual_update_multi(tab.dev_ptr, tab.host_ptr, tab.n, p, stream_handle()), 'tta_dual_update_multi')
+
+
+def penalty_fwd(tab, rho, loss_out):
+    _check(lib().tta_penalty_fwd_multi(tab.dev_ptr, tab.host_ptr, tab.n, float(rho),
+                                       ctypes.c_void_p(loss_out.data_ptr()), stream_handle()),
+           'tta_penalty_fwd_multi')
+
+
+def penalty_bwd(tab, rho, grad_scale, accumulate):
+    p = ctypes.c_void_p(grad_scale.data_ptr()) if grad_scale is not None else None
+    _check(lib().tta_penalty_bwd_multi(tab.dev_ptr, tab.host_ptr, tab.n, float(rho), p, int(bool(accumulate)),
+                                       stream_handle()), 'tta_penalty_bwd_multi')
+
+
+def unfold_add(tab):
+    _check(lib().tta_unfold_add_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_unfold_add_batched')
+
+
+def fold_store(tab):
+    _check(lib().tta_fold_store_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_fold_store_batched')
+
+
+def gram(tab):
+    _check(lib().tta_gram_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_gram_batched')
+
+
+def jacobi_scratch_bytes(tab):
+    return int(lib().tta_jacobi_scratch_bytes(tab.host_ptr, tab.n))
+
+
+def jacobi_eigh(tab, scratch, tol=5e-7, max_sweeps=40):
+    sweeps = np.zeros(max(tab.n, 1), dtype=np.int32)
+    _check(lib().tta_jacobi_eigh_batched(tab.dev_ptr, tab.host_ptr, tab.n, float(tol), int(max_sweeps),
+                                         ctypes.c_void_p(scratch.data_ptr()),
+                                         scratch.numel() * scratch.element_size(),
+                                         ctypes.c_void_p(sweeps.ctypes.data), stream_handle()),
+           'tta_jacobi_eigh_batched')
+    return sweeps[:tab.n]
+
+
+def select(tab):
+    _check(lib().tta_select_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_select_batched')
+
+
+def gemm(tab):
+    _check(lib().tta_gemm_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_gemm_batched')
+
+
+def sqnorm(tab, out):
+    _check(lib().tta_sqnorm_batched(tab.dev_ptr, tab.host_ptr, tab.n, ctypes.c_void_p(out.data_ptr()),
+                                    stream_handle()), 'tta_sqnorm_batched')

@@ -1,0 +1,178 @@
+/*
+ * tta.h -- C ABI of libtta.so: B200 (sm_100a) kernels for the ADMM low-rank projection hot path of
+ * miaoyin390/DNN-Compression-Tensor-ADMM.
+ *
+ * The reference has no FFI of its own (pure Python: numpy/LAPACK/tensorly/torch library calls); the
+ * boundary a maintainer binds is the set of batched operators below.  Each entry cites the reference
+ * call site(s) it replaces (file:line relative to the reference repo).
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller; the library never allocates device
+ *     memory and keeps no global state except `tta_last_error()`'s thread-local string;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; calls only enqueue work unless stated otherwise;
+ *   - "task tables" are arrays of the plain structs below living in DEVICE memory (one kernel launch
+ *     serves a whole table: all layers of a network step are batched);
+ *   - return value: 0 on success, negative `TTA_E_*` on failure (`tta_last_error()` has the text);
+ *   - matrices are row-major unless a stride says otherwise; all floating data is fp32, Gram
+ *     accumulation is fp64.
+ */
+#ifndef TTA_H_
+#define TTA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTA_OK 0
+#define TTA_E_INVALID (-1)   /* bad argument                                   */
+#define TTA_E_CUDA (-2)      /* CUDA runtime error (text in tta_last_error)    */
+#define TTA_E_NOCONV (-3)    /* eigensolver hit max_sweeps without converging  */
+#define TTA_E_ARCH (-4)      /* device is not sm_100                           */
+
+const char* tta_last_error(void);
+int tta_version(void);
+/* 0 if device `dev` can run this library (compute capability 10.x), else TTA_E_ARCH. */
+int tta_check_device(int dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dual update and penalty (fused multi-tensor elementwise)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w; /* parameter                                  */
+  const float* z; /* projected copy                             */
+  float* u;       /* scaled dual (read; written by dual_update) */
+  float* g;       /* gradient buffer (penalty_bwd only)         */
+  int64_t numel;
+} tta_ew_task;
+
+/* admm.py:71-78   U += W - Z for every listed layer; if `sqnorm_out` != NULL also
+ * sqnorm_out[t] = ||W_t - Z_t||^2 (fp64; the value admm.py:76,78 logs is its square root).
+ * `sqnorm_out` must be zeroed by the caller.  One launch for all tensors. */
+int tta_dual_update_multi(const tta_ew_task* tasks_dev, const tta_ew_task* tasks_host, int n_tasks,
+                          double* sqnorm_out, void* stream);
+
+/* admm.py:80-85   loss_out[0] += sum_t 0.5*rho*||W_t - Z_t + U_t||^2   (fp64 accumulator, caller
+ * zeroes it). */
+int tta_penalty_fwd_multi(const tta_ew_task* tasks_dev, const tta_ew_task* tasks_host, int n_tasks,
+                          float rho, double* loss_out, void* stream);
+
+/* autograd of admm.py:83:  g_t (+)= grad_scale[0] * rho * (W_t - Z_t + U_t).
+ * `grad_scale` is a device scalar (the incoming grad_output -- GradScaler scales the loss,
+ * engines.py:315).  accumulate != 0 adds into g (existing .grad), else overwrites. */
+int tta_penalty_bwd_multi(const tta_ew_task* tasks_dev, const tta_ew_task* tasks_host, int n_tasks,
+                          float rho, const float* grad_scale, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Unfold / fold (admm.py:45 + admm.py:96 and admm.py:99)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w; /* (O, I, KK) contiguous                                         */
+  const float* u; /* same shape, may be NULL                                       */
+  float* t;       /* unfold: out (O, KK, I);  fold: in                             */
+  float* z;       /* fold: out (O, I, KK); unfold: unused                          */
+  int32_t O, I, KK; /* KK == 1 (linear / 1x1) degenerates to a plain add / copy    */
+  int32_t pad_;
+} tta_fold_task;
+
+/* t[o,kk,i] = w[o,i,kk] + u[o,i,kk]   (V = W + U of admm.py:45 fused with the permute of :96) */
+int tta_unfold_add_batched(const tta_fold_task* tasks_dev, const tta_fold_task* tasks_host,
+                           int n_tasks, void* stream);
+/* z[o,i,kk] = t[o,kk,i]               (admm.py:99) */
+int tta_fold_store_batched(const tta_fold_task* tasks_dev, const tta_fold_task* tasks_host,
+                           int n_tasks, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gram matrices  G = sum_{b,c} a(i,b,c) a(j,b,c)   (replaces the SVD input side of ttd.py:16-17 and
+ * tensorly's unfold+svd in admm.py:116,124)
+ *   element a(i,b,c) lives at  a + i*si + b*sb + c*sc ;  i < k, b < nb, c < nc
+ *   row Gram  A A^T of a row-major m x n matrix:  k=m, si=n, nb=1, nc=n, sc=1
+ *   col Gram  A^T A:                              k=n, si=1, nb=1, nc=m, sc=n
+ *   mode Gram of a (B, k, c) tensor:              si=c, sb=k*c, nc=c, sc=1, nb=B
+ * Output: x (fp32) holds G as `kpad` columns of length `ld` (column j at x + j*ld), zero padded --
+ * the eigensolver's in-place state.  `part` is fp64 scratch of nsplit*k*k doubles.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* a;
+  double* part;
+  float* x;
+  int64_t si, sb, sc;
+  int32_t k, nb, nc, nsplit;
+  int32_t ld, kpad;
+} tta_gram_task;
+
+int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_task* tasks_host, int n_tasks,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Symmetric eigensolver: one-sided (Hestenes) block Jacobi on the columns of X = G
+ * (replaces numpy.linalg.svd / LAPACK gesdd of ttd.py:17, admm.py:131,143 and tensorly partial_svd)
+ * On return the columns of X are mutually orthogonal: x_j = lambda_j * v_j.
+ * Synchronises `stream` once per sweep (convergence test on the host).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* x;         /* kpad columns of length ld                       */
+  int32_t k;        /* true order                                      */
+  int32_t ld;       /* column length, multiple of 4, >= k              */
+  int32_t kpad;     /* column count, multiple of bw                    */
+  int32_t bw;       /* column block width (8 or 16)                    */
+} tta_eig_task;
+
+/* sweeps_out (host, nullable): number of sweeps each problem needed. */
+int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* tasks_host,
+                            int n_tasks, float tol, int max_sweeps, int32_t* scratch_dev,
+                            size_t scratch_bytes, int32_t* sweeps_out, void* stream);
+size_t tta_jacobi_scratch_bytes(const tta_eig_task* tasks_host, int n_tasks);
+
+/* ---------------------------------------------------------------------------------------------
+ * Select the r dominant eigenpairs of a converged X (truncation of ttd.py:21-23, admm.py:132-134)
+ *   e      (r x k) row-major: row p = p-th dominant unit eigenvector (zero row when lambda ~ 0)
+ *   et     (k x r) row-major: transpose of e            (nullable)
+ *   se     (r x k) row-major: sqrt(lambda_p) * e row p  (nullable; = diag(s) V^T of ttd.py:26)
+ *   sigma  (r)     sqrt(lambda_p)                        (nullable)
+ *   isigma (r)     1/sqrt(lambda_p), 0 when lambda ~ 0   (nullable)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x;
+  float* e;
+  float* et;
+  float* se;
+  float* sigma;
+  float* isigma;
+  int32_t k, ld, r, pad_;
+} tta_select_task;
+
+int tta_select_batched(const tta_select_task* tasks_dev, const tta_select_task* tasks_host,
+                       int n_tasks, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched fp32 GEMM  C[M,N] = (A[M,K] * B[K,N]) .* colscale[N]
+ *   A(i,k) at a + i*sai + k*sak ; B(k,j) at b + k*sbk + j*sbj ; C row-major, leading dim ldc.
+ * (replaces np.dot of ttd.py:26,39-40, the projection side of the SVDs, tensorly mode products)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* a;
+  const float* b;
+  float* c;
+  const float* colscale; /* nullable */
+  int64_t sai, sak, sbk, sbj, ldc;
+  int32_t M, N, K, pad_;
+} tta_gemm_task;
+
+int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
+                     void* stream);
+
+/* out[t] = sum of squares of n floats (fp64): tensorly `tl.norm(core, 2)**2` in the HOOI stopping rule. */
+typedef struct {
+  const float* x;
+  int64_t n;
+} tta_sqnorm_task;
+int tta_sqnorm_batched(const tta_sqnorm_task* tasks_dev, const tta_sqnorm_task* tasks_host,
+                       int n_tasks, double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTA_H_ */

@@ -1,0 +1,193 @@
+"""numpy emulator of the libtta C ABI over HOST memory (test infrastructure only).
+
+It lets `-m "not gpu"` tests drive the real host-side planning code (`projector.py`, `admm.py`, ...)
+end to end on a box without a GPU: the plans bake raw addresses of torch CPU tensors into the same
+task tables they would hand to the CUDA kernels, and this module interprets those tables exactly as
+include/tta.h specifies.  It is never importable from the product package.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+import tta_runtime as rt
+
+
+def _view(ptr, count, dtype=np.float32):
+    ptr = int(ptr)
+    if count == 0:
+        return np.zeros(0, dtype=dtype)
+    nbytes = int(count) * np.dtype(dtype).itemsize
+    return np.frombuffer((ctypes.c_char * nbytes).from_address(ptr), dtype=dtype)
+
+
+def _val(p):
+    if p is None:
+        return 0
+    if isinstance(p, ctypes.c_void_p):
+        return p.value or 0
+    return int(p)
+
+
+def _table(ptr, n, dtype):
+    return _view(_val(ptr), n * dtype.itemsize, np.uint8).view(dtype)
+
+
+class FakeTTA:
+    def __init__(self, scramble=True):
+        self.err = b''
+        self.calls = []
+        self.scramble = scramble
+
+    def tta_last_error(self):
+        return self.err
+
+    def tta_version(self):
+        return 100
+
+    def tta_check_device(self, dev):
+        return 0
+
+    # ---- elementwise ----
+    def tta_dual_update_multi(self, tdev, thost, n, sq, stream):
+        self.calls.append('dual_update')
+        out = _view(_val(sq), n, np.float64) if _val(sq) else None
+        for i, tk in enumerate(_table(thost, n, rt.EW_TASK)):
+            m = int(tk['numel'])
+            w, z, u = _view(tk['w'], m), _view(tk['z'], m), _view(tk['u'], m)
+            d = w - z
+            u += d
+            if out is not None:
+                out[i] += float(np.sum(d.astype(np.float64) ** 2))
+        return 0
+
+    def tta_penalty_fwd_multi(self, tdev, thost, n, rho, loss, stream):
+        self.calls.append('penalty_fwd')
+        out = _view(_val(loss), 1, np.float64)
+        for tk in _table(thost, n, rt.EW_TASK):
+            m = int(tk['numel'])
+            d = _view(tk['w'], m) - _view(tk['z'], m) + _view(tk['u'], m)
+            out[0] += 0.5 * float(np.float32(rho)) * float(np.sum(d.astype(np.float64) ** 2))
+        return 0
+
+    def tta_penalty_bwd_multi(self, tdev, thost, n, rho, gscale, accumulate, stream):
+        self.calls.append('penalty_bwd')
+        s = float(_view(_val(gscale), 1)[0]) if _val(gscale) else 1.0
+        coef = np.float32(np.float32(rho) * np.float32(s))
+        for tk in _table(thost, n, rt.EW_TASK):
+            m = int(tk['numel'])
+            d = coef * (_view(tk['w'], m) - _view(tk['z'], m) + _view(tk['u'], m))
+            g = _view(tk['g'], m)
+            if accumulate:
+                g += d
+            else:
+                g[:] = d
+        return 0
+
+    # ---- fold / unfold ----
+    def tta_unfold_add_batched(self, tdev, thost, n, stream):
+        self.calls.append('unfold')
+        for tk in _table(thost, n, rt.FOLD_TASK):
+            O, I, KK = int(tk['O']), int(tk['I']), int(tk['KK'])
+            v = _view(tk['w'], O * I * KK).reshape(O, I, KK).copy()
+            if tk['u']:
+                v += _view(tk['u'], O * I * KK).reshape(O, I, KK)
+            _view(tk['t'], O * I * KK).reshape(O, KK, I)[:] = v.transpose(0, 2, 1)
+        return 0
+
+    def tta_fold_store_batched(self, tdev, thost, n, stream):
+        self.calls.append('fold')
+        for tk in _table(thost, n, rt.FOLD_TASK):
+            O, I, KK = int(tk['O']), int(tk['I']), int(tk['KK'])
+            t = _view(tk['t'], O * I * KK).reshape(O, KK, I)
+            _view(tk['z'], O * I * KK).reshape(O, I, KK)[:] = t.transpose(0, 2, 1)
+        return 0
+
+    # ---- gram ----
+    def tta_gram_batched(self, tdev, thost, n, stream):
+        self.calls.append('gram')
+        for tk in _table(thost, n, rt.GRAM_TASK):
+            k, nb, nc = int(tk['k']), int(tk['nb']), int(tk['nc'])
+            si, sb, sc = int(tk['si']), int(tk['sb']), int(tk['sc'])
+            span = (k - 1) * si + (nb - 1) * sb + (nc - 1) * sc + 1
+            base = _view(tk['a'], span)
+            a = np.lib.stride_tricks.as_strided(base, shape=(k, nb, nc), strides=(4 * si, 4 * sb, 4 * sc))
+            a = a.reshape(k, nb * nc).astype(np.float64)
+            g = a @ a.T
+            ld, kpad = int(tk['ld']), int(tk['kpad'])
+            x = _view(tk['x'], ld * kpad).reshape(kpad, ld)
+            x[:] = 0
+            x[:k, :k] = g.T.astype(np.float32)
+        return 0
+
+    # ---- eigensolver: exact fp64 eigh, stored as x_j = lambda_j v_j in scrambled column order ----
+    def tta_jacobi_scratch_bytes(self, thost, n):
+        return 4096
+
+    def tta_jacobi_eigh_batched(self, tdev, thost, n, tol, max_sweeps, scratch, scratch_bytes, sweeps_out, stream):
+        self.calls.append('jacobi')
+        sw = _view(_val(sweeps_out), n, np.int32) if _val(sweeps_out) else None
+        rng = np.random.RandomState(1234)
+        for i, tk in enumerate(_table(thost, n, rt.EIG_TASK)):
+            k, ld, kpad = int(tk['k']), int(tk['ld']), int(tk['kpad'])
+            x = _view(tk['x'], ld * kpad).reshape(kpad, ld)
+            g = x[:k, :k].T.astype(np.float64)
+            g = 0.5 * (g + g.T)
+            lam, v = np.linalg.eigh(g)
+            lam = np.maximum(lam, 0.0)
+            order = rng.permutation(k) if self.scramble else np.arange(k)
+            x[:k, :k] = (v[:, order] * lam[order]).T.astype(np.float32)
+            if sw is not None:
+                sw[i] = 7
+        return 0
+
+    def tta_select_batched(self, tdev, thost, n, stream):
+        self.calls.append('select')
+        for tk in _table(thost, n, rt.SELECT_TASK):
+            k, ld, r = int(tk['k']), int(tk['ld']), int(tk['r'])
+            kpad_rows = k  # only the first k columns are read
+            x = _view(tk['x'], ld * kpad_rows).reshape(kpad_rows, ld)[:, :k]
+            lam = np.sqrt(np.sum(x.astype(np.float32) ** 2, axis=1, dtype=np.float32))
+            order = np.argsort(-lam, kind='stable')[:r]
+            lmax = lam.max() if k else 0.0
+            e = np.zeros((r, k), dtype=np.float32)
+            sg = np.zeros(r, dtype=np.float32)
+            for p, j in enumerate(order):
+                if lam[j] > lmax * 4e-7 and lam[j] > 0:
+                    e[p] = x[j] / lam[j]
+                    sg[p] = np.sqrt(lam[j])
+            _view(tk['e'], r * k).reshape(r, k)[:] = e
+            if tk['et']:
+                _view(tk['et'], r * k).reshape(k, r)[:] = e.T
+            if tk['se']:
+                _view(tk['se'], r * k).reshape(r, k)[:] = e * sg[:, None]
+            if tk['sigma']:
+                _view(tk['sigma'], r)[:] = sg
+            if tk['isigma']:
+                _view(tk['isigma'], r)[:] = np.where(sg > 0, 1.0 / np.where(sg > 0, sg, 1), 0).astype(np.float32)
+        return 0
+
+    # ---- gemm ----
+    def tta_gemm_batched(self, tdev, thost, n, stream):
+        self.calls.append('gemm')
+        for tk in _table(thost, n, rt.GEMM_TASK):
+            M, N, K = int(tk['M']), int(tk['N']), int(tk['K'])
+            sai, sak, sbk, sbj, ldc = (int(tk[f]) for f in ('sai', 'sak', 'sbk', 'sbj', 'ldc'))
+            abase = _view(tk['a'], (M - 1) * sai + (K - 1) * sak + 1)
+            bbase = _view(tk['b'], (K - 1) * sbk + (N - 1) * sbj + 1)
+            a = np.lib.stride_tricks.as_strided(abase, shape=(M, K), strides=(4 * sai, 4 * sak))
+            b = np.lib.stride_tricks.as_strided(bbase, shape=(K, N), strides=(4 * sbk, 4 * sbj))
+            c = (a @ b).astype(np.float32)
+            if tk['colscale']:
+                c = c * _view(tk['colscale'], N)[None, :]
+            cbase = _view(tk['c'], (M - 1) * ldc + N)
+            np.lib.stride_tricks.as_strided(cbase, shape=(M, N), strides=(4 * ldc, 4))[:] = c
+        return 0
+
+    def tta_sqnorm_batched(self, tdev, thost, n, out, stream):
+        self.calls.append('sqnorm')
+        o = _view(_val(out), n, np.float64)
+        for i, tk in enumerate(_table(thost, n, rt.SQNORM_TASK)):
+            o[i] += float(np.sum(_view(tk['x'], int(tk['n'])).astype(np.float64) ** 2))
+        return 0

@@ -1,0 +1,251 @@
+"""Kernel-level parity through the C ABI on a B200: each batched operator of include/tta.h against
+numpy on the same seeded inputs (bit-exact where the arithmetic is order-free, tolerance stated)."""
+import numpy as np
+import pytest
+import torch
+
+import tta_runtime as rt
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _ew_table(ws, zs, us, gs=None):
+    arr = np.zeros(len(ws), dtype=rt.EW_TASK)
+    for i in range(len(ws)):
+        arr[i] = (ws[i].data_ptr(), zs[i].data_ptr(), us[i].data_ptr(), gs[i].data_ptr() if gs else 0, ws[i].numel())
+    return rt.TaskTable(arr, DEV)
+
+
+@pytest.mark.parametrize('offset', [0, 1])
+def test_dual_update_bit_exact_ragged(offset):
+    rng = np.random.RandomState(0)
+    sizes = [1, 7, 4095, 4096, 4097, 36864, 1000003]
+    W = [rng.randn(n + offset).astype(np.float32) for n in sizes]
+    Z = [rng.randn(n + offset).astype(np.float32) for n in sizes]
+    U = [rng.randn(n + offset).astype(np.float32) for n in sizes]
+    w = [_t(a)[offset:] for a in W]
+    z = [_t(a)[offset:] for a in Z]
+    u = [_t(a)[offset:] for a in U]
+    sq = torch.zeros(len(sizes), dtype=torch.float64, device=DEV)
+    rt.dual_update(_ew_table(w, z, u), sq)
+    torch.cuda.synchronize()
+    for i in range(len(sizes)):
+        d = W[i][offset:] - Z[i][offset:]
+        assert np.array_equal(u[i].cpu().numpy(), U[i][offset:] + d)          # bit-exact (integer/byte bar)
+        ref = float(np.sum(d.astype(np.float64) ** 2))
+        assert abs(float(sq[i]) - ref) <= 1e-6 * ref + 1e-30                   # fp32 partials, fp64 tree
+
+
+def test_penalty_forward_backward():
+    rng = np.random.RandomState(1)
+    sizes = [5, 4096 * 3, 123457]
+    W, Z, U = ([rng.randn(n).astype(np.float32) for n in sizes] for _ in range(3))
+    w, z, u = [_t(a) for a in W], [_t(a) for a in Z], [_t(a) for a in U]
+    rho = 1e-3
+    loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    rt.penalty_fwd(_ew_table(w, z, u), rho, loss)
+    ref = sum(0.5 * float(np.float32(rho)) * float(np.sum((a - b + c).astype(np.float64) ** 2)) for a, b, c in zip(W, Z, U))
+    assert abs(float(loss) - ref) <= 1e-6 * ref                                 # tolerance: 1e-6 relative
+    g = [torch.full_like(a, 2.0) for a in w]
+    scale = torch.tensor([3.0], device=DEV)
+    rt.penalty_bwd(_ew_table(w, z, u, g), rho, scale, accumulate=False)
+    coef = np.float32(np.float32(rho) * np.float32(3.0))
+    for i in range(len(sizes)):
+        assert np.array_equal(g[i].cpu().numpy(), coef * (W[i] - Z[i] + U[i]))  # overwrite: bit-exact
+    rt.penalty_bwd(_ew_table(w, z, u, g), rho, scale, accumulate=True)
+    for i in range(len(sizes)):
+        ref_g = 2.0 * coef * (W[i] - Z[i] + U[i])
+        assert np.allclose(g[i].cpu().numpy(), ref_g, rtol=1e-6, atol=1e-9)    # FMA contraction allowed
+
+
+@pytest.mark.parametrize('O,I,KK', [(16, 16, 9), (64, 37, 9), (8, 600, 9), (12, 20, 1), (5, 33, 4), (3, 7, 25)])
+def test_unfold_fold_exact(O, I, KK):
+    rng = np.random.RandomState(2)
+    W = rng.randn(O, I, KK).astype(np.float32)
+    U = rng.randn(O, I, KK).astype(np.float32)
+    w, u = _t(W), _t(U)
+    t = torch.empty(O * KK * I, device=DEV)
+    z = torch.empty(O * I * KK, device=DEV)
+    tab = np.zeros(1, dtype=rt.FOLD_TASK)
+    tab[0] = (w.data_ptr(), u.data_ptr(), t.data_ptr(), z.data_ptr(), O, I, KK, 0)
+    table = rt.TaskTable(tab, DEV)
+    rt.unfold_add(table)
+    assert np.array_equal(t.cpu().numpy().reshape(O, KK, I), (W + U).transpose(0, 2, 1))
+    rt.fold_store(table)
+    assert np.array_equal(z.cpu().numpy().reshape(O, I, KK), W + U)
+
+
+def _gram_task(a, x, part, k, si, sb, sc, nb, nc, nsplit, ld, kpad):
+    tab = np.zeros(1, dtype=rt.GRAM_TASK)
+    tab[0] = (a.data_ptr(), part.data_ptr(), x.data_ptr(), si, sb, sc, k, nb, nc, nsplit, ld, kpad)
+    return rt.TaskTable(tab, DEV)
+
+
+@pytest.mark.parametrize('m,n,nsplit', [(8, 4608, 9), (64, 576, 2), (75, 512, 1), (130, 512, 3), (480, 1000, 2)])
+def test_gram_row_and_col(m, n, nsplit):
+    rng = np.random.RandomState(3)
+    A = rng.randn(m, n).astype(np.float32)
+    a = _t(A)
+    for mode in ('row', 'col'):
+        k = m if mode == 'row' else n
+        if k > 600:
+            continue
+        ld, kpad = (k + 3) // 4 * 4, (k + 15) // 16 * 16
+        x = torch.full((kpad * ld,), 7.0, device=DEV)
+        part = torch.empty(nsplit * k * k, dtype=torch.float64, device=DEV)
+        if mode == 'row':
+            tab = _gram_task(a, x, part, k, n, 0, 1, 1, n, nsplit, ld, kpad)
+            G = A.astype(np.float64) @ A.astype(np.float64).T
+        else:
+            tab = _gram_task(a, x, part, k, 1, 0, n, 1, m, nsplit, ld, kpad)
+            G = A.astype(np.float64).T @ A.astype(np.float64)
+        rt.gram(tab)
+        X = x.cpu().numpy().reshape(kpad, ld)
+        assert np.allclose(X[:k, :k], G.astype(np.float32).T, rtol=2e-7, atol=1e-12 * np.abs(G).max())  # fp64 accumulation
+        assert not X[k:].any() and not X[:, k:].any()                 # zero padding
+
+
+def test_gram_mode_layout():
+    """Tucker mode Gram: tensor (B, k, c), G = sum_b M_b M_b^T."""
+    rng = np.random.RandomState(4)
+    B, k, c = 11, 40, 9
+    Y = rng.randn(B, k, c).astype(np.float32)
+    y = _t(Y)
+    ld, kpad = 40, 48
+    x = torch.empty(kpad * ld, device=DEV)
+    part = torch.empty(2 * k * k, dtype=torch.float64, device=DEV)
+    rt.gram(_gram_task(y, x, part, k, c, k * c, 1, B, c, 2, ld, kpad))
+    G = np.einsum('bic,bjc->ij', Y.astype(np.float64), Y.astype(np.float64))
+    assert np.allclose(x.cpu().numpy().reshape(kpad, ld)[:k, :k], G.astype(np.float32).T, rtol=2e-7, atol=1e-12 * np.abs(G).max())
+
+
+def _eig_problem(k, rng, spectrum='flat'):
+    n = 3 * k
+    A = rng.randn(k, n).astype(np.float64)
+    if spectrum == 'decay':
+        A = A * np.logspace(0, -2, k)[:, None]
+    G = (A @ A.T).astype(np.float32)
+    return G
+
+
+@pytest.mark.parametrize('ks', [[8], [64, 75, 16], [130, 240], [512], [256, 32, 480]])
+def test_jacobi_eigh_and_select(ks):
+    rng = np.random.RandomState(5)
+    Gs = [_eig_problem(k, rng, 'decay' if i % 2 else 'flat') for i, k in enumerate(ks)]
+    etab = np.zeros(len(ks), dtype=rt.EIG_TASK)
+    stab = np.zeros(len(ks), dtype=rt.SELECT_TASK)
+    bufs = []
+    for i, (k, G) in enumerate(zip(ks, Gs)):
+        ld, kpad, bw = (k + 3) // 4 * 4, (k + 15) // 16 * 16, 16
+        X = np.zeros((kpad, ld), dtype=np.float32)
+        X[:k, :k] = G.T
+        x = _t(X.reshape(-1))
+        r = max(1, k // 3)
+        e = torch.empty(r * k, device=DEV)
+        et = torch.empty(k * r, device=DEV)
+        se = torch.empty(r * k, device=DEV)
+        sg = torch.empty(r, device=DEV)
+        isg = torch.empty(r, device=DEV)
+        etab[i] = (x.data_ptr(), k, ld, kpad, bw)
+        stab[i] = (x.data_ptr(), e.data_ptr(), et.data_ptr(), se.data_ptr(), sg.data_ptr(), isg.data_ptr(), k, ld, r, 0)
+        bufs.append((x, e, et, se, sg, isg, r, ld, kpad))
+    et_tab = rt.TaskTable(etab, DEV)
+    scratch = torch.empty(rt.jacobi_scratch_bytes(et_tab) // 4 + 16, dtype=torch.int32, device=DEV)
+    sweeps = rt.jacobi_eigh(et_tab, scratch, tol=5e-7, max_sweeps=40)
+    rt.select(rt.TaskTable(stab, DEV))
+    torch.cuda.synchronize()
+    for i, (k, G) in enumerate(zip(ks, Gs)):
+        x, e, et, se, sg, isg, r, ld, kpad = bufs[i]
+        assert 1 <= sweeps[i] <= 20, sweeps
+        X = x.cpu().numpy().reshape(kpad, ld)[:k, :k].astype(np.float64)   # rows = columns x_j
+        lam = np.linalg.norm(X, axis=1)
+        ref = np.linalg.eigvalsh(G.astype(np.float64))[::-1]
+        assert np.max(np.abs(np.sort(lam)[::-1] - ref)) <= 2e-5 * ref[0]    # eigenvalues: 2e-5 * lambda_max
+        E = e.cpu().numpy().reshape(r, k).astype(np.float64)
+        assert np.max(np.abs(E @ E.T - np.eye(r))) <= 2e-5                   # orthonormal rows
+        # invariant-subspace residual ||G E^T - E^T (E G E^T)|| relative to lambda_max
+        Gd = G.astype(np.float64)
+        res = Gd @ E.T - E.T @ (E @ Gd @ E.T)
+        assert np.linalg.norm(res, 2) <= 5e-5 * ref[0]
+        assert np.array_equal(et.cpu().numpy().reshape(k, r), e.cpu().numpy().reshape(r, k).T)
+        s = sg.cpu().numpy()
+        assert np.allclose(s ** 2, ref[:r], rtol=1e-4, atol=1e-5 * ref[0])
+        assert np.allclose(se.cpu().numpy().reshape(r, k), e.cpu().numpy().reshape(r, k) * s[:, None], rtol=1e-6, atol=0)
+        assert np.allclose(isg.cpu().numpy() * s, 1.0, rtol=1e-5)
+
+
+def test_jacobi_rank_deficient_and_zero():
+    rng = np.random.RandomState(6)
+    k, rank = 96, 20
+    B = rng.randn(k, rank)
+    G = (B @ B.T).astype(np.float32)
+    Z = np.zeros((32, 32), dtype=np.float32)
+    etab = np.zeros(2, dtype=rt.EIG_TASK)
+    xs = []
+    for i, M in enumerate((G, Z)):
+        kk = M.shape[0]
+        X = np.zeros((kk, kk), dtype=np.float32)
+        X[:] = M.T
+        x = _t(X.reshape(-1))
+        xs.append(x)
+        etab[i] = (x.data_ptr(), kk, kk, kk, 16)
+    tab = rt.TaskTable(etab, DEV)
+    scratch = torch.empty(rt.jacobi_scratch_bytes(tab) // 4 + 16, dtype=torch.int32, device=DEV)
+    sweeps = rt.jacobi_eigh(tab, scratch, tol=5e-7, max_sweeps=40)
+    assert sweeps[0] <= 25 and sweeps[1] == 1
+    r = 30
+    e = torch.empty(r * k, device=DEV)
+    stab = np.zeros(1, dtype=rt.SELECT_TASK)
+    stab[0] = (xs[0].data_ptr(), e.data_ptr(), 0, 0, 0, 0, k, k, r, 0)
+    rt.select(rt.TaskTable(stab, DEV))
+    E = e.cpu().numpy().reshape(r, k).astype(np.float64)
+    P = E.T @ E
+    Gd = G.astype(np.float64)
+    assert np.linalg.norm(P @ Gd - Gd) <= 1e-4 * np.linalg.norm(Gd)      # spans the range; extra rows are zero
+    assert np.count_nonzero(np.linalg.norm(E, axis=1) > 0.5) == rank
+
+
+@pytest.mark.parametrize('M,N,K', [(8, 4608, 8), (105, 513, 480), (300, 70, 15), (1, 1, 1), (64, 64, 64)])
+def test_gemm_strides(M, N, K):
+    rng = np.random.RandomState(7)
+    A = rng.randn(M, K).astype(np.float32)
+    B = rng.randn(K, N).astype(np.float32)
+    cs = rng.rand(N).astype(np.float32) + 0.5
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    tol = 2e-6 * np.sqrt(K) * np.abs(A).max() * np.abs(B).max() * 4
+    for ta in (False, True):
+        for tb in (False, True):
+            a = _t(A.T if ta else A)
+            b = _t(B.T if tb else B)
+            c = torch.zeros(M, N + 3, device=DEV)
+            s = _t(cs)
+            tab = np.zeros(2, dtype=rt.GEMM_TASK)
+            sai, sak = (1, M) if ta else (K, 1)
+            sbk, sbj = (1, K) if tb else (N, 1)
+            tab[0] = (a.data_ptr(), b.data_ptr(), c.data_ptr(), 0, sai, sak, sbk, sbj, N + 3, M, N, K, 0)
+            c2 = torch.zeros(M, N, device=DEV)
+            tab[1] = (a.data_ptr(), b.data_ptr(), c2.data_ptr(), s.data_ptr(), sai, sak, sbk, sbj, N, M, N, K, 0)
+            rt.gemm(rt.TaskTable(tab, DEV))
+            out = c.cpu().numpy()
+            assert np.max(np.abs(out[:, :N] - ref)) <= tol
+            assert not out[:, N:].any()
+            assert np.max(np.abs(c2.cpu().numpy() - ref * cs[None, :])) <= tol * 1.5
+
+
+def test_sqnorm():
+    rng = np.random.RandomState(8)
+    xs = [rng.randn(n).astype(np.float32) for n in (1, 1000, 300001)]
+    ts = [_t(x) for x in xs]
+    tab = np.zeros(len(xs), dtype=rt.SQNORM_TASK)
+    for i, t in enumerate(ts):
+        tab[i] = (t.data_ptr(), t.numel())
+    out = torch.zeros(len(xs), dtype=torch.float64, device=DEV)
+    rt.sqnorm(rt.TaskTable(tab, DEV), out)
+    for i, x in enumerate(xs):
+        ref = float(np.sum(x.astype(np.float64) ** 2))
+        assert abs(float(out[i]) - ref) <= 1e-12 * ref

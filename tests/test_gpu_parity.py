@@ -1,0 +1,136 @@
+"""End-to-end parity of the drop-in ADMM path on a B200 against the CPU oracle (same seeded weights)
+and against the golden records of the reference itself.  Bar (BASELINE.json north_star): projected
+Z within 1e-4 relative Frobenius error per layer, fp32."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hp_tables
+import workloads
+from helpers import GOLDEN, check_summary, rel_fro
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+Z_TOL = 1e-4      # north_star: relative Frobenius error of the reconstructed projection Z
+
+
+def _run_pair(key, names=None, updates=2):
+    from admm import ADMM
+    wb, hb, fmt = workloads.CONFIGS[key]
+    weights = wb()
+    if names:
+        weights = {n: weights[n] for n in names}
+    hp, hp_o = hb(), hb()
+    model = workloads.ParamBag(weights, device=DEV)
+    a = ADMM(model, 1e-3, hp, fmt, DEV, log=True)
+    o = port.OracleADMM({n: w.numpy() for n, w in weights.items()}, 1e-3, hp_o, fmt)
+    a.update(update_u=False)
+    o.update(update_u=False)
+    z0 = {n: a.z[n].cpu().numpy() for n in weights}
+    z0_ref = {n: o.z[n].copy() for n in weights}
+    for _ in range(updates):
+        a.update()
+        o.update()
+    torch.cuda.synchronize()
+    return a, o, z0, z0_ref, weights, hp, hp_o, model
+
+
+@pytest.mark.parametrize('key', ['resnet32_tt', 'resnet50_tt', 'deit_small_tt', 'resnet50_tt_special'])
+def test_tt_projection_parity(key, golden_summary):
+    a, o, z0, z0_ref, weights, hp, hp_o, model = _run_pair(key)
+    worst = 0.0
+    for n in weights:
+        e0 = rel_fro(z0[n], z0_ref[n])
+        e2 = rel_fro(a.z[n].cpu().numpy(), o.z[n])
+        worst = max(worst, e0, e2)
+        assert e0 <= Z_TOL and e2 <= Z_TOL, (n, e0, e2)
+        # dual: U_new - U_old = W - Z holds exactly in the kernel; vs oracle U differs only through Z
+        assert np.linalg.norm(a.u[n].cpu().numpy() - o.u[n]) <= 3 * Z_TOL * np.linalg.norm(o.z[n]), n
+        assert [int(v) for v in hp.ranks[n]] == [int(v) for v in hp_o.ranks[n]]
+    print('{}: worst rel Z error {:.3e}; jacobi sweeps max {}'.format(
+        key, worst, max(max(v) for v in a.sweeps.values())))
+    gold = golden_summary[key]
+    for n in weights:                                       # records of the UNMODIFIED reference
+        check_summary(z0[n], gold['layers'][n]['z0'])
+        check_summary(a.z[n].cpu().numpy(), gold['layers'][n]['z2'])
+    loss = a.append_admm_loss(torch.zeros((), device=DEV))
+    pen = gold['penalty_after_3_updates']
+    assert abs(float(loss.detach()) - pen) <= 2e-3 * abs(pen)
+    loss.backward()
+    for n, p in model.named_parameters():
+        ref = o.penalty_grad(n)
+        assert np.linalg.norm(p.grad.cpu().numpy() - ref) <= 3 * Z_TOL * 1e-3 * np.linalg.norm(o.w[n]), n
+
+
+def test_golden_arrays_of_reference():
+    from admm import ADMM
+    for key in ('resnet32_tt', 'resnet50_tt'):
+        arrays = np.load(os.path.join(GOLDEN, key + '_arrays.npz'))
+        names = sorted({k.split('|')[0] for k in arrays.files})
+        wb, hb, fmt = workloads.CONFIGS[key]
+        w_all = wb()
+        weights = {n: w_all[n] for n in names}
+        a = ADMM(workloads.ParamBag(weights, device=DEV), 1e-3, hb(), fmt, DEV)
+        a.update(update_u=False)
+        for n in names:
+            assert rel_fro(a.z[n].cpu().numpy(), arrays[n + '|z0']) <= Z_TOL, (key, n)
+        a.update()
+        a.update()
+        for n in names:
+            assert rel_fro(a.z[n].cpu().numpy(), arrays[n + '|z2']) <= Z_TOL, (key, n)
+            assert np.linalg.norm(a.u[n].cpu().numpy() - arrays[n + '|u2']) <= 3 * Z_TOL * np.linalg.norm(arrays[n + '|z2'])
+
+
+def test_properties_idempotence_fullrank_conservation():
+    from admm import ADMM
+    wb, hb, fmt = workloads.CONFIGS['resnet50_tt']
+    names = ['layer1.0.conv2.weight', 'layer2.1.conv2.weight', 'layer3.0.conv3.weight', 'layer4.0.conv1.weight']
+    w_all = wb()
+    weights = {n: w_all[n] for n in names}
+    model = workloads.ParamBag(weights, device=DEV)
+    a = ADMM(model, 1e-3, hb(), fmt, DEV)
+    a.update(update_u=False)
+    z1 = {n: a.z[n].clone() for n in names}
+    # full-rank ranks => Z == W  (layer1.0.conv2 has ranks [1,8,64,64,8,1])
+    assert rel_fro(z1[names[0]].cpu().numpy(), weights[names[0]].numpy()) <= 5e-6
+    # idempotence: projecting an already projected tensor returns it
+    model2 = workloads.ParamBag({n: z1[n].cpu() for n in names}, device=DEV)
+    b = ADMM(model2, 1e-3, hb(), fmt, DEV)
+    b.update(update_u=False)
+    for n in names:
+        assert rel_fro(b.z[n].cpu().numpy(), z1[n].cpu().numpy()) <= Z_TOL, n
+    # U-update conservation: U_new - U_old == W - Z bit-exactly
+    u_old = {n: a.u[n].clone() for n in names}
+    a.update()
+    for n, p in model.named_parameters():
+        assert torch.equal(a.u[n], u_old[n] + (p.data - a.z[n]))
+
+
+def test_ttd_dropin_on_gpu():
+    import ttd
+    with open(os.path.join(GOLDEN, 'ttd_kats.json')) as f:
+        cases = json.load(f)
+    arrays = np.load(os.path.join(GOLDEN, 'ttd_kats.npz'))
+    for ci, case in enumerate(cases):
+        x = arrays['case{}|x'.format(ci)]
+        ranks = list(case['ranks_in'])
+        cores = ttd.ten2tt(x, case['shape'], ranks)
+        assert ranks == case['ranks_out']                     # in-place clip (ttd.py:18-19)
+        assert [list(c.shape) for c in cores] == case['core_shapes']
+        rec = ttd.tt2ten(cores, x.shape)
+        assert rel_fro(rec, arrays['case{}|rec'.format(ci)]) <= Z_TOL
+
+
+def test_svd_format_parity():
+    from admm import ADMM
+    g = torch.Generator().manual_seed(3)
+    weights = {'fc.weight': torch.randn(200, 320, generator=g), 'pw.weight': torch.randn(96, 160, 1, 1, generator=g)}
+    hp = hp_tables.HpTable('svd', {'fc.weight': 40, 'pw.weight': [24]})
+    a = ADMM(workloads.ParamBag(weights, device=DEV), 1e-3, hp, 'svd', DEV)
+    a.update()
+    assert rel_fro(a.z['fc.weight'].cpu().numpy(), port.project_linear_svd(weights['fc.weight'].numpy(), 40)) <= Z_TOL
+    assert rel_fro(a.z['pw.weight'].cpu().numpy(), port.project_conv_svd(weights['pw.weight'].numpy(), [24])) <= Z_TOL
