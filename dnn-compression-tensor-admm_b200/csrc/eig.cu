@@ -90,14 +90,18 @@ __device__ __forceinline__ int jacobi_rotate_pair(float* __restrict__ x, float* 
   const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
   const float cs = 1.f / sqrtf(1.f + t * t);
   const float sn = cs * t;
+  // x' = x - sn*(y + tau*x), y' = y + sn*(x - tau*y) with tau = sn/(1+cs)  (== cs*x - sn*y, sn*x + cs*y).
+  // Late rotations have cs == 1.0f after rounding; applying the 1-cs part explicitly keeps every
+  // rotation norm-preserving to rounding error instead of inflating the columns by t^2/2 each time.
+  const float tau = sn / (1.f + cs);
   for (int e = lane * 4; e < ld; e += 128) {
     float4 xv = *reinterpret_cast<const float4*>(x + e);
     float4 yv = *reinterpret_cast<const float4*>(y + e);
     float4 xn, yn;
-    xn.x = cs * xv.x - sn * yv.x; yn.x = sn * xv.x + cs * yv.x;
-    xn.y = cs * xv.y - sn * yv.y; yn.y = sn * xv.y + cs * yv.y;
-    xn.z = cs * xv.z - sn * yv.z; yn.z = sn * xv.z + cs * yv.z;
-    xn.w = cs * xv.w - sn * yv.w; yn.w = sn * xv.w + cs * yv.w;
+    xn.x = fmaf(-sn, fmaf(tau, xv.x, yv.x), xv.x); yn.x = fmaf(sn, fmaf(-tau, yv.x, xv.x), yv.x);
+    xn.y = fmaf(-sn, fmaf(tau, xv.y, yv.y), xv.y); yn.y = fmaf(sn, fmaf(-tau, yv.y, xv.y), yv.y);
+    xn.z = fmaf(-sn, fmaf(tau, xv.z, yv.z), xv.z); yn.z = fmaf(sn, fmaf(-tau, yv.z, xv.z), yv.z);
+    xn.w = fmaf(-sn, fmaf(tau, xv.w, yv.w), xv.w); yn.w = fmaf(sn, fmaf(-tau, yv.w, xv.w), yv.w);
     *reinterpret_cast<float4*>(x + e) = xn;
     *reinterpret_cast<float4*>(y + e) = yn;
   }
@@ -233,6 +237,10 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const tta_select_ta
   }
 }
 
+static bool g_prof_on = false;
+static double g_prof_ms = 0.0;
+static unsigned long long g_prof_launches = 0;
+
 static void build_schedule(const tta_eig_task* th, int n, std::vector<std::vector<JacItem>>& launches) {
   launches.clear();
   for (int p = 0; p < n; ++p) {
@@ -257,6 +265,14 @@ static void build_schedule(const tta_eig_task* th, int n, std::vector<std::vecto
 }  // namespace tta
 
 extern "C" {
+
+void tta_jacobi_profile_enable(int on) { tta::g_prof_on = on != 0; }
+void tta_jacobi_profile_read(double* step_ms, unsigned long long* step_launches) {
+  if (step_ms) *step_ms = tta::g_prof_ms;
+  if (step_launches) *step_launches = tta::g_prof_launches;
+  tta::g_prof_ms = 0.0;
+  tta::g_prof_launches = 0;
+}
 
 size_t tta_jacobi_scratch_bytes(const tta_eig_task* tasks_host, int n_tasks) {
   using namespace tta;
@@ -333,16 +349,24 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     nl[p] = nb <= 1 ? 1 : 1 + ((nb & 1) ? nb : nb - 1);
   }
   bool all_done = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_prof_on) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+  }
   for (int sweep = 0; sweep < max_sweeps && !all_done; ++sweep) {
     int need = 0;
     for (int p = 0; p < n_tasks; ++p)
       if (!done_h[p]) need = nl[p] > need ? nl[p] : need;
+    if (ev0) cudaEventRecord(ev0, st);
     for (int l = 0; l < need; ++l) {
       const int cnt = (int)launches[l].size();
       if (cnt == 0) continue;
       jacobi_step_kernel<<<cnt, kJacThreads, smem, st>>>(items_dev + offs[l], tasks_dev, counts, done, floor2, tol);
       TTA_CHECK_LAUNCH("jacobi step launch");
+      if (ev0) ++g_prof_launches;
     }
+    if (ev1) cudaEventRecord(ev1, st);
     jacobi_sweep_end_kernel<<<(n_tasks + 127) / 128, 128, 0, st>>>(counts, done, sweeps, n_tasks);
     TTA_CHECK_LAUNCH("jacobi sweep_end launch");
     rc = check_cuda(cudaMemcpyAsync(done_h.data(), done, n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
@@ -350,8 +374,16 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     if (rc) return rc;
     rc = check_cuda(cudaStreamSynchronize(st), "jacobi sweep sync");
     if (rc) return rc;
+    if (ev0) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) g_prof_ms += ms;
+    }
     all_done = true;
     for (int p = 0; p < n_tasks; ++p) all_done = all_done && done_h[p];
+  }
+  if (ev0) {
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
   }
   rc = check_cuda(cudaMemcpyAsync(sweeps_h.data(), sweeps, n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
                   "jacobi sweeps readback");

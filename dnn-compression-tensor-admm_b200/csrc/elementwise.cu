@@ -6,6 +6,8 @@
 // grid-strided over a grid that is a multiple of the SM count.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "tta_common.cuh"
 
 namespace tta {
@@ -17,6 +19,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 constexpr int kEwThreads = 256;
 constexpr int kEwVecPerThread = 4;                                  // float4 per thread per chunk
@@ -166,6 +171,7 @@ extern "C" {
 
 const char* tta_last_error(void) { return tta::g_err; }
 int tta_version(void) { return 100; }
+unsigned long long tta_launch_count(void) { return tta::g_launches.load(std::memory_order_relaxed); }
 
 int tta_check_device(int dev) {
   cudaDeviceProp p;

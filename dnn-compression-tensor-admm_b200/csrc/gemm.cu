@@ -17,10 +17,24 @@ struct GemmTable {
   int start[kGemmMaxTasks + 1];
 };
 
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  using type = float4;
+};
+template <>
+struct Vec4<double> {
+  using type = double4;
+};
+
+// T = float: the fp32 path.  T = double: same tiling with DFMA, used by the eigenvector refinement
+// (all pointers of the task then address doubles).
+template <typename T>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task* __restrict__ tasks,
                                                            const __grid_constant__ GemmTable tab) {
-  __shared__ __align__(16) float As[kGemmBK][kGemmBM + 4];
-  __shared__ __align__(16) float Bs[kGemmBK][kGemmBN + 4];
+  __shared__ __align__(32) T As[kGemmBK][kGemmBM + 4];
+  __shared__ __align__(32) T Bs[kGemmBK][kGemmBN + 4];
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
 
@@ -38,11 +52,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task*
     const bool a_kfast = (tk.sak == 1);
     const bool b_jfast = (tk.sbj == 1);
 
-    float acc[4][4];
+    const T* __restrict__ pa = reinterpret_cast<const T*>(tk.a);
+    const T* __restrict__ pb = reinterpret_cast<const T*>(tk.b);
+    T* __restrict__ pc = reinterpret_cast<T*>(tk.c);
+    const T* __restrict__ pcs = reinterpret_cast<const T*>(tk.colscale);
+    T acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
 
     for (int k0 = 0; k0 < tk.K; k0 += kGemmBK) {
 #pragma unroll
@@ -51,27 +69,28 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task*
         int ar, ak;
         if (a_kfast) { ar = e >> 4; ak = e & 15; } else { ak = e >> 6; ar = e & 63; }
         const int gi = m0 + ar, gk = k0 + ak;
-        float v = 0.f;
-        if (gi < tk.M && gk < tk.K) v = __ldg(tk.a + (int64_t)gi * tk.sai + (int64_t)gk * tk.sak);
+        T v = T(0);
+        if (gi < tk.M && gk < tk.K) v = __ldg(pa + (int64_t)gi * tk.sai + (int64_t)gk * tk.sak);
         As[ak][ar] = v;
         int bk, bj;
         if (b_jfast) { bk = e >> 6; bj = e & 63; } else { bj = e >> 4; bk = e & 15; }
         const int gj = n0 + bj, gkb = k0 + bk;
-        float vb = 0.f;
-        if (gj < tk.N && gkb < tk.K) vb = __ldg(tk.b + (int64_t)gkb * tk.sbk + (int64_t)gj * tk.sbj);
+        T vb = T(0);
+        if (gj < tk.N && gkb < tk.K) vb = __ldg(pb + (int64_t)gkb * tk.sbk + (int64_t)gj * tk.sbj);
         Bs[bk][bj] = vb;
       }
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < kGemmBK; ++kk) {
-        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-        const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-        const float a[4] = {av.x, av.y, av.z, av.w};
-        const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+        using V4 = typename Vec4<T>::type;
+        const V4 av = *reinterpret_cast<const V4*>(&As[kk][ty * 4]);
+        const V4 bv = *reinterpret_cast<const V4*>(&Bs[kk][tx * 4]);
+        const T a[4] = {av.x, av.y, av.z, av.w};
+        const T b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
       }
       __syncthreads();
     }
@@ -84,9 +103,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task*
       for (int j = 0; j < 4; ++j) {
         const int gj = n0 + tx * 4 + j;
         if (gj >= tk.N) continue;
-        float v = acc[i][j];
-        if (tk.colscale) v *= __ldg(tk.colscale + gj);
-        tk.c[(int64_t)gi * tk.ldc + gj] = v;
+        T v = acc[i][j];
+        if (pcs) v *= __ldg(pcs + gj);
+        pc[(int64_t)gi * tk.ldc + gj] = v;
       }
     }
   }
@@ -113,11 +132,9 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const tta_sqnorm_task* __re
 
 }  // namespace tta
 
-extern "C" {
-
-int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
-                     void* stream) {
-  using namespace tta;
+namespace tta {
+template <typename T>
+static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks, void* stream) {
   if (n_tasks < 0 || (n_tasks > 0 && (!tasks_dev || !tasks_host))) {
     set_error("gemm: bad task table");
     return TTA_E_INVALID;
@@ -145,10 +162,23 @@ int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_
     tab.total = (int)total;
     if (total == 0) continue;
     const int grid = total < (int64_t)kNumSMs * 16 ? (int)total : kNumSMs * 16;
-    gemm_kernel<<<grid, kGemmThreads, 0, st>>>(tasks_dev + first, tab);
+    gemm_kernel<T><<<grid, kGemmThreads, 0, st>>>(tasks_dev + first, tab);
     TTA_CHECK_LAUNCH("gemm launch");
   }
   return TTA_OK;
+}
+}  // namespace tta
+
+extern "C" {
+
+int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
+                     void* stream) {
+  return tta::launch_gemm<float>(tasks_dev, tasks_host, n_tasks, stream);
+}
+
+int tta_gemm_f64_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
+                         void* stream) {
+  return tta::launch_gemm<double>(tasks_dev, tasks_host, n_tasks, stream);
 }
 
 int tta_sqnorm_batched(const tta_sqnorm_task* tasks_dev, const tta_sqnorm_task* tasks_host, int n_tasks,

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restri
       double s = 0.0;
       for (int sidx = 0; sidx < tk.nsplit; ++sidx) s += p[(int64_t)sidx * kk2];
       v = (float)s;
+      if (tk.g64) tk.g64[(int64_t)row * tk.k + col] = s;
     }
     tk.x[e] = v;
   }

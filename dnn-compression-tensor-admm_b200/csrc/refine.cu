@@ -1,0 +1,198 @@
+// fp64 refinement of the fp32 Jacobi eigenvectors + dominant-r selection (see include/tta.h).
+//
+// With Q the (nearly orthonormal) fp32 eigenvector estimate, S = Q^T G Q, T = Q^T Q, R = I - T:
+//   lambda_j = S_jj / T_jj
+//   E_ij     = (S_ij + lambda_j R_ij) / (lambda_j - lambda_i)      i != j, gap resolved
+//   E_ij     = R_ij / 2                                            unresolved cluster (span-neutral)
+//   E_jj     = R_jj / 2
+//   q_j'     = q_j + sum_i q_i E_ij                                (Ogita & Aishima 2018, one step)
+// Only the r dominant columns j are formed (the truncation of ttd.py:21-23 / admm.py:132-134).
+#include "tta_common.cuh"
+
+namespace tta {
+
+constexpr int kRefThreads = 512;
+constexpr double kRefCutRel = 4e-7;     // eigenvalues below cut_rel * lambda_max count as zero
+constexpr double kRefGapRel = 1e-6;     // |lambda_i - lambda_j| below gap_rel * lambda_max: cluster
+constexpr double kRefMaxCorr = 0.05;    // first-order correction must stay small
+
+__global__ void __launch_bounds__(kRefThreads) refine_prepare_kernel(const tta_refine_task* __restrict__ tasks) {
+  __shared__ double s_max[kRefThreads / 32];
+  __shared__ double s_cut;
+  const tta_refine_task tk = tasks[blockIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarp = kRefThreads / 32;
+  // pass 1: largest column norm
+  double mx = 0.0;
+  for (int j = warp; j < tk.k; j += nwarp) {
+    const float* x = tk.x + (int64_t)j * tk.ld;
+    double a = 0.0;
+    for (int e = lane; e < tk.k; e += 32) a = fma((double)x[e], (double)x[e], a);
+    a = warp_sum(a);
+    mx = a > mx ? a : mx;
+  }
+  if (lane == 0) s_max[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int i = 0; i < nwarp; ++i) m = s_max[i] > m ? s_max[i] : m;
+    s_cut = m * (kRefCutRel * kRefCutRel);
+  }
+  __syncthreads();
+  const double cut = s_cut;
+  // pass 2: qt row j = x_j / ||x_j||  (zero row for numerically-null columns)
+  for (int j = warp; j < tk.k; j += nwarp) {
+    const float* x = tk.x + (int64_t)j * tk.ld;
+    double a = 0.0;
+    for (int e = lane; e < tk.k; e += 32) a = fma((double)x[e], (double)x[e], a);
+    a = warp_sum(a);
+    const double inv = (a > cut && a > 0.0) ? 1.0 / sqrt(a) : 0.0;
+    double* q = tk.qt + (int64_t)j * tk.k;
+    for (int e = lane; e < tk.k; e += 32) q[e] = (double)x[e] * inv;
+  }
+}
+
+__global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_refine_task* __restrict__ tasks) {
+  extern __shared__ double s_lam[];  // k eigenvalues, then k ints (rank), then k ints (live flag)
+  const tta_refine_task tk = tasks[blockIdx.x];
+  const int k = tk.k;
+  int* s_pos = reinterpret_cast<int*>(s_lam + k);
+  int* s_sel = s_pos + k;            // s_sel[p] = column index holding rank p
+  const int tid = threadIdx.x;
+  for (int j = tid; j < k; j += kRefThreads) {
+    const double tjj = tk.t[(int64_t)j * k + j];
+    s_lam[j] = tjj > 0.5 ? tk.s[(int64_t)j * k + j] / tjj : 0.0;
+  }
+  __syncthreads();
+  double lmax = 0.0;
+  for (int j = 0; j < k; ++j) lmax = fmax(lmax, s_lam[j]);
+  for (int j = tid; j < k; j += kRefThreads) {
+    const double lj = s_lam[j];
+    int pos = 0;
+    for (int i = 0; i < k; ++i) {
+      const double li = s_lam[i];
+      pos += (li > lj) || (li == lj && i < j);
+    }
+    s_pos[j] = pos;
+    if (pos < tk.r) s_sel[pos] = j;
+  }
+  __syncthreads();
+  const double gap_min = kRefGapRel * lmax;
+  for (int idx = tid; idx < tk.r * k; idx += kRefThreads) {
+    const int p = idx / k, i = idx - p * k;
+    const int j = s_sel[p];
+    const double lj = s_lam[j], li = s_lam[i];
+    const double tij = tk.t[(int64_t)j * k + i];
+    const double tii = tk.t[(int64_t)i * k + i];
+    double c;
+    if (i == j) {
+      c = 1.0 + 0.5 * (1.0 - tij);
+    } else if (!(tii > 0.5)) {
+      c = 0.0;                                   // null direction: nothing to mix in
+    } else {
+      const double rij = -tij;
+      const double gap = lj - li;
+      c = 0.5 * rij;
+      if (fabs(gap) > gap_min) {
+        const double e = (tk.s[(int64_t)j * k + i] + lj * rij) / gap;
+        if (fabs(e) <= kRefMaxCorr) c = e;
+      }
+    }
+    tk.c[idx] = c;
+  }
+  for (int p = tid; p < tk.r; p += kRefThreads) tk.lam[p] = s_lam[s_sel[p]];
+  if (tid == 0 && tk.r > 0) {
+    // stash lambda_max behind the r selected values? -- no: finalize recomputes the cut from lam[0]
+  }
+}
+
+__global__ void __launch_bounds__(256) refine_finalize_kernel(const tta_refine_task* __restrict__ tasks) {
+  const tta_refine_task tk = tasks[blockIdx.y];
+  const int k = tk.k, r = tk.r;
+  const double lmax = tk.lam[0];
+  const int64_t total = (int64_t)r * k;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / k), e = (int)(idx - (int64_t)p * k);
+    const double lam = tk.lam[p];
+    const bool live = lam > kRefCutRel * lmax && lam > 0.0;
+    const float v = live ? (float)tk.e64[idx] : 0.f;
+    const float sg = live ? (float)sqrt(lam) : 0.f;
+    tk.e[idx] = v;
+    if (tk.et) tk.et[(int64_t)e * r + p] = v;
+    if (tk.se) tk.se[idx] = v * sg;
+    if (e == 0) {
+      if (tk.sigma) tk.sigma[p] = sg;
+      if (tk.isigma) tk.isigma[p] = live ? (float)(1.0 / sqrt(lam)) : 0.f;
+    }
+  }
+}
+
+static int validate(const tta_refine_task* th, int n, const char* what) {
+  if (n < 0 || (n > 0 && !th)) {
+    set_error("%s: bad task table", what);
+    return TTA_E_INVALID;
+  }
+  for (int t = 0; t < n; ++t) {
+    const tta_refine_task& tk = th[t];
+    if (tk.k <= 0 || tk.r <= 0 || tk.r > tk.k || tk.ld < tk.k || !tk.x || !tk.qt || !tk.s || !tk.t || !tk.c ||
+        !tk.lam || !tk.e64 || !tk.e) {
+      set_error("%s: task %d invalid (k=%d r=%d ld=%d)", what, t, tk.k, tk.r, tk.ld);
+      return TTA_E_INVALID;
+    }
+  }
+  return TTA_OK;
+}
+
+}  // namespace tta
+
+extern "C" {
+
+int tta_refine_prepare_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host, int n_tasks,
+                               void* stream) {
+  using namespace tta;
+  int rc = validate(tasks_host, n_tasks, "refine_prepare");
+  if (rc || n_tasks == 0) return rc;
+  refine_prepare_kernel<<<n_tasks, kRefThreads, 0, (cudaStream_t)stream>>>(tasks_dev);
+  TTA_CHECK_LAUNCH("refine_prepare launch");
+  return TTA_OK;
+}
+
+int tta_refine_coeff_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host, int n_tasks,
+                             void* stream) {
+  using namespace tta;
+  int rc = validate(tasks_host, n_tasks, "refine_coeff");
+  if (rc || n_tasks == 0) return rc;
+  size_t smem = 0;
+  for (int t = 0; t < n_tasks; ++t) {
+    const size_t need = (size_t)tasks_host[t].k * 16;
+    smem = need > smem ? need : smem;
+  }
+  if (smem > 48 * 1024) {
+    rc = check_cuda(cudaFuncSetAttribute(refine_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "refine_coeff smem attribute");
+    if (rc) return rc;
+  }
+  refine_coeff_kernel<<<n_tasks, kRefThreads, smem, (cudaStream_t)stream>>>(tasks_dev);
+  TTA_CHECK_LAUNCH("refine_coeff launch");
+  return TTA_OK;
+}
+
+int tta_refine_finalize_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host, int n_tasks,
+                                void* stream) {
+  using namespace tta;
+  int rc = validate(tasks_host, n_tasks, "refine_finalize");
+  if (rc || n_tasks == 0) return rc;
+  int64_t mx = 0;
+  for (int t = 0; t < n_tasks; ++t) {
+    const int64_t el = (int64_t)tasks_host[t].r * tasks_host[t].k;
+    mx = el > mx ? el : mx;
+  }
+  int gx = (int)((mx + 255) / 256);
+  if (gx > kNumSMs * 2) gx = kNumSMs * 2;
+  if (gx < 1) gx = 1;
+  refine_finalize_kernel<<<dim3(gx, n_tasks), 256, 0, (cudaStream_t)stream>>>(tasks_dev);
+  TTA_CHECK_LAUNCH("refine_finalize launch");
+  return TTA_OK;
+}
+}

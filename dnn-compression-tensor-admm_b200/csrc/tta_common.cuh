@@ -15,6 +15,7 @@ namespace tta {
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of the library is counted (bench.py reports `gpu_launches`)
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {
@@ -28,6 +29,7 @@ inline int check_cuda(cudaError_t e, const char* what) {
   do {                                                           \
     int rc_ = ::tta::check_cuda(cudaGetLastError(), what);       \
     if (rc_ != TTA_OK) return rc_;                               \
+    ::tta::count_launch();                                       \
   } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -75,6 +75,34 @@ def tt_step_flops(shapes, ranks):
     return gram, proj, eig, recon
 
 
+class _Phases:
+    """Optional per-phase device timing (CUDA events on the launching stream); used by bench.py only.
+
+    `sink` is None (no timing, no extra syncs) or a dict phase -> accumulated milliseconds.
+    """
+
+    def __init__(self, sink):
+        self.sink = sink if (sink is not None and not rt.backend_is_emulated()) else None
+        self.marks = []
+
+    def mark(self, name):
+        if self.sink is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.marks.append((name, ev))
+
+    def finish(self):
+        if self.sink is None:
+            return
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        end.synchronize()
+        evs = self.marks + [('end', end)]
+        for (name, a), (_, b) in zip(evs[:-1], evs[1:]):
+            self.sink[name] = self.sink.get(name, 0.0) + a.elapsed_time(b)
+
+
 class _Buf:
     """fp32/fp64 workspace tensor + raw address."""
 
@@ -113,12 +141,14 @@ class TTLayer:
 class TTProjectionPlan:
     """Batched TT-SVD projection of a list of layers: Z_l = Proj_TT(W_l + U_l)."""
 
-    def __init__(self, layers, device, tol=5e-7, max_sweeps=40):
+    def __init__(self, layers, device, tol=2e-6, max_sweeps=40, refine=True):
         self.layers = list(layers)
         self.device = torch.device(device)
         self.tol = float(tol)
         self.max_sweeps = int(max_sweeps)
+        self.refine = bool(refine)
         self.sweeps = {}
+        self.profile = None
         self._bound = None
         self._alloc()
 
@@ -142,6 +172,13 @@ class TTProjectionPlan:
                 if m > n:
                     st['sigma'] = _Buf(r, dev)
                     st['isigma'] = _Buf(r, dev)
+                if self.refine:
+                    f64 = torch.float64
+                    for nm in ('g64', 'qt', 'y', 's', 't'):
+                        st[nm] = _Buf(k * k, dev, f64)
+                    st['c'] = _Buf(r * k, dev, f64)
+                    st['e64'] = _Buf(r * k, dev, f64)
+                    st['lam'] = _Buf(r, dev, f64)
                 w['steps'].append(st)
                 carry = st['carry']
             # reconstruction accumulators acc_j, j = 1..d-1 ; acc_0 is core_0
@@ -149,8 +186,6 @@ class TTProjectionPlan:
                 rows = _prod(L.shapes[:j + 1])
                 w['acc'][j] = _Buf(rows * L.ranks[j + 1], dev)
             self.ws.append(w)
-        n_eig = max((sum(1 for L in self.layers if L.d - 1 > i) for i in range(self.max_order() - 1)), default=0)
-        self._n_eig_max = n_eig
 
     def max_order(self):
         return max((L.d for L in self.layers), default=0)
@@ -182,24 +217,42 @@ class TTProjectionPlan:
             e = np.zeros(len(idx), dtype=rt.EIG_TASK)
             s = np.zeros(len(idx), dtype=rt.SELECT_TASK)
             mm = np.zeros(len(idx), dtype=rt.GEMM_TASK)
+            rf = np.zeros(len(idx), dtype=rt.REFINE_TASK)
+            dg = [np.zeros(len(idx), dtype=rt.GEMM_TASK) for _ in range(4)]
             for q, li in enumerate(idx):
                 st = self.ws[li]['steps'][i]
                 m, n, k, r = st['m'], st['n'], st['k'], st['r']
                 a = st['A'].ptr
+                g64 = st['g64'].ptr if self.refine else 0
                 if m <= n:   # row Gram A A^T
-                    g[q] = (a, st['part'].ptr, st['X'].ptr, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'])
+                    g[q] = (a, st['part'].ptr, st['X'].ptr, g64, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'])
                     s[q] = (st['X'].ptr, st['E'].ptr, st['core'].ptr, 0, 0, 0, k, st['ld'], r, 0)
                     # carry' (r x n) = E (r x m) * A (m x n)
                     mm[q] = (st['E'].ptr, a, st['carry'].ptr, 0, m, 1, n, 1, n, r, n, m, 0)
                 else:        # column Gram A^T A
-                    g[q] = (a, st['part'].ptr, st['X'].ptr, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'])
+                    g[q] = (a, st['part'].ptr, st['X'].ptr, g64, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'])
                     s[q] = (st['X'].ptr, st['E'].ptr, 0, st['carry'].ptr, st['sigma'].ptr, st['isigma'].ptr,
                             k, st['ld'], r, 0)
                     # core (m x r) = A (m x n) * E^T (n x r) * diag(1/sigma)
                     mm[q] = (a, st['E'].ptr, st['core'].ptr, st['isigma'].ptr, n, 1, 1, n, r, m, r, n, 0)
                 e[q] = (st['X'].ptr, k, st['ld'], st['kpad'], st['bw'])
+                if self.refine:
+                    sel = s[q]
+                    rf[q] = (st['X'].ptr, st['qt'].ptr, st['s'].ptr, st['t'].ptr, st['c'].ptr, st['lam'].ptr,
+                             st['e64'].ptr, sel['e'], sel['et'], sel['se'], sel['sigma'], sel['isigma'],
+                             k, st['ld'], r, 0)
+                    qt = st['qt'].ptr
+                    dg[0][q] = (qt, st['g64'].ptr, st['y'].ptr, 0, k, 1, k, 1, k, k, k, k, 0)      # y = qt * g64
+                    dg[1][q] = (st['y'].ptr, qt, st['s'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)        # s = y * qt^T
+                    dg[2][q] = (qt, qt, st['t'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)                 # t = qt * qt^T
+                    dg[3][q] = (st['c'].ptr, qt, st['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)      # e64 = c * qt
             wave = dict(idx=idx, gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev),
                         select=rt.TaskTable(s, dev), gemm=rt.TaskTable(mm, dev))
+            if self.refine:
+                wave['refine'] = rt.TaskTable(rf, dev)
+                wave['dgemm_ys_t'] = rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev)   # independent: one launch
+                wave['dgemm_s'] = rt.TaskTable(dg[1], dev)
+                wave['dgemm_e'] = rt.TaskTable(dg[3], dev)
             nbytes = rt.jacobi_scratch_bytes(wave['eig'])
             wave['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
             self.waves.append(wave)
@@ -231,18 +284,36 @@ class TTProjectionPlan:
     # -- execution ---------------------------------------------------------------------------------
     def run(self, w_list, u_list, z_list):
         self.bind(w_list, u_list, z_list)
+        self.sweeps = {}
+        ph = _Phases(self.profile)
+        ph.mark('unfold')
         rt.unfold_add(self.t_unfold)
         for wave in self.waves:
+            ph.mark('gram')
             rt.gram(wave['gram'])
+            ph.mark('eig')
             sw = rt.jacobi_eigh(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
             for q, li in enumerate(wave['idx']):
                 self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
-            rt.select(wave['select'])
+            ph.mark('select')
+            if self.refine:
+                rt.refine_prepare(wave['refine'])
+                rt.gemm_f64(wave['dgemm_ys_t'])
+                rt.gemm_f64(wave['dgemm_s'])
+                rt.refine_coeff(wave['refine'])
+                rt.gemm_f64(wave['dgemm_e'])
+                rt.refine_finalize(wave['refine'])
+            else:
+                rt.select(wave['select'])
+            ph.mark('project')
             rt.gemm(wave['gemm'])
+        ph.mark('recon')
         for tab in self.recon:
             rt.gemm(tab)
+        ph.mark('fold')
         if self.t_fold.n:
             rt.fold_store(self.t_fold)
+        ph.finish()
 
     def cores(self, li):
         """Cores of layer `li` after `run()` as tensors shaped (r_i, s_i, r_{i+1}) (ten2tt's return)."""

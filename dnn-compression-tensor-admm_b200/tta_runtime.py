@@ -22,7 +22,7 @@ P = np.uint64  # pointers
 EW_TASK = np.dtype([('w', P), ('z', P), ('u', P), ('g', P), ('numel', np.int64)], align=True)
 FOLD_TASK = np.dtype([('w', P), ('u', P), ('t', P), ('z', P), ('O', np.int32), ('I', np.int32),
                       ('KK', np.int32), ('pad_', np.int32)], align=True)
-GRAM_TASK = np.dtype([('a', P), ('part', P), ('x', P), ('si', np.int64), ('sb', np.int64), ('sc', np.int64),
+GRAM_TASK = np.dtype([('a', P), ('part', P), ('x', P), ('g64', P), ('si', np.int64), ('sb', np.int64), ('sc', np.int64),
                       ('k', np.int32), ('nb', np.int32), ('nc', np.int32), ('nsplit', np.int32),
                       ('ld', np.int32), ('kpad', np.int32)], align=True)
 EIG_TASK = np.dtype([('x', P), ('k', np.int32), ('ld', np.int32), ('kpad', np.int32), ('bw', np.int32)],
@@ -33,16 +33,22 @@ GEMM_TASK = np.dtype([('a', P), ('b', P), ('c', P), ('colscale', P), ('sai', np.
                       ('sbk', np.int64), ('sbj', np.int64), ('ldc', np.int64), ('M', np.int32),
                       ('N', np.int32), ('K', np.int32), ('pad_', np.int32)], align=True)
 SQNORM_TASK = np.dtype([('x', P), ('n', np.int64)], align=True)
+REFINE_TASK = np.dtype([('x', P), ('qt', P), ('s', P), ('t', P), ('c', P), ('lam', P), ('e64', P), ('e', P),
+                        ('et', P), ('se', P), ('sigma', P), ('isigma', P), ('k', np.int32), ('ld', np.int32),
+                        ('r', np.int32), ('pad_', np.int32)], align=True)
 
 STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.itemsize,
                 'tta_gram_task': GRAM_TASK.itemsize, 'tta_eig_task': EIG_TASK.itemsize,
                 'tta_select_task': SELECT_TASK.itemsize, 'tta_gemm_task': GEMM_TASK.itemsize,
-                'tta_sqnorm_task': SQNORM_TASK.itemsize}
+                'tta_sqnorm_task': SQNORM_TASK.itemsize, 'tta_refine_task': REFINE_TASK.itemsize}
 
-EXPORTS = ['tta_last_error', 'tta_version', 'tta_check_device', 'tta_dual_update_multi',
+EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_device', 'tta_jacobi_profile_enable',
+           'tta_jacobi_profile_read', 'tta_dual_update_multi',
            'tta_penalty_fwd_multi', 'tta_penalty_bwd_multi', 'tta_unfold_add_batched',
            'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
-           'tta_jacobi_scratch_bytes', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched']
+           'tta_jacobi_scratch_bytes', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
+           'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
+           'tta_refine_finalize_batched']
 
 
 class TtaError(RuntimeError):
@@ -76,6 +82,12 @@ def _load():
     lib.tta_last_error.restype = ctypes.c_char_p
     lib.tta_last_error.argtypes = []
     lib.tta_version.restype = ci
+    lib.tta_launch_count.restype = ctypes.c_ulonglong
+    lib.tta_launch_count.argtypes = []
+    lib.tta_jacobi_profile_enable.argtypes = [ci]
+    lib.tta_jacobi_profile_enable.restype = None
+    lib.tta_jacobi_profile_read.argtypes = [vp, vp]
+    lib.tta_jacobi_profile_read.restype = None
     lib.tta_check_device.argtypes = [ci]
     lib.tta_dual_update_multi.argtypes = [vp, vp, ci, vp, vp]
     lib.tta_penalty_fwd_multi.argtypes = [vp, vp, ci, cf, vp, vp]
@@ -89,8 +101,12 @@ def _load():
     lib.tta_select_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_gemm_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_sqnorm_batched.argtypes = [vp, vp, ci, vp, vp]
+    for nm in ('tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
+               'tta_refine_finalize_batched'):
+        getattr(lib, nm).argtypes = [vp, vp, ci, vp]
     for name in EXPORTS:
-        if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes'):
+        if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
+                        'tta_jacobi_profile_enable', 'tta_jacobi_profile_read'):
             getattr(lib, name).restype = ci
     _LIB = lib
     return lib
@@ -203,6 +219,43 @@ def select(tab):
 
 def gemm(tab):
     _check(lib().tta_gemm_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_gemm_batched')
+
+
+def gemm_f64(tab):
+    _check(lib().tta_gemm_f64_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_gemm_f64_batched')
+
+
+def refine_prepare(tab):
+    _check(lib().tta_refine_prepare_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()),
+           'tta_refine_prepare_batched')
+
+
+def refine_coeff(tab):
+    _check(lib().tta_refine_coeff_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()),
+           'tta_refine_coeff_batched')
+
+
+def refine_finalize(tab):
+    _check(lib().tta_refine_finalize_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()),
+           'tta_refine_finalize_batched')
+
+
+def launch_count():
+    return int(lib().tta_launch_count()) if _FAKE is None else 0
+
+
+def jacobi_profile(enable):
+    if _FAKE is None:
+        lib().tta_jacobi_profile_enable(int(bool(enable)))
+
+
+def jacobi_profile_read():
+    """(device ms spent in jacobi_step launch sequences, number of jacobi_step launches) since last read."""
+    ms = ctypes.c_double(0.0)
+    n = ctypes.c_ulonglong(0)
+    if _FAKE is None:
+        lib().tta_jacobi_profile_read(ctypes.byref(ms), ctypes.byref(n))
+    return ms.value, int(n.value)
 
 
 def sqnorm(tab, out):

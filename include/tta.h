@@ -34,6 +34,8 @@ extern "C" {
 
 const char* tta_last_error(void);
 int tta_version(void);
+/* number of kernels this library has launched so far in this process (bench.py: `gpu_launches`) */
+unsigned long long tta_launch_count(void);
 /* 0 if device `dev` can run this library (compute capability 10.x), else TTA_E_ARCH. */
 int tta_check_device(int dev);
 
@@ -98,6 +100,7 @@ typedef struct {
   const float* a;
   double* part;
   float* x;
+  double* g64; /* nullable: G as a k x k row-major fp64 matrix (input of the refinement step) */
   int64_t si, sb, sc;
   int32_t k, nb, nc, nsplit;
   int32_t ld, kpad;
@@ -125,6 +128,11 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
                             int n_tasks, float tol, int max_sweeps, int32_t* scratch_dev,
                             size_t scratch_bytes, int32_t* sweeps_out, void* stream);
 size_t tta_jacobi_scratch_bytes(const tta_eig_task* tasks_host, int n_tasks);
+/* Profiling aid for bench.py: when enabled, every sweep's launch sequence is bracketed by CUDA events
+ * on `stream` (no host sync inside the bracket) and the elapsed device time / number of
+ * jacobi_step launches are accumulated.  `tta_jacobi_profile_read` returns and clears them. */
+void tta_jacobi_profile_enable(int on);
+void tta_jacobi_profile_read(double* step_ms, unsigned long long* step_launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Select the r dominant eigenpairs of a converged X (truncation of ttd.py:21-23, admm.py:132-134)
@@ -163,6 +171,44 @@ typedef struct {
 
 int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
                      void* stream);
+/* Same operator in fp64: a, b, c, colscale address doubles (used by the refinement step below). */
+int tta_gemm_f64_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp64 refinement of the fp32 Jacobi eigenvectors (one Ogita-Aishima step) fused with the dominant-r
+ * selection.  Thousands of fp32 plane rotations leave an O(1e-5) error in the invariant subspace;
+ * one first-order correction computed from S = Q^T G Q and T = Q^T Q in fp64 squares it away.
+ * Sequence per problem (all batched):
+ *   refine_prepare : qt (k x k fp64, row j = x_j / ||x_j||)               from the Jacobi state x
+ *   3 x gemm_f64   : y = qt * g64 ; s = y * qt^T ; t = qt * qt^T           (caller enqueues these)
+ *   refine_coeff   : lambda_j = s_jj / t_jj, descending rank, and for each of the r dominant j the
+ *                    coefficient row c[p,:] = e_j + (first-order correction)  (r x k fp64)
+ *   1 x gemm_f64   : e64 = c * qt                                          (caller enqueues)
+ *   refine_finalize: e / et / se / sigma / isigma in fp32 -- same outputs as tta_select_batched
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x;   /* Jacobi state: kpad columns of length ld                   */
+  double* qt;       /* k x k                                                     */
+  const double* s;  /* k x k                                                     */
+  const double* t;  /* k x k                                                     */
+  double* c;        /* r x k                                                     */
+  double* lam;      /* r      refined eigenvalues of the selected vectors        */
+  const double* e64;/* r x k                                                     */
+  float* e;
+  float* et;        /* nullable */
+  float* se;        /* nullable */
+  float* sigma;     /* nullable */
+  float* isigma;    /* nullable */
+  int32_t k, ld, r, pad_;
+} tta_refine_task;
+
+int tta_refine_prepare_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host,
+                               int n_tasks, void* stream);
+int tta_refine_coeff_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host,
+                             int n_tasks, void* stream);
+int tta_refine_finalize_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host,
+                                int n_tasks, void* stream);
 
 /* out[t] = sum of squares of n floats (fp64): tensorly `tl.norm(core, 2)**2` in the HOOI stopping rule. */
 typedef struct {

@@ -119,6 +119,8 @@ class FakeTTA:
             x = _view(tk['x'], ld * kpad).reshape(kpad, ld)
             x[:] = 0
             x[:k, :k] = g.T.astype(np.float32)
+            if tk['g64']:
+                _view(tk['g64'], k * k, np.float64).reshape(k, k)[:] = g
         return 0
 
     # ---- eigensolver: exact fp64 eigh, stored as x_j = lambda_j v_j in scrambled column order ----
@@ -168,21 +170,86 @@ class FakeTTA:
                 _view(tk['isigma'], r)[:] = np.where(sg > 0, 1.0 / np.where(sg > 0, sg, 1), 0).astype(np.float32)
         return 0
 
+    # ---- refinement (include/tta.h: one Ogita-Aishima step) ----
+    def tta_refine_prepare_batched(self, tdev, thost, n, stream):
+        self.calls.append('refine_prepare')
+        for tk in _table(thost, n, rt.REFINE_TASK):
+            k, ld = int(tk['k']), int(tk['ld'])
+            x = _view(tk['x'], ld * k).reshape(k, ld)[:, :k].astype(np.float64)
+            nrm2 = np.sum(x * x, axis=1)
+            cut = nrm2.max() * (4e-7) ** 2 if k else 0.0
+            inv = np.where((nrm2 > cut) & (nrm2 > 0), 1.0 / np.sqrt(np.where(nrm2 > 0, nrm2, 1.0)), 0.0)
+            _view(tk['qt'], k * k, np.float64).reshape(k, k)[:] = x * inv[:, None]
+        return 0
+
+    def tta_refine_coeff_batched(self, tdev, thost, n, stream):
+        self.calls.append('refine_coeff')
+        for tk in _table(thost, n, rt.REFINE_TASK):
+            k, r = int(tk['k']), int(tk['r'])
+            S = _view(tk['s'], k * k, np.float64).reshape(k, k)
+            T = _view(tk['t'], k * k, np.float64).reshape(k, k)
+            tdiag = np.diag(T)
+            lam = np.where(tdiag > 0.5, np.diag(S) / np.where(tdiag > 0.5, tdiag, 1.0), 0.0)
+            order = np.argsort(-lam, kind='stable')[:r]
+            lmax = lam.max()
+            C = np.zeros((r, k))
+            for p, j in enumerate(order):
+                rrow = -T[j]
+                gap = lam[j] - lam
+                c = 0.5 * rrow
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    e = (S[j] + lam[j] * rrow) / gap
+                use = (np.abs(gap) > 1e-6 * lmax) & (np.abs(e) <= 0.05)
+                c = np.where(use, e, c)
+                c = np.where(tdiag > 0.5, c, 0.0)
+                c[j] = 1.0 + 0.5 * (1.0 - T[j, j])
+                C[p] = c
+            _view(tk['c'], r * k, np.float64).reshape(r, k)[:] = C
+            _view(tk['lam'], r, np.float64)[:] = lam[order]
+        return 0
+
+    def tta_refine_finalize_batched(self, tdev, thost, n, stream):
+        self.calls.append('refine_finalize')
+        for tk in _table(thost, n, rt.REFINE_TASK):
+            k, r = int(tk['k']), int(tk['r'])
+            lam = _view(tk['lam'], r, np.float64)
+            live = (lam > 4e-7 * lam[0]) & (lam > 0)
+            e = np.where(live[:, None], _view(tk['e64'], r * k, np.float64).reshape(r, k), 0.0).astype(np.float32)
+            sg = np.where(live, np.sqrt(np.where(live, lam, 0.0)), 0.0).astype(np.float32)
+            _view(tk['e'], r * k).reshape(r, k)[:] = e
+            if tk['et']:
+                _view(tk['et'], r * k).reshape(k, r)[:] = e.T
+            if tk['se']:
+                _view(tk['se'], r * k).reshape(r, k)[:] = e * sg[:, None]
+            if tk['sigma']:
+                _view(tk['sigma'], r)[:] = sg
+            if tk['isigma']:
+                _view(tk['isigma'], r)[:] = np.where(live, 1.0 / np.sqrt(np.where(live, lam, 1.0)), 0.0).astype(np.float32)
+        return 0
+
     # ---- gemm ----
+    def tta_gemm_f64_batched(self, tdev, thost, n, stream):
+        self.calls.append('gemm_f64')
+        return self._gemm(thost, n, np.float64)
+
     def tta_gemm_batched(self, tdev, thost, n, stream):
         self.calls.append('gemm')
+        return self._gemm(thost, n, np.float32)
+
+    def _gemm(self, thost, n, dt):
+        isz = np.dtype(dt).itemsize
         for tk in _table(thost, n, rt.GEMM_TASK):
             M, N, K = int(tk['M']), int(tk['N']), int(tk['K'])
             sai, sak, sbk, sbj, ldc = (int(tk[f]) for f in ('sai', 'sak', 'sbk', 'sbj', 'ldc'))
-            abase = _view(tk['a'], (M - 1) * sai + (K - 1) * sak + 1)
-            bbase = _view(tk['b'], (K - 1) * sbk + (N - 1) * sbj + 1)
-            a = np.lib.stride_tricks.as_strided(abase, shape=(M, K), strides=(4 * sai, 4 * sak))
-            b = np.lib.stride_tricks.as_strided(bbase, shape=(K, N), strides=(4 * sbk, 4 * sbj))
-            c = (a @ b).astype(np.float32)
+            abase = _view(tk['a'], (M - 1) * sai + (K - 1) * sak + 1, dt)
+            bbase = _view(tk['b'], (K - 1) * sbk + (N - 1) * sbj + 1, dt)
+            a = np.lib.stride_tricks.as_strided(abase, shape=(M, K), strides=(isz * sai, isz * sak))
+            b = np.lib.stride_tricks.as_strided(bbase, shape=(K, N), strides=(isz * sbk, isz * sbj))
+            c = (a @ b).astype(dt)
             if tk['colscale']:
-                c = c * _view(tk['colscale'], N)[None, :]
-            cbase = _view(tk['c'], (M - 1) * ldc + N)
-            np.lib.stride_tricks.as_strided(cbase, shape=(M, N), strides=(4 * ldc, 4))[:] = c
+                c = c * _view(tk['colscale'], N, dt)[None, :]
+            cbase = _view(tk['c'], (M - 1) * ldc + N, dt)
+            np.lib.stride_tricks.as_strided(cbase, shape=(M, N), strides=(isz * ldc, isz))[:] = c
         return 0
 
     def tta_sqnorm_batched(self, tdev, thost, n, out, stream):

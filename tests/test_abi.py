@@ -38,7 +38,7 @@ def test_struct_layouts_match_header(tmp_path):
     fields = {
         'tta_ew_task': rt.EW_TASK, 'tta_fold_task': rt.FOLD_TASK, 'tta_gram_task': rt.GRAM_TASK,
         'tta_eig_task': rt.EIG_TASK, 'tta_select_task': rt.SELECT_TASK, 'tta_gemm_task': rt.GEMM_TASK,
-        'tta_sqnorm_task': rt.SQNORM_TASK}
+        'tta_sqnorm_task': rt.SQNORM_TASK, 'tta_refine_task': rt.REFINE_TASK}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tta.h"', 'int main(void){']
     for sname, dt in fields.items():
         lines.append('printf("%s %zu\\n", "{0}", sizeof({0}));'.format(sname))

@@ -82,7 +82,7 @@ def test_unfold_fold_exact(O, I, KK):
 
 def _gram_task(a, x, part, k, si, sb, sc, nb, nc, nsplit, ld, kpad):
     tab = np.zeros(1, dtype=rt.GRAM_TASK)
-    tab[0] = (a.data_ptr(), part.data_ptr(), x.data_ptr(), si, sb, sc, k, nb, nc, nsplit, ld, kpad)
+    tab[0] = (a.data_ptr(), part.data_ptr(), x.data_ptr(), 0, si, sb, sc, k, nb, nc, nsplit, ld, kpad)
     return rt.TaskTable(tab, DEV)
 
 
@@ -249,3 +249,57 @@ def test_sqnorm():
     for i, x in enumerate(xs):
         ref = float(np.sum(x.astype(np.float64) ** 2))
         assert abs(float(out[i]) - ref) <= 1e-12 * ref
+
+
+@pytest.mark.parametrize('k,r', [(64, 20), (240, 82), (512, 105)])
+def test_refinement_reaches_fp64_subspace(k, r):
+    """fp32 Jacobi + one fp64 Ogita-Aishima step: dominant-r projector vs numpy fp64 eigh."""
+    rng = np.random.RandomState(9)
+    A = rng.randn(k, 3 * k)
+    G64 = A @ A.T
+    ld, kpad = (k + 3) // 4 * 4, (k + 15) // 16 * 16
+    X = np.zeros((kpad, ld), dtype=np.float32)
+    X[:k, :k] = G64.astype(np.float32).T
+    x = _t(X.reshape(-1))
+    g64 = _t(G64.reshape(-1))
+    f64 = dict(dtype=torch.float64, device=DEV)
+    qt, y, s, t = (torch.empty(k * k, **f64) for _ in range(4))
+    c, e64 = torch.empty(r * k, **f64), torch.empty(r * k, **f64)
+    lam = torch.empty(r, **f64)
+    e = torch.empty(r * k, device=DEV)
+    et = torch.empty(r * k, device=DEV)
+    sg = torch.empty(r, device=DEV)
+    etab = np.zeros(1, dtype=rt.EIG_TASK)
+    etab[0] = (x.data_ptr(), k, ld, kpad, 16)
+    tab = rt.TaskTable(etab, DEV)
+    scratch = torch.empty(rt.jacobi_scratch_bytes(tab) // 4 + 16, dtype=torch.int32, device=DEV)
+    rt.jacobi_eigh(tab, scratch, tol=2e-6, max_sweeps=40)
+    rf = np.zeros(1, dtype=rt.REFINE_TASK)
+    rf[0] = (x.data_ptr(), qt.data_ptr(), s.data_ptr(), t.data_ptr(), c.data_ptr(), lam.data_ptr(), e64.data_ptr(),
+             e.data_ptr(), et.data_ptr(), 0, sg.data_ptr(), 0, k, ld, r, 0)
+    rtab = rt.TaskTable(rf, DEV)
+
+    def dg(a, b, cc, sai, sak, sbk, sbj, ldc, M, N, K):
+        tb = np.zeros(1, dtype=rt.GEMM_TASK)
+        tb[0] = (a.data_ptr(), b.data_ptr(), cc.data_ptr(), 0, sai, sak, sbk, sbj, ldc, M, N, K, 0)
+        rt.gemm_f64(rt.TaskTable(tb, DEV))
+
+    rt.refine_prepare(rtab)
+    dg(qt, g64, y, k, 1, k, 1, k, k, k, k)
+    dg(y, qt, s, k, 1, 1, k, k, k, k, k)
+    dg(qt, qt, t, k, 1, 1, k, k, k, k, k)
+    rt.refine_coeff(rtab)
+    dg(c, qt, e64, k, 1, k, 1, k, r, k, k)
+    rt.refine_finalize(rtab)
+    torch.cuda.synchronize()
+    lam_ref, v_ref = np.linalg.eigh(G64)
+    lam_ref, v_ref = lam_ref[::-1], v_ref[:, ::-1]
+    E = e.cpu().numpy().reshape(r, k).astype(np.float64)
+    P = E.T @ E
+    P_ref = v_ref[:, :r] @ v_ref[:, :r].T
+    gap = (lam_ref[r - 1] - lam_ref[r]) / lam_ref[0]
+    # fp32 storage of E bounds the projector error at ~1e-7 * sqrt(r); gap amplification is second order
+    assert np.linalg.norm(P - P_ref) <= 2e-6 * np.sqrt(r) / max(min(gap * 1e3, 1.0), 1e-3), (np.linalg.norm(P - P_ref), gap)
+    assert np.allclose(lam.cpu().numpy(), lam_ref[:r], rtol=1e-9, atol=1e-9 * lam_ref[0])
+    assert np.allclose(sg.cpu().numpy() ** 2, lam_ref[:r], rtol=1e-6)
+    assert np.array_equal(et.cpu().numpy().reshape(k, r), e.cpu().numpy().reshape(r, k).T)
