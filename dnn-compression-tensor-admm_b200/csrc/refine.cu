@@ -106,22 +106,29 @@ __global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_ref
   }
 }
 
+// One warp per selected row: renormalise the corrected vector in fp64 (the first-order update leaves
+// ||q'||^2 = 1 + O(theta^2)), then emit the fp32 outputs.
 __global__ void __launch_bounds__(256) refine_finalize_kernel(const tta_refine_task* __restrict__ tasks) {
   const tta_refine_task tk = tasks[blockIdx.y];
   const int k = tk.k, r = tk.r;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double lmax = tk.lam[0];
-  const int64_t total = (int64_t)r * k;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int p = (int)(idx / k), e = (int)(idx - (int64_t)p * k);
+  for (int p = blockIdx.x * 8 + warp; p < r; p += gridDim.x * 8) {
     const double lam = tk.lam[p];
     const bool live = lam > kRefCutRel * lmax && lam > 0.0;
-    const float v = live ? (float)tk.e64[idx] : 0.f;
+    const double* src = tk.e64 + (int64_t)p * k;
+    double nrm = 0.0;
+    for (int e = lane; e < k; e += 32) nrm = fma(src[e], src[e], nrm);
+    nrm = warp_sum(nrm);
+    const double inv = (live && nrm > 0.0) ? 1.0 / sqrt(nrm) : 0.0;
     const float sg = live ? (float)sqrt(lam) : 0.f;
-    tk.e[idx] = v;
-    if (tk.et) tk.et[(int64_t)e * r + p] = v;
-    if (tk.se) tk.se[idx] = v * sg;
-    if (e == 0) {
+    for (int e = lane; e < k; e += 32) {
+      const float v = (float)(src[e] * inv);
+      tk.e[(int64_t)p * k + e] = v;
+      if (tk.et) tk.et[(int64_t)e * r + p] = v;
+      if (tk.se) tk.se[(int64_t)p * k + e] = v * sg;
+    }
+    if (lane == 0) {
       if (tk.sigma) tk.sigma[p] = sg;
       if (tk.isigma) tk.isigma[p] = live ? (float)(1.0 / sqrt(lam)) : 0.f;
     }
@@ -183,13 +190,10 @@ int tta_refine_finalize_batched(const tta_refine_task* tasks_dev, const tta_refi
   using namespace tta;
   int rc = validate(tasks_host, n_tasks, "refine_finalize");
   if (rc || n_tasks == 0) return rc;
-  int64_t mx = 0;
-  for (int t = 0; t < n_tasks; ++t) {
-    const int64_t el = (int64_t)tasks_host[t].r * tasks_host[t].k;
-    mx = el > mx ? el : mx;
-  }
-  int gx = (int)((mx + 255) / 256);
-  if (gx > kNumSMs * 2) gx = kNumSMs * 2;
+  int mx = 0;
+  for (int t = 0; t < n_tasks; ++t) mx = tasks_host[t].r > mx ? tasks_host[t].r : mx;
+  int gx = (mx + 7) / 8;
+  if (gx > kNumSMs) gx = kNumSMs;
   if (gx < 1) gx = 1;
   refine_finalize_kernel<<<dim3(gx, n_tasks), 256, 0, (cudaStream_t)stream>>>(tasks_dev);
   TTA_CHECK_LAUNCH("refine_finalize launch");

@@ -141,7 +141,7 @@ class TTLayer:
 class TTProjectionPlan:
     """Batched TT-SVD projection of a list of layers: Z_l = Proj_TT(W_l + U_l)."""
 
-    def __init__(self, layers, device, tol=2e-6, max_sweeps=40, refine=True):
+    def __init__(self, layers, device, tol=5e-7, max_sweeps=40, refine=True):
         self.layers = list(layers)
         self.device = torch.device(device)
         self.tol = float(tol)

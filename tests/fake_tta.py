@@ -214,7 +214,10 @@ class FakeTTA:
             k, r = int(tk['k']), int(tk['r'])
             lam = _view(tk['lam'], r, np.float64)
             live = (lam > 4e-7 * lam[0]) & (lam > 0)
-            e = np.where(live[:, None], _view(tk['e64'], r * k, np.float64).reshape(r, k), 0.0).astype(np.float32)
+            e64 = _view(tk['e64'], r * k, np.float64).reshape(r, k)
+            nrm = np.linalg.norm(e64, axis=1)
+            e64 = e64 / np.where(nrm > 0, nrm, 1.0)[:, None]
+            e = np.where(live[:, None], e64, 0.0).astype(np.float32)
             sg = np.where(live, np.sqrt(np.where(live, lam, 0.0)), 0.0).astype(np.float32)
             _view(tk['e'], r * k).reshape(r, k)[:] = e
             if tk['et']:
