@@ -22,7 +22,7 @@
 
 #include <vector>
 
-#include "tta_common.cuh"
+#include "eig_device.cuh"
 
 namespace tta {
 
@@ -36,17 +36,6 @@ struct JacItem {
 constexpr int kJacMaxBw = 16;
 constexpr int kJacThreads = kJacMaxBw * 32;
 constexpr float kJacFloorRel = 1e-7f;  // columns below floor_rel * max column norm are numerically zero
-
-// round `r` of the circle-method tournament on n (even) players; pair q in [0, n/2)
-__host__ __device__ inline void rr_pair(int n, int r, int q, int& p0, int& p1) {
-  if (q == 0) {
-    p0 = n - 1;
-    p1 = r;
-  } else {
-    p0 = (r + q) % (n - 1);
-    p1 = (r - q + (n - 1)) % (n - 1);
-  }
-}
 
 // floor2[p] = (floor_rel * max_j ||x_j||)^2
 __global__ void __launch_bounds__(256) jacobi_floor_kernel(const tta_eig_task* __restrict__ tasks,
@@ -71,48 +60,11 @@ __global__ void __launch_bounds__(256) jacobi_floor_kernel(const tta_eig_task* _
   }
 }
 
-__device__ __forceinline__ int jacobi_rotate_pair(float* __restrict__ x, float* __restrict__ y, int ld, int lane,
-                                                  float tol, float floor2) {
-  float a = 0.f, b = 0.f, c = 0.f;
-  for (int e = lane * 4; e < ld; e += 128) {
-    const float4 xv = *reinterpret_cast<const float4*>(x + e);
-    const float4 yv = *reinterpret_cast<const float4*>(y + e);
-    a = fmaf(xv.x, xv.x, a); a = fmaf(xv.y, xv.y, a); a = fmaf(xv.z, xv.z, a); a = fmaf(xv.w, xv.w, a);
-    b = fmaf(yv.x, yv.x, b); b = fmaf(yv.y, yv.y, b); b = fmaf(yv.z, yv.z, b); b = fmaf(yv.w, yv.w, b);
-    c = fmaf(xv.x, yv.x, c); c = fmaf(xv.y, yv.y, c); c = fmaf(xv.z, yv.z, c); c = fmaf(xv.w, yv.w, c);
-  }
-  a = warp_sum(a);
-  b = warp_sum(b);
-  c = warp_sum(c);
-  if (!(a > floor2) || !(b > floor2)) return 0;
-  if (!(fabsf(c) > tol * (sqrtf(a) * sqrtf(b)))) return 0;
-  const float zeta = (b - a) / (2.f * c);
-  const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-  const float cs = 1.f / sqrtf(1.f + t * t);
-  const float sn = cs * t;
-  // x' = x - sn*(y + tau*x), y' = y + sn*(x - tau*y) with tau = sn/(1+cs)  (== cs*x - sn*y, sn*x + cs*y).
-  // Late rotations have cs == 1.0f after rounding; applying the 1-cs part explicitly keeps every
-  // rotation norm-preserving to rounding error instead of inflating the columns by t^2/2 each time.
-  const float tau = sn / (1.f + cs);
-  for (int e = lane * 4; e < ld; e += 128) {
-    float4 xv = *reinterpret_cast<const float4*>(x + e);
-    float4 yv = *reinterpret_cast<const float4*>(y + e);
-    float4 xn, yn;
-    xn.x = fmaf(-sn, fmaf(tau, xv.x, yv.x), xv.x); yn.x = fmaf(sn, fmaf(-tau, yv.x, xv.x), yv.x);
-    xn.y = fmaf(-sn, fmaf(tau, xv.y, yv.y), xv.y); yn.y = fmaf(sn, fmaf(-tau, yv.y, xv.y), yv.y);
-    xn.z = fmaf(-sn, fmaf(tau, xv.z, yv.z), xv.z); yn.z = fmaf(sn, fmaf(-tau, yv.z, xv.z), yv.z);
-    xn.w = fmaf(-sn, fmaf(tau, xv.w, yv.w), xv.w); yn.w = fmaf(sn, fmaf(-tau, yv.w, xv.w), yv.w);
-    *reinterpret_cast<float4*>(x + e) = xn;
-    *reinterpret_cast<float4*>(y + e) = yn;
-  }
-  return 1;
-}
-
 __global__ void __launch_bounds__(kJacThreads) jacobi_step_kernel(const JacItem* __restrict__ items,
                                                                   const tta_eig_task* __restrict__ tasks,
                                                                   int32_t* __restrict__ counts,
                                                                   const int32_t* __restrict__ done,
-                                                                  const float* __restrict__ floor2, float tol) {
+                                                                  const float* __restrict__ floor2, float tol2) {
   extern __shared__ __align__(16) float cols[];
   __shared__ int s_rot;
   const JacItem it = items[blockIdx.x];
@@ -134,32 +86,19 @@ __global__ void __launch_bounds__(kJacThreads) jacobi_step_kernel(const JacItem*
   __syncthreads();
 
   const float fl = floor2[it.prob];
-  int nrot = 0;
-  if (it.kind == 1) {
-    // cross pairs: step s pairs column w of A with column (w+s)%bw of B
-    for (int s = 0; s < bw; ++s) {
-      if (warp < bw) {
-        float* x = cols + (int64_t)warp * ld;
-        float* y = cols + (int64_t)(bw + (warp + s) % bw) * ld;
-        nrot += jacobi_rotate_pair(x, y, ld, lane, tol, fl);
-      }
-      __syncthreads();
-    }
-  } else {
-    const int half = bw >> 1;
-    for (int r = 0; r < bw - 1; ++r) {
-      if (warp < half * nblk) {
-        const int h = warp / half, q = warp - h * half;
-        int p0, p1;
-        rr_pair(bw, r, q, p0, p1);
-        float* x = cols + (int64_t)(h * bw + (p0 < p1 ? p0 : p1)) * ld;
-        float* y = cols + (int64_t)(h * bw + (p0 < p1 ? p1 : p0)) * ld;
-        nrot += jacobi_rotate_pair(x, y, ld, lane, tol, fl);
-      }
-      __syncthreads();
-    }
+  int nrot;
+  const int nv = (ld + 127) >> 7;
+  switch (nv) {
+    case 1: nrot = jacobi_block<1>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    case 2: nrot = jacobi_block<2>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    case 3: nrot = jacobi_block<3>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    case 4: nrot = jacobi_block<4>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    default: nrot = jacobi_block<0>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
   }
   if (lane == 0 && nrot) atomicAdd(&s_rot, nrot);
+  __syncthreads();
+  const int total_rot = s_rot;
+  if (total_rot == 0) return;   // nothing changed: skip the write-back (uniform across the CTA)
 
   for (int h = 0; h < nblk; ++h) {
     const int blk = h == 0 ? it.blk_a : it.blk_b;
@@ -167,8 +106,7 @@ __global__ void __launch_bounds__(kJacThreads) jacobi_step_kernel(const JacItem*
     const float4* src = reinterpret_cast<const float4*>(cols + (int64_t)h * bw * ld);
     for (int e = tid; e < bw * ld4; e += kJacThreads) dst[e] = src[e];
   }
-  __syncthreads();
-  if (tid == 0 && s_rot) atomicAdd(counts + it.prob, s_rot);
+  if (tid == 0) atomicAdd(counts + it.prob, total_rot);
 }
 
 // done[p] |= (counts[p] == 0); counts[p] = 0
@@ -241,9 +179,14 @@ static bool g_prof_on = false;
 static double g_prof_ms = 0.0;
 static unsigned long long g_prof_launches = 0;
 
+static bool g_force_legacy = false;   // test hook: route every problem through the multi-launch solver
+
+static bool use_cluster(const tta_eig_task& tk) { return !g_force_legacy && jacobi_cluster_eligible(tk); }
+
 static void build_schedule(const tta_eig_task* th, int n, std::vector<std::vector<JacItem>>& launches) {
   launches.clear();
   for (int p = 0; p < n; ++p) {
+    if (use_cluster(th[p])) continue;
     const int bw = th[p].bw;
     const int nb = th[p].kpad / bw;
     const int nlaunch = nb <= 1 ? 1 : 1 + ((nb & 1) ? nb : nb - 1);
@@ -267,6 +210,7 @@ static void build_schedule(const tta_eig_task* th, int n, std::vector<std::vecto
 extern "C" {
 
 void tta_jacobi_profile_enable(int on) { tta::g_prof_on = on != 0; }
+void tta_jacobi_force_multilaunch(int on) { tta::g_force_legacy = on != 0; }
 void tta_jacobi_profile_read(double* step_ms, unsigned long long* step_launches) {
   if (step_ms) *step_ms = tta::g_prof_ms;
   if (step_launches) *step_launches = tta::g_prof_launches;
@@ -281,8 +225,8 @@ size_t tta_jacobi_scratch_bytes(const tta_eig_task* tasks_host, int n_tasks) {
   build_schedule(tasks_host, n_tasks, launches);
   size_t items = 0;
   for (auto& l : launches) items += l.size();
-  // counts, done, sweeps (int32 each), floor2 (float), items
-  return (size_t)n_tasks * 4 * sizeof(int32_t) + items * sizeof(JacItem) + 64;
+  // counts, done, sweeps (int32 each), floor2 (float), cluster ids, cluster status, items
+  return (size_t)n_tasks * 6 * sizeof(int32_t) + items * sizeof(JacItem) + 64;
 }
 
 int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* tasks_host, int n_tasks, float tol,
@@ -295,13 +239,24 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     return TTA_E_INVALID;
   }
   size_t smem = 0;
+  std::vector<int> cl_probs;
+  int n_legacy = 0;
   for (int p = 0; p < n_tasks; ++p) {
     const tta_eig_task& tk = tasks_host[p];
-    if ((tk.bw != 8 && tk.bw != 16) || tk.k <= 0 || tk.ld < tk.k || (tk.ld & 3) || tk.kpad < tk.k ||
+    if (tk.bw < 2 || tk.bw > 32 || (tk.bw & 1) || tk.k <= 0 || tk.ld < tk.k || (tk.ld & 3) || tk.kpad < tk.k ||
         (tk.kpad % tk.bw) || !tk.x) {
       set_error("jacobi: task %d invalid (k=%d ld=%d kpad=%d bw=%d)", p, tk.k, tk.ld, tk.kpad, tk.bw);
       return TTA_E_INVALID;
     }
+    if (use_cluster(tk)) {
+      cl_probs.push_back(p);
+      continue;
+    }
+    if (tk.bw > kJacMaxBw) {
+      set_error("jacobi: task %d (k=%d) needs the multi-launch solver, which supports bw <= %d", p, tk.k, kJacMaxBw);
+      return TTA_E_INVALID;
+    }
+    ++n_legacy;
     const size_t need = (size_t)2 * tk.bw * tk.ld * sizeof(float);
     smem = need > smem ? need : smem;
   }
@@ -321,7 +276,9 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
   int32_t* done = scratch_dev + n_tasks;
   int32_t* sweeps = scratch_dev + 2 * n_tasks;
   float* floor2 = reinterpret_cast<float*>(scratch_dev + 3 * n_tasks);
-  JacItem* items_dev = reinterpret_cast<JacItem*>(scratch_dev + 4 * n_tasks);
+  int32_t* cl_ids = scratch_dev + 4 * n_tasks;
+  int32_t* cl_status = scratch_dev + 5 * n_tasks;
+  JacItem* items_dev = reinterpret_cast<JacItem*>(scratch_dev + 6 * n_tasks);
 
   std::vector<JacItem> flat;
   std::vector<size_t> offs;
@@ -329,28 +286,44 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     offs.push_back(flat.size());
     flat.insert(flat.end(), l.begin(), l.end());
   }
-  int rc = check_cuda(cudaMemsetAsync(scratch_dev, 0, (size_t)n_tasks * 4 * sizeof(int32_t), st), "jacobi memset");
+  int rc = check_cuda(cudaMemsetAsync(scratch_dev, 0, (size_t)n_tasks * 6 * sizeof(int32_t), st), "jacobi memset");
   if (rc) return rc;
-  rc = check_cuda(cudaMemcpyAsync(items_dev, flat.data(), flat.size() * sizeof(JacItem), cudaMemcpyHostToDevice, st),
-                  "jacobi schedule upload");
-  if (rc) return rc;
-  rc = check_cuda(cudaFuncSetAttribute(jacobi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                  "jacobi smem attribute");
-  if (rc) return rc;
+  std::vector<int32_t> done_h(n_tasks, 0), sweeps_h(n_tasks, 0);
+  for (int p : cl_probs) done_h[p] = 1;     // owned by the cluster solver: the step kernels skip them
+  if (n_legacy) {
+    rc = check_cuda(cudaMemcpyAsync(done, done_h.data(), n_tasks * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+                    "jacobi done upload");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemcpyAsync(items_dev, flat.data(), flat.size() * sizeof(JacItem), cudaMemcpyHostToDevice, st),
+                    "jacobi schedule upload");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(jacobi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "jacobi smem attribute");
+    if (rc) return rc;
+  }
 
   jacobi_floor_kernel<<<n_tasks, 256, 0, st>>>(tasks_dev, floor2);
   TTA_CHECK_LAUNCH("jacobi floor launch");
 
-  std::vector<int32_t> done_h(n_tasks, 0), sweeps_h(n_tasks, 0);
+  cudaEvent_t cev0 = nullptr, cev1 = nullptr;
+  if (g_prof_on && !cl_probs.empty()) {
+    cudaEventCreate(&cev0);
+    cudaEventCreate(&cev1);
+    cudaEventRecord(cev0, st);
+  }
+  rc = jacobi_cluster_run(tasks_dev, tasks_host, cl_probs, tol * tol, max_sweeps, cl_ids, sweeps, cl_status, floor2, st);
+  if (rc) return rc;
+  if (cev0) cudaEventRecord(cev1, st);
+
   // launches needed by each problem
   std::vector<int> nl(n_tasks);
   for (int p = 0; p < n_tasks; ++p) {
     const int nb = tasks_host[p].kpad / tasks_host[p].bw;
     nl[p] = nb <= 1 ? 1 : 1 + ((nb & 1) ? nb : nb - 1);
   }
-  bool all_done = false;
+  bool all_done = (n_legacy == 0);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (g_prof_on) {
+  if (g_prof_on && n_legacy) {
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
   }
@@ -362,7 +335,8 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     for (int l = 0; l < need; ++l) {
       const int cnt = (int)launches[l].size();
       if (cnt == 0) continue;
-      jacobi_step_kernel<<<cnt, kJacThreads, smem, st>>>(items_dev + offs[l], tasks_dev, counts, done, floor2, tol);
+      jacobi_step_kernel<<<cnt, kJacThreads, smem, st>>>(items_dev + offs[l], tasks_dev, counts, done, floor2,
+                                                         tol * tol);
       TTA_CHECK_LAUNCH("jacobi step launch");
       if (ev0) ++g_prof_launches;
     }
@@ -385,11 +359,26 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }
+  std::vector<int32_t> status_h(n_tasks, 0);
   rc = check_cuda(cudaMemcpyAsync(sweeps_h.data(), sweeps, n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
                   "jacobi sweeps readback");
   if (rc) return rc;
+  rc = check_cuda(cudaMemcpyAsync(status_h.data(), cl_status, n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
+                  "jacobi status readback");
+  if (rc) return rc;
   rc = check_cuda(cudaStreamSynchronize(st), "jacobi final sync");
   if (rc) return rc;
+  if (cev0) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, cev0, cev1) == cudaSuccess) g_prof_ms += ms;
+    g_prof_launches += 1;
+    cudaEventDestroy(cev0);
+    cudaEventDestroy(cev1);
+  }
+  for (int p : cl_probs) {
+    done_h[p] = status_h[p];
+    all_done = all_done && status_h[p];
+  }
   if (sweeps_out) memcpy(sweeps_out, sweeps_h.data(), n_tasks * sizeof(int32_t));
   if (!all_done) {
     int bad = 0;

@@ -1,0 +1,273 @@
+// Persistent thread-block-cluster Jacobi eigensolver (k <= 512): one cluster of P CTAs owns one
+// eigenproblem for ALL of its sweeps.
+//
+// The multi-launch solver in eig.cu pays one kernel launch (~13 us of fixed cost on B200 for a
+// 512-thread / 64 KB CTA) per block round, runs all problems of a wave in lock step and needs a host
+// synchronisation per sweep.  Here instead:
+//   * the kpad = 2*P*bw columns live in the shared memory of the P CTAs of one cluster (2*bw columns
+//     each; every warp keeps its own column in registers during a block round);
+//   * one sweep = the pairs inside each block + a (2P-1)-round circle tournament over the 2P blocks;
+//     between rounds the blocks rotate between CTAs through L2 (global X) bracketed by two hardware
+//     cluster barriers -- no kernel boundary, no host involvement;
+//   * convergence ("no rotation in a full sweep") is decided inside the cluster through distributed
+//     shared memory, so every problem stops by itself and small problems free their SMs early;
+//   * independent problems are independent clusters of the same launch (problems with different P
+//     go to concurrent internal streams).
+#include <cooperative_groups.h>
+
+#include <map>
+#include <vector>
+
+#include "eig_device.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tta {
+
+
+__device__ __forceinline__ void cl_copy_block(float* __restrict__ dst, const float* __restrict__ src, int n4, int tid,
+                                              int nthreads, bool from_global) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+  float4* d = reinterpret_cast<float4*>(dst);
+  if (from_global) {
+    for (int e = tid; e < n4; e += nthreads) d[e] = __ldcg(s + e);   // L2-coherent: written by a peer CTA
+  } else {
+    for (int e = tid; e < n4; e += nthreads) __stcg(d + e, s[e]);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* __restrict__ cols, int* s_rot,
+                                             int* s_total, int* s_counts, const tta_eig_task& tk, int prob,
+                                             int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
+                                             float fl, float tol2, int max_sweeps) {
+  const int P = (int)cluster.num_blocks();
+  const int c = (int)cluster.block_rank();
+  const int bw = tk.bw, ld = tk.ld;
+  const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5, lane = tid & 31;
+  const int blk4 = bw * (ld >> 2);                 // float4 per block
+  const int64_t blk = (int64_t)bw * ld;            // floats per block
+  float* top = cols;
+  float* bot = cols + blk;
+
+  // block slots in global X: top row 0..P-1, bottom row P..2P-1
+  cl_copy_block(top, tk.x + (int64_t)c * blk, blk4, tid, nthreads, true);
+  cl_copy_block(bot, tk.x + (int64_t)(P + c) * blk, blk4, tid, nthreads, true);
+  if (tid == 0) *s_rot = 0;
+  __syncthreads();
+
+  // circle-method rotation of the block slots: t0 fixed; t_c -> t_{c+1}; t_{P-1} -> b_{P-1};
+  // b_c -> b_{c-1}; b_0 -> t_1.
+  const int top_dst = (c == 0) ? 0 : (c == P - 1 ? (2 * P - 1) : c + 1);
+  const int bot_dst = (c == 0) ? 1 : (P + c - 1);
+
+  int sweep = 0;
+  int converged = 0;
+  while (sweep < max_sweeps) {
+    int nrot = jacobi_block<NV>(cols, 0, 2, bw, ld, warp, lane, tol2, fl);     // pairs inside both blocks
+    for (int round = 0; round < 2 * P - 1; ++round) {
+      nrot += jacobi_block<NV>(cols, 1, 2, bw, ld, warp, lane, tol2, fl);      // top x bottom pairs
+      if (P > 1) {
+        // jacobi_block ends with __syncthreads(): shared columns are final for this round
+        if (c != 0) cl_copy_block(tk.x + (int64_t)top_dst * blk, top, blk4, tid, nthreads, false);
+        cl_copy_block(tk.x + (int64_t)bot_dst * blk, bot, blk4, tid, nthreads, false);
+        __threadfence();
+        cluster.sync();                          // all blocks of this round are in L2
+        if (c != 0) cl_copy_block(top, tk.x + (int64_t)c * blk, blk4, tid, nthreads, true);
+        cl_copy_block(bot, tk.x + (int64_t)(P + c) * blk, blk4, tid, nthreads, true);
+        cluster.sync();                          // nobody overwrites a slot that is still being read
+      }
+    }
+    ++sweep;
+    // ---- convergence: total number of rotations of this sweep over the cluster ----
+    if (lane == 0 && nrot) atomicAdd(s_rot, nrot);
+    __syncthreads();
+    int total;
+    if (P == 1) {
+      total = *s_rot;
+      __syncthreads();
+      if (tid == 0) *s_rot = 0;
+    } else {
+      if (tid == 0) {
+        int* remote = cluster.map_shared_rank(s_counts, 0);
+        remote[c] = *s_rot;
+        *s_rot = 0;
+      }
+      cluster.sync();
+      if (tid == 0) {
+        const int* remote = cluster.map_shared_rank(s_counts, 0);
+        int t = 0;
+        for (int i = 0; i < P; ++i) t += remote[i];
+        *s_total = t;
+      }
+      __syncthreads();
+      total = *s_total;
+      cluster.sync();                            // s_counts of CTA 0 may be rewritten after this point
+    }
+    if (total == 0) {
+      converged = 1;
+      break;
+    }
+  }
+
+  // final state back to global X (column order is irrelevant to the selection stage)
+  cl_copy_block(tk.x + (int64_t)c * blk, top, blk4, tid, nthreads, false);
+  cl_copy_block(tk.x + (int64_t)(P + c) * blk, bot, blk4, tid, nthreads, false);
+  if (c == 0 && tid == 0) {
+    sweeps_out[prob] = sweep;
+    status_out[prob] = converged;
+  }
+}
+
+// THREADS = 512: bw <= 16 (up to 128 registers per thread); THREADS = 1024: bw <= 32.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+    jacobi_cluster_kernel(const tta_eig_task* __restrict__ tasks, const int32_t* __restrict__ prob_ids,
+                          int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
+                          const float* __restrict__ floor2, float tol2, int max_sweeps) {
+  extern __shared__ __align__(16) float cols[];
+  __shared__ int s_rot;
+  __shared__ int s_total;
+  __shared__ int s_counts[16];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int prob = prob_ids[blockIdx.x / cluster.num_blocks()];
+  const tta_eig_task tk = tasks[prob];
+  const float fl = floor2[prob];
+  switch ((tk.ld + 127) >> 7) {
+    case 1: cluster_body<1>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
+    case 2: cluster_body<2>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
+    case 3: cluster_body<3>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
+    default: cluster_body<4>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
+  }
+}
+
+struct StreamPool {
+  cudaStream_t s[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr;
+  cudaEvent_t join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+static StreamPool* pool_for_device(int dev) {
+  static std::map<int, StreamPool*> pools;
+  auto it = pools.find(dev);
+  if (it != pools.end()) return it->second;
+  StreamPool* p = new StreamPool();
+  for (int i = 0; i < 5; ++i) {
+    if (cudaStreamCreateWithFlags(&p->s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  if (cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  pools[dev] = p;
+  return p;
+}
+
+bool jacobi_cluster_eligible(const tta_eig_task& tk) {
+  if (tk.ld > 512 || tk.bw < 2 || (tk.bw & 1) || tk.bw > 32) return false;
+  if (tk.kpad % (2 * tk.bw)) return false;
+  const int P = tk.kpad / (2 * tk.bw);
+  return P == 1 || P == 2 || P == 4 || P == 8 || P == 16;
+}
+
+// Enqueue the cluster solver for the problems listed in `probs` (indices into the task table).
+// `ids_dev` must hold probs.size() int32.  Work is forked from / joined back into `st`.
+int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs,
+                       float tol2, int max_sweeps, int32_t* ids_dev, int32_t* sweeps_dev, int32_t* status_dev,
+                       const float* floor2, cudaStream_t st) {
+  if (probs.empty()) return TTA_OK;
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  StreamPool* pool = pool_for_device(dev);
+  if (!pool) {
+    set_error("jacobi cluster: cannot create internal streams");
+    return TTA_E_CUDA;
+  }
+  // group by cluster size
+  const int sizes[5] = {1, 2, 4, 8, 16};
+  std::vector<int> grouped[5];
+  for (int p : probs) {
+    const int P = th[p].kpad / (2 * th[p].bw);
+    for (int g = 0; g < 5; ++g)
+      if (sizes[g] == P) grouped[g].push_back(p);
+  }
+  std::vector<int32_t> flat;
+  int offs[5];
+  for (int g = 0; g < 5; ++g) {
+    offs[g] = (int)flat.size();
+    flat.insert(flat.end(), grouped[g].begin(), grouped[g].end());
+  }
+  rc = check_cuda(cudaMemcpyAsync(ids_dev, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+                  "jacobi cluster ids upload");
+  if (rc) return rc;
+  rc = check_cuda(cudaEventRecord(pool->fork, st), "jacobi cluster fork");
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
+                    "jacobi cluster non-portable attribute");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<1024>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
+                    "jacobi cluster non-portable attribute");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  size_t smem_all = 0;
+  for (int p : probs) {
+    const size_t need = (size_t)2 * th[p].bw * th[p].ld * sizeof(float);
+    smem_all = need > smem_all ? need : smem_all;
+  }
+  rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_all),
+                  "jacobi cluster smem attribute");
+  if (rc) return rc;
+  rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_all),
+                  "jacobi cluster smem attribute");
+  if (rc) return rc;
+
+  for (int g = 0; g < 5; ++g) {
+    if (grouped[g].empty()) continue;
+    const int P = sizes[g];
+    size_t smem = 0;
+    int bwmax = 2;
+    for (int p : grouped[g]) {
+      const size_t need = (size_t)2 * th[p].bw * th[p].ld * sizeof(float);
+      smem = need > smem ? need : smem;
+      bwmax = th[p].bw > bwmax ? th[p].bw : bwmax;
+    }
+    cudaStream_t gs = pool->s[g];
+    rc = check_cuda(cudaStreamWaitEvent(gs, pool->fork, 0), "jacobi cluster stream wait");
+    if (rc) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(grouped[g].size() * P), 1, 1);
+    cfg.blockDim = dim3((unsigned)(bwmax * 32), 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = gs;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int32_t* ids = ids_dev + offs[g];
+    if (bwmax <= 16)
+      rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<512>, tasks_dev, ids, sweeps_dev, status_dev,
+                                         floor2, tol2, max_sweeps),
+                      "jacobi cluster launch");
+    else
+      rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<1024>, tasks_dev, ids, sweeps_dev, status_dev,
+                                         floor2, tol2, max_sweeps),
+                      "jacobi cluster launch");
+    if (rc) return rc;
+    count_launch();
+    rc = check_cuda(cudaEventRecord(pool->join[g], gs), "jacobi cluster join record");
+    if (rc) return rc;
+    rc = check_cuda(cudaStreamWaitEvent(st, pool->join[g], 0), "jacobi cluster join wait");
+    if (rc) return rc;
+  }
+  return TTA_OK;
+}
+
+}  // namespace tta

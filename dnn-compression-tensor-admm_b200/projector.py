@@ -15,6 +15,7 @@ into Z (through the (O,KK,I)->(O,I,KK) fold for k x k convolutions, admm.py:99).
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -44,9 +45,23 @@ def clip_tt_ranks(shapes, ranks):
     return ranks
 
 
-def eig_geometry(k):
-    """Column-state geometry of the Jacobi solver for a k x k Gram matrix."""
+def eig_geometry(k, pmax=None):
+    """Column-state geometry (ld, kpad, bw) of the Jacobi solver for a k x k Gram matrix.
+
+    k <= 512: persistent cluster solver -- kpad = 2 * P * bw with P (CTAs per problem) the smallest
+    power of two such that a CTA's block width bw = ceil(k / 2P) is <= 16 (one warp per column, 512
+    threads), P <= pmax (default 16; TTA_JACOBI_PMAX overrides, then bw grows up to 32).
+    k > 512 (Tucker sweep): multi-launch solver, blocks of 16 (8 if shared memory is short).
+    """
     ld = _round_up(k, 4)
+    if ld <= 512:
+        if pmax is None:
+            pmax = int(os.environ.get('TTA_JACOBI_PMAX', '16'))
+        p = 1
+        while (k + 2 * p - 1) // (2 * p) > 16 and p < pmax:
+            p *= 2
+        bw = max(2, _round_up((k + 2 * p - 1) // (2 * p), 2))
+        return ld, 2 * p * bw, bw
     bw = 16 if 2 * 16 * ld * 4 <= 200 * 1024 else 8
     return ld, _round_up(k, bw), bw
 

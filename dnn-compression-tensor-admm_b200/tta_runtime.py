@@ -43,7 +43,7 @@ STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.item
                 'tta_sqnorm_task': SQNORM_TASK.itemsize, 'tta_refine_task': REFINE_TASK.itemsize}
 
 EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_device', 'tta_jacobi_profile_enable',
-           'tta_jacobi_profile_read', 'tta_dual_update_multi',
+           'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch', 'tta_dual_update_multi',
            'tta_penalty_fwd_multi', 'tta_penalty_bwd_multi', 'tta_unfold_add_batched',
            'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
            'tta_jacobi_scratch_bytes', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
@@ -86,6 +86,8 @@ def _load():
     lib.tta_launch_count.argtypes = []
     lib.tta_jacobi_profile_enable.argtypes = [ci]
     lib.tta_jacobi_profile_enable.restype = None
+    lib.tta_jacobi_force_multilaunch.argtypes = [ci]
+    lib.tta_jacobi_force_multilaunch.restype = None
     lib.tta_jacobi_profile_read.argtypes = [vp, vp]
     lib.tta_jacobi_profile_read.restype = None
     lib.tta_check_device.argtypes = [ci]
@@ -106,7 +108,7 @@ def _load():
         getattr(lib, nm).argtypes = [vp, vp, ci, vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
-                        'tta_jacobi_profile_enable', 'tta_jacobi_profile_read'):
+                        'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch'):
             getattr(lib, name).restype = ci
     _LIB = lib
     return lib
@@ -242,6 +244,11 @@ def refine_finalize(tab):
 
 def launch_count():
     return int(lib().tta_launch_count()) if _FAKE is None else 0
+
+
+def jacobi_force_multilaunch(on):
+    if _FAKE is None:
+        lib().tta_jacobi_force_multilaunch(int(bool(on)))
 
 
 def jacobi_profile(enable):

@@ -112,15 +112,15 @@ int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_task* tasks_
 /* ---------------------------------------------------------------------------------------------
  * Symmetric eigensolver: one-sided (Hestenes) block Jacobi on the columns of X = G
  * (replaces numpy.linalg.svd / LAPACK gesdd of ttd.py:17, admm.py:131,143 and tensorly partial_svd)
- * On return the columns of X are mutually orthogonal: x_j = lambda_j * v_j.
- * Synchronises `stream` once per sweep (convergence test on the host).
+ * On return the columns of X are mutually orthogonal: x_j = lambda_j * v_j (column order arbitrary).
+ * Synchronises `stream` at least once (convergence status is read back).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   float* x;         /* kpad columns of length ld                       */
   int32_t k;        /* true order                                      */
   int32_t ld;       /* column length, multiple of 4, >= k              */
   int32_t kpad;     /* column count, multiple of bw                    */
-  int32_t bw;       /* column block width (8 or 16)                    */
+  int32_t bw;       /* column block width: even, <= 32 (<= 16 for ld > 512) */
 } tta_eig_task;
 
 /* sweeps_out (host, nullable): number of sweeps each problem needed. */
@@ -132,6 +132,10 @@ size_t tta_jacobi_scratch_bytes(const tta_eig_task* tasks_host, int n_tasks);
  * on `stream` (no host sync inside the bracket) and the elapsed device time / number of
  * jacobi_step launches are accumulated.  `tta_jacobi_profile_read` returns and clears them. */
 void tta_jacobi_profile_enable(int on);
+/* Test hook: != 0 routes every problem through the multi-launch solver (default: problems with
+ * ld <= 512 whose geometry is kpad == 2*P*bw, P in {1,2,4,8,16}, bw even <= 32, run on the persistent
+ * thread-block-cluster solver; the rest -- k up to 2048 in the Tucker sweep -- on the multi-launch one). */
+void tta_jacobi_force_multilaunch(int on);
 void tta_jacobi_profile_read(double* step_ms, unsigned long long* step_launches);
 
 /* ---------------------------------------------------------------------------------------------

@@ -303,3 +303,42 @@ def test_refinement_reaches_fp64_subspace(k, r):
     assert np.allclose(lam.cpu().numpy(), lam_ref[:r], rtol=1e-9, atol=1e-9 * lam_ref[0])
     assert np.allclose(sg.cpu().numpy() ** 2, lam_ref[:r], rtol=1e-6)
     assert np.array_equal(et.cpu().numpy().reshape(k, r), e.cpu().numpy().reshape(r, k).T)
+
+
+@pytest.mark.parametrize('multilaunch', [False, True])
+def test_jacobi_cluster_and_multilaunch_paths_agree(multilaunch):
+    """Plan geometry (persistent cluster solver) vs the multi-launch solver on the same matrices."""
+    import projector
+    rng = np.random.RandomState(11)
+    ks = [8, 16, 30, 64, 75, 130, 240, 384, 480, 512]
+    Gs = [_eig_problem(k, rng) for k in ks]
+    etab = np.zeros(len(ks), dtype=rt.EIG_TASK)
+    xs = []
+    for i, (k, G) in enumerate(zip(ks, Gs)):
+        ld, kpad, bw = projector.eig_geometry(k)
+        if multilaunch and bw > 16:
+            pytest.skip('multi-launch solver supports bw <= 16')
+        X = np.zeros((kpad, ld), dtype=np.float32)
+        X[:k, :k] = G.T
+        x = _t(X.reshape(-1))
+        xs.append((x, ld, kpad))
+        etab[i] = (x.data_ptr(), k, ld, kpad, bw)
+    tab = rt.TaskTable(etab, DEV)
+    scratch = torch.empty(rt.jacobi_scratch_bytes(tab) // 4 + 16, dtype=torch.int32, device=DEV)
+    rt.jacobi_force_multilaunch(multilaunch)
+    try:
+        sweeps = rt.jacobi_eigh(tab, scratch, tol=5e-7, max_sweeps=40)
+    finally:
+        rt.jacobi_force_multilaunch(False)
+    torch.cuda.synchronize()
+    for i, (k, G) in enumerate(zip(ks, Gs)):
+        x, ld, kpad = xs[i]
+        assert 1 <= sweeps[i] <= 24, sweeps
+        X = x.cpu().numpy().reshape(kpad, ld).astype(np.float64)
+        lam = np.sort(np.linalg.norm(X, axis=1))[::-1]
+        ref = np.linalg.eigvalsh(G.astype(np.float64))[::-1]
+        assert np.max(np.abs(lam[:k] - ref)) <= 2e-5 * ref[0], (k, multilaunch)
+        assert np.all(lam[k:] <= 1e-6 * ref[0])                       # padded columns stay (numerically) zero
+        Xn = X[np.argsort(-np.linalg.norm(X, axis=1))[:k]]
+        Q = Xn / np.linalg.norm(Xn, axis=1, keepdims=True)
+        assert np.max(np.abs(Q @ Q.T - np.eye(k))) <= 5e-6            # columns mutually orthogonal (tol 5e-7)
