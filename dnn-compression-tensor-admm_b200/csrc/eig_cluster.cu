@@ -25,6 +25,16 @@ namespace cg = cooperative_groups;
 namespace tta {
 
 
+// Cluster-wide barrier with release/acquire semantics.  Written as inline PTX with "memory" clobbers:
+// the compiler must not move shared/global accesses across either half (with the cooperative-groups
+// builtins ptxas was seen hoisting a global load between arrive and wait).  The leading
+// __syncthreads() orders this CTA's own shared-memory traffic first.
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void cl_copy_block(float* __restrict__ dst, const float* __restrict__ src, int n4, int tid,
                                               int nthreads, bool from_global) {
   const float4* s = reinterpret_cast<const float4*>(src);
@@ -63,6 +73,9 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
 
   int sweep = 0;
   int converged = 0;
+#ifdef TTA_DEBUG_CLUSTER
+  if (tid == 0) printf("[cl] blk %d P %d c %d prob %d bw %d ld %d top_dst %d bot_dst %d\n", (int)blockIdx.x, P, c, prob, bw, ld, top_dst, bot_dst);
+#endif
   while (sweep < max_sweeps) {
     int nrot = jacobi_block<NV>(cols, 0, 2, bw, ld, warp, lane, tol2, fl);     // pairs inside both blocks
     for (int round = 0; round < 2 * P - 1; ++round) {
@@ -72,10 +85,10 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
         if (c != 0) cl_copy_block(tk.x + (int64_t)top_dst * blk, top, blk4, tid, nthreads, false);
         cl_copy_block(tk.x + (int64_t)bot_dst * blk, bot, blk4, tid, nthreads, false);
         __threadfence();
-        cluster.sync();                          // all blocks of this round are in L2
+        cluster_sync_all();                          // all blocks of this round are in L2
         if (c != 0) cl_copy_block(top, tk.x + (int64_t)c * blk, blk4, tid, nthreads, true);
         cl_copy_block(bot, tk.x + (int64_t)(P + c) * blk, blk4, tid, nthreads, true);
-        cluster.sync();                          // nobody overwrites a slot that is still being read
+        cluster_sync_all();                          // nobody overwrites a slot that is still being read
       }
     }
     ++sweep;
@@ -93,7 +106,7 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
         remote[c] = *s_rot;
         *s_rot = 0;
       }
-      cluster.sync();
+      cluster_sync_all();
       if (tid == 0) {
         const int* remote = cluster.map_shared_rank(s_counts, 0);
         int t = 0;
@@ -102,8 +115,11 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
       }
       __syncthreads();
       total = *s_total;
-      cluster.sync();                            // s_counts of CTA 0 may be rewritten after this point
+      cluster_sync_all();                            // s_counts of CTA 0 may be rewritten after this point
     }
+#ifdef TTA_DEBUG_CLUSTER
+    if (tid == 0 && sweep <= 12) printf("[cl] c %d sweep %d total %d\n", c, sweep, total);
+#endif
     if (total == 0) {
       converged = 1;
       break;
@@ -119,9 +135,10 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
   }
 }
 
-// THREADS = 512: bw <= 16 (up to 128 registers per thread); THREADS = 1024: bw <= 32.
+// THREADS = 512: bw <= 16, two CTAs per SM (a network step has more cluster CTAs than the 148 SMs, and
+// a cluster that cannot be co-scheduled waits for a whole eigensolve); THREADS = 1024: bw <= 32.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
     jacobi_cluster_kernel(const tta_eig_task* __restrict__ tasks, const int32_t* __restrict__ prob_ids,
                           int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
                           const float* __restrict__ floor2, float tol2, int max_sweeps) {
@@ -226,7 +243,7 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
                   "jacobi cluster smem attribute");
   if (rc) return rc;
 
-  for (int g = 0; g < 5; ++g) {
+  for (int g = 4; g >= 0; --g) {   // largest clusters first: they are the critical path
     if (grouped[g].empty()) continue;
     const int P = sizes[g];
     size_t smem = 0;

@@ -63,8 +63,8 @@ __device__ __forceinline__ void store_col(float* __restrict__ col, int ld, int l
 }
 
 // One column pair held in registers (NV float4 per lane per column).  Returns 1 if rotated.
-// When rotating, the column with the larger norm is left in `x` (de Rijk ordering: large columns
-// migrate to low positions, which shortens the sweep count).
+// (No de Rijk column swap: with the parallel tournament orderings used here, moving the larger
+// column to `x` makes pairs chase each other across blocks and the sweep count explodes.)
 template <int NV>
 __device__ __forceinline__ int rotate_regs(float4 (&x)[NV], float4 (&y)[NV], float tol2, float floor2) {
   float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f;
@@ -86,7 +86,6 @@ __device__ __forceinline__ int rotate_regs(float4 (&x)[NV], float4 (&y)[NV], flo
   }
   float sn, tau;
   if (!jacobi_params(a, b, c, tol2, floor2, sn, tau)) return 0;
-  const bool swp = a < b;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     float4 xn, yn;
@@ -94,8 +93,8 @@ __device__ __forceinline__ int rotate_regs(float4 (&x)[NV], float4 (&y)[NV], flo
     rot2(sn, tau, x[j].y, y[j].y, xn.y, yn.y);
     rot2(sn, tau, x[j].z, y[j].z, xn.z, yn.z);
     rot2(sn, tau, x[j].w, y[j].w, xn.w, yn.w);
-    x[j] = swp ? yn : xn;
-    y[j] = swp ? xn : yn;
+    x[j] = xn;
+    y[j] = yn;
   }
   return 1;
 }
@@ -116,7 +115,6 @@ __device__ __forceinline__ int rotate_smem(float* __restrict__ x, float* __restr
   c = warp_sum(c);
   float sn, tau;
   if (!jacobi_params(a, b, c, tol2, floor2, sn, tau)) return 0;
-  const bool swp = a < b;
   for (int e = lane * 4; e < ld; e += 128) {
     const float4 xv = *reinterpret_cast<const float4*>(x + e);
     const float4 yv = *reinterpret_cast<const float4*>(y + e);
@@ -125,8 +123,8 @@ __device__ __forceinline__ int rotate_smem(float* __restrict__ x, float* __restr
     rot2(sn, tau, xv.y, yv.y, xn.y, yn.y);
     rot2(sn, tau, xv.z, yv.z, xn.z, yn.z);
     rot2(sn, tau, xv.w, yv.w, xn.w, yn.w);
-    *reinterpret_cast<float4*>(x + e) = swp ? yn : xn;
-    *reinterpret_cast<float4*>(y + e) = swp ? xn : yn;
+    *reinterpret_cast<float4*>(x + e) = xn;
+    *reinterpret_cast<float4*>(y + e) = yn;
   }
   return 1;
 }

@@ -300,7 +300,7 @@ def test_refinement_reaches_fp64_subspace(k, r):
     gap = (lam_ref[r - 1] - lam_ref[r]) / lam_ref[0]
     # fp32 storage of E bounds the projector error at ~1e-7 * sqrt(r); gap amplification is second order
     assert np.linalg.norm(P - P_ref) <= 2e-6 * np.sqrt(r) / max(min(gap * 1e3, 1.0), 1e-3), (np.linalg.norm(P - P_ref), gap)
-    assert np.allclose(lam.cpu().numpy(), lam_ref[:r], rtol=1e-9, atol=1e-9 * lam_ref[0])
+    assert np.allclose(lam.cpu().numpy(), lam_ref[:r], rtol=1e-7, atol=1e-9 * lam_ref[0])   # Rayleigh quotients
     assert np.allclose(sg.cpu().numpy() ** 2, lam_ref[:r], rtol=1e-6)
     assert np.array_equal(et.cpu().numpy().reshape(k, r), e.cpu().numpy().reshape(r, k).T)
 
@@ -324,9 +324,9 @@ def test_jacobi_cluster_and_multilaunch_paths_agree(multilaunch):
         xs.append((x, ld, kpad))
         etab[i] = (x.data_ptr(), k, ld, kpad, bw)
     tab = rt.TaskTable(etab, DEV)
-    scratch = torch.empty(rt.jacobi_scratch_bytes(tab) // 4 + 16, dtype=torch.int32, device=DEV)
     rt.jacobi_force_multilaunch(multilaunch)
     try:
+        scratch = torch.empty(rt.jacobi_scratch_bytes(tab) // 4 + 16, dtype=torch.int32, device=DEV)
         sweeps = rt.jacobi_eigh(tab, scratch, tol=5e-7, max_sweeps=40)
     finally:
         rt.jacobi_force_multilaunch(False)
