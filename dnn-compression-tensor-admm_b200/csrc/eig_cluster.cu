@@ -84,8 +84,7 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
         // jacobi_block ends with __syncthreads(): shared columns are final for this round
         if (c != 0) cl_copy_block(tk.x + (int64_t)top_dst * blk, top, blk4, tid, nthreads, false);
         cl_copy_block(tk.x + (int64_t)bot_dst * blk, bot, blk4, tid, nthreads, false);
-        __threadfence();
-        cluster_sync_all();                          // all blocks of this round are in L2
+        cluster_sync_all();                          // release/acquire at cluster scope: blocks visible in L2
         if (c != 0) cl_copy_block(top, tk.x + (int64_t)c * blk, blk4, tid, nthreads, true);
         cl_copy_block(bot, tk.x + (int64_t)(P + c) * blk, blk4, tid, nthreads, true);
         cluster_sync_all();                          // nobody overwrites a slot that is still being read

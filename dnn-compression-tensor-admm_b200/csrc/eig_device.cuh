@@ -22,17 +22,29 @@ __host__ __device__ inline void rr_pair(int n, int r, int q, int& p0, int& p1) {
 // exact plane rotation up to rounding, so approximate division / rsqrt only perturbs the annihilation
 // angle by O(ulp) (a slightly slower convergence), never the orthogonality of the transform.  The
 // serial latency of this scalar chain is what bounds a Jacobi step, hence no IEEE div / sqrt here.
+__device__ __forceinline__ float mufu_rcp(float x) {   // single MUFU.RCP, no range fix-up code
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_rsqrt(float x) {  // single MUFU.RSQ
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ bool jacobi_params(float a, float b, float c, float tol2, float floor2, float& sn,
                                               float& tau) {
   if (!(a > floor2) || !(b > floor2)) return false;
   if (!(c * c > (tol2 * a) * b)) return false;
-  const float zeta = __fdividef(b - a, 2.f * c);
+  const float zeta = (b - a) * mufu_rcp(2.f * c);
   const float h = fmaf(zeta, zeta, 1.f);
-  float t = (h < 1e30f) ? __fdividef(1.f, fabsf(zeta) + h * rsqrtf(h)) : __fdividef(0.5f, fabsf(zeta));
+  // |zeta| < ~1e15 here (c passed the threshold test), so h is finite and rsqrt is safe
+  float t = mufu_rcp(fabsf(zeta) + h * mufu_rsqrt(h));
   t = copysignf(t, zeta);
-  const float cs = rsqrtf(fmaf(t, t, 1.f));
+  const float cs = mufu_rsqrt(fmaf(t, t, 1.f));
   sn = cs * t;
-  tau = __fdividef(sn, 1.f + cs);
+  tau = sn * mufu_rcp(1.f + cs);
   return true;
 }
 
@@ -139,11 +151,13 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, int kind, 
     // cross pairs: warp w keeps column w of block A in registers for the whole block step and meets
     // column (w+s)%bw of block B at step s (disjoint pairs within a step).
     float4 x[N];
-    float* xcol = cols + (int64_t)warp * ld;
+    float* xcol = cols + warp * ld;
     if (NV > 0 && warp < bw) load_col<N>(xcol, ld, lane, x);
-    for (int s = 0; s < bw; ++s) {
+    int yslot = warp;                       // (warp + s) % bw without the integer division
+    for (int s = 0; s < bw; ++s, ++yslot) {
       if (warp < bw) {
-        float* ycol = cols + (int64_t)(bw + (warp + s) % bw) * ld;
+        if (yslot >= bw) yslot -= bw;
+        float* ycol = cols + (bw + yslot) * ld;
         if (NV > 0) {
           float4 y[N];
           load_col<N>(ycol, ld, lane, y);
@@ -166,8 +180,8 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, int kind, 
         const int h = warp / half, q = warp - h * half;
         int p0, p1;
         rr_pair(bw, r, q, p0, p1);
-        float* xcol = cols + (int64_t)(h * bw + (p0 < p1 ? p0 : p1)) * ld;
-        float* ycol = cols + (int64_t)(h * bw + (p0 < p1 ? p1 : p0)) * ld;
+        float* xcol = cols + (h * bw + (p0 < p1 ? p0 : p1)) * ld;
+        float* ycol = cols + (h * bw + (p0 < p1 ? p1 : p0)) * ld;
         if (NV > 0) {
           float4 x[N], y[N];
           load_col<N>(xcol, ld, lane, x);

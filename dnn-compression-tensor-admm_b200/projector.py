@@ -341,3 +341,238 @@ class TTProjectionPlan:
         out.append(last.t[:L.ranks[L.d - 1] * L.shapes[L.d - 1] * L.ranks[L.d]]
                    .view(L.ranks[L.d - 1], L.shapes[L.d - 1], L.ranks[L.d]))
         return out
+
+
+# ==================================================================================================
+# Tucker-2 (HOOI) projection                                   admm.py:113-127 -> tensorly partial_tucker
+# ==================================================================================================
+class EigBatch:
+    """Gram -> Jacobi -> fp64 refinement -> dominant-r selection for a list of independent problems.
+
+    Each problem: dict(a=ptr, k=, r=, si=, sb=, sc=, nb=, nc=) describing the Gram operand as in
+    include/tta.h (tta_gram_task); outputs E (r x k, rows = dominant eigenvectors) and optionally ET.
+    """
+
+    def __init__(self, device, tol=5e-7, max_sweeps=40):
+        self.device = device
+        self.tol = tol
+        self.max_sweeps = max_sweeps
+        self.bufs = {}
+        self.tables = {}
+
+    def buffers(self, key, k, r, red_len, want_et):
+        if key in self.bufs:
+            return self.bufs[key]
+        dev = self.device
+        ld, kpad, bw = eig_geometry(k)
+        nsplit = gram_splits(k, red_len)
+        f64 = torch.float64
+        b = dict(k=k, r=r, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, X=_Buf(ld * kpad, dev),
+                 part=_Buf(nsplit * k * k, dev, f64), E=_Buf(r * k, dev),
+                 ET=_Buf(r * k, dev) if want_et else None,
+                 g64=_Buf(k * k, dev, f64), qt=_Buf(k * k, dev, f64), y=_Buf(k * k, dev, f64),
+                 s=_Buf(k * k, dev, f64), t=_Buf(k * k, dev, f64), c=_Buf(r * k, dev, f64),
+                 e64=_Buf(r * k, dev, f64), lam=_Buf(r, dev, f64))
+        self.bufs[key] = b
+        return b
+
+    def build(self, sig, problems):
+        """problems: list of (bufs, gram operand dict).  Cached by `sig` (hashable)."""
+        if sig in self.tables:
+            return self.tables[sig]
+        dev = self.device
+        n = len(problems)
+        g = np.zeros(n, dtype=rt.GRAM_TASK)
+        e = np.zeros(n, dtype=rt.EIG_TASK)
+        rf = np.zeros(n, dtype=rt.REFINE_TASK)
+        dg = [np.zeros(n, dtype=rt.GEMM_TASK) for _ in range(4)]
+        for q, (b, op) in enumerate(problems):
+            k, r = b['k'], b['r']
+            g[q] = (op['a'], b['part'].ptr, b['X'].ptr, b['g64'].ptr, op['si'], op['sb'], op['sc'], k,
+                    op['nb'], op['nc'], b['nsplit'], b['ld'], b['kpad'])
+            e[q] = (b['X'].ptr, k, b['ld'], b['kpad'], b['bw'])
+            rf[q] = (b['X'].ptr, b['qt'].ptr, b['s'].ptr, b['t'].ptr, b['c'].ptr, b['lam'].ptr, b['e64'].ptr,
+                     b['E'].ptr, b['ET'].ptr if b['ET'] is not None else 0, 0, 0, 0, k, b['ld'], r, 0)
+            qt = b['qt'].ptr
+            dg[0][q] = (qt, b['g64'].ptr, b['y'].ptr, 0, k, 1, k, 1, k, k, k, k, 0)
+            dg[1][q] = (b['y'].ptr, qt, b['s'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)
+            dg[2][q] = (qt, qt, b['t'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)
+            dg[3][q] = (b['c'].ptr, qt, b['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)
+        tabs = dict(gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev), refine=rt.TaskTable(rf, dev),
+                    d_yt=rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev), d_s=rt.TaskTable(dg[1], dev),
+                    d_e=rt.TaskTable(dg[3], dev))
+        nbytes = rt.jacobi_scratch_bytes(tabs['eig'])
+        tabs['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
+        self.tables[sig] = tabs
+        return tabs
+
+    def run(self, tabs):
+        rt.gram(tabs['gram'])
+        sweeps = rt.jacobi_eigh(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
+        rt.refine_prepare(tabs['refine'])
+        rt.gemm_f64(tabs['d_yt'])
+        rt.gemm_f64(tabs['d_s'])
+        rt.refine_coeff(tabs['refine'])
+        rt.gemm_f64(tabs['d_e'])
+        rt.refine_finalize(tabs['refine'])
+        return sweeps
+
+
+class TKLayer:
+    """Tucker-2 projection of a conv (O, I, kh, kw) or linear (O, I) weight on modes (0, 1).
+
+    ranks = [r_out, r_in] as in hp_dicts/tk_*.py (admm.py:115,123 pass them as `rank=`).
+    """
+
+    def __init__(self, name, weight_shape, ranks):
+        self.name = name
+        self.weight_shape = tuple(int(v) for v in weight_shape)
+        if len(self.weight_shape) == 4:
+            self.O, self.I, self.KK = self.weight_shape[0], self.weight_shape[1], self.weight_shape[2] * self.weight_shape[3]
+        elif len(self.weight_shape) == 2:
+            self.O, self.I, self.KK = self.weight_shape[0], self.weight_shape[1], 1
+        else:
+            raise Exception('ERROR: unsupported layer in ADMM!')
+        self.numel = self.O * self.I * self.KK
+        if isinstance(ranks, int) or len(ranks) != 2:
+            raise ValueError('Tucker-2 needs ranks [r_out, r_in] for {}'.format(name))
+        self.r0, self.r1 = min(int(ranks[0]), self.O), min(int(ranks[1]), self.I)
+
+
+class TKProjectionPlan:
+    """Batched Tucker-2 HOOI projection: HOSVD initialisation + alternating sweeps with tensorly's
+    stopping rule (`iteration > 1 and |err[-2] - err[-1]| < tol`, n_iter_max = 100, tol = 1e-4), every
+    layer stopping at its own sweep.  All contractions are plain 2-D GEMMs / Grams because the
+    tensor is kept in the (O, KK, I) layout produced by the unfold kernel:
+
+        mode-1 products contract the fastest index   (O*KK x I) . E1^T
+        mode-0 products contract the slowest index   E0 . (O x KK*I)
+    """
+
+    def __init__(self, layers, device, tol=5e-7, max_sweeps=40, n_iter_max=100, hooi_tol=10e-5):
+        self.layers = list(layers)
+        self.device = torch.device(device)
+        self.n_iter_max = int(n_iter_max)
+        self.hooi_tol = float(hooi_tol)
+        self.eig = EigBatch(self.device, tol, max_sweeps)
+        self.sweeps = {}
+        self.hooi_sweeps = {}
+        self.errors = {}
+        self.profile = None
+        self._bound = None
+        dev = self.device
+        self.ws = []
+        for li, L in enumerate(self.layers):
+            O, I, KK, r0, r1 = L.O, L.I, L.KK, L.r0, L.r1
+            w = dict(T=_Buf(L.numel, dev), P0=_Buf(O * KK * r1, dev), P1=_Buf(r0 * KK * I, dev),
+                     core=_Buf(r0 * KK * r1, dev), tmp=_Buf(r0 * KK * I, dev), ZT=_Buf(L.numel, dev))
+            w['e0'] = self.eig.buffers((li, 0), O, r0, max(KK * I, O), False)
+            w['e1'] = self.eig.buffers((li, 1), I, r1, max(O * KK, I), False)
+            self.ws.append(w)
+        self.norms = torch.zeros(2 * max(len(self.layers), 1), dtype=torch.float64, device=dev)
+
+    # -- static per-layer task rows ---------------------------------------------------------------
+    def bind(self, w_list, u_list, z_list):
+        key = tuple((w.data_ptr(), (u.data_ptr() if u is not None else 0), z.data_ptr())
+                    for w, u, z in zip(w_list, u_list, z_list))
+        if key == self._bound:
+            return
+        for t in list(w_list) + [u for u in u_list if u is not None] + list(z_list):
+            rt.require_device(t)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise rt.TtaError('W/U/Z must be contiguous fp32 tensors')
+        n = len(self.layers)
+        self.row = dict(unfold=np.zeros(n, dtype=rt.FOLD_TASK), fold=np.zeros(n, dtype=rt.FOLD_TASK),
+                        p0=np.zeros(n, dtype=rt.GEMM_TASK), p1=np.zeros(n, dtype=rt.GEMM_TASK),
+                        core=np.zeros(n, dtype=rt.GEMM_TASK), rec1=np.zeros(n, dtype=rt.GEMM_TASK),
+                        rec2=np.zeros(n, dtype=rt.GEMM_TASK), nx=np.zeros(n, dtype=rt.SQNORM_TASK),
+                        nc=np.zeros(n, dtype=rt.SQNORM_TASK))
+        self.gram_ops = []
+        for li, (L, w) in enumerate(zip(self.layers, self.ws)):
+            O, I, KK, r0, r1 = L.O, L.I, L.KK, L.r0, L.r1
+            T, E0, E1 = w['T'].ptr, w['e0']['E'].ptr, w['e1']['E'].ptr
+            up = u_list[li].data_ptr() if u_list[li] is not None else 0
+            self.row['unfold'][li] = (w_list[li].data_ptr(), up, T, 0, O, I, KK, 0)
+            self.row['fold'][li] = (0, 0, w['ZT'].ptr, z_list[li].data_ptr(), O, I, KK, 0)
+            # P0 (O*KK x r1) = T (O*KK x I) . E1^T          [B(k=i, j) = E1[j, i]]
+            self.row['p0'][li] = (T, E1, w['P0'].ptr, 0, I, 1, 1, I, r1, O * KK, r1, I, 0)
+            # P1 (r0 x KK*I) = E0 (r0 x O) . T (O x KK*I)
+            self.row['p1'][li] = (E0, T, w['P1'].ptr, 0, O, 1, KK * I, 1, KK * I, r0, KK * I, O, 0)
+            # core (r0*KK x r1) = P1 (r0*KK x I) . E1^T
+            self.row['core'][li] = (w['P1'].ptr, E1, w['core'].ptr, 0, I, 1, 1, I, r1, r0 * KK, r1, I, 0)
+            # tmp (r0*KK x I) = core (r0*KK x r1) . E1 (r1 x I)
+            self.row['rec1'][li] = (w['core'].ptr, E1, w['tmp'].ptr, 0, r1, 1, I, 1, I, r0 * KK, I, r1, 0)
+            # ZT (O x KK*I) = E0^T (O x r0) . tmp (r0 x KK*I)       [A(i, k) = E0[k, i]]
+            self.row['rec2'][li] = (E0, w['tmp'].ptr, w['ZT'].ptr, 0, 1, O, KK * I, 1, KK * I, O, KK * I, r0, 0)
+            self.row['nx'][li] = (T, L.numel)
+            self.row['nc'][li] = (w['core'].ptr, r0 * KK * r1)
+            self.gram_ops.append(dict(
+                init0=dict(a=T, si=KK * I, sb=0, sc=1, nb=1, nc=KK * I),            # unfold_0(X) rows
+                init1=dict(a=T, si=1, sb=0, sc=I, nb=1, nc=O * KK),                  # columns of (O*KK x I)
+                sweep0=dict(a=w['P0'].ptr, si=KK * r1, sb=0, sc=1, nb=1, nc=KK * r1),
+                sweep1=dict(a=w['P1'].ptr, si=1, sb=0, sc=I, nb=1, nc=r0 * KK)))
+        self._tab_cache = {}
+        self.eig.tables = {}
+        self._bound = key
+
+    def _tab(self, kind, active):
+        key = (kind, active)
+        if key not in self._tab_cache:
+            self._tab_cache[key] = rt.TaskTable(self.row[kind][list(active)], self.device)
+        return self._tab_cache[key]
+
+    def _eig_tabs(self, which, active):
+        mode = 0 if which in ('init0', 'sweep0') else 1
+        probs = [(self.ws[li]['e%d' % mode], self.gram_ops[li][which]) for li in active]
+        return self.eig.build((which, active), probs)
+
+    def run(self, w_list, u_list, z_list):
+        self.bind(w_list, u_list, z_list)
+        n = len(self.layers)
+        everyone = tuple(range(n))
+        ph = _Phases(self.profile)
+        ph.mark('unfold')
+        rt.unfold_add(self._tab('unfold', everyone))
+        self.norms.zero_()
+        rt.sqnorm(self._tab('nx', everyone), self.norms[:n])
+        ph.mark('hosvd')
+        # HOSVD initialisation: both factor problems of every layer in one eigensolver batch
+        probs = [(self.ws[li]['e0'], self.gram_ops[li]['init0']) for li in everyone] + \
+                [(self.ws[li]['e1'], self.gram_ops[li]['init1']) for li in everyone]
+        sw = self.eig.run(self.eig.build(('init', everyone), probs))
+        jac = {L.name: [int(sw[i]), int(sw[n + i])] for i, L in enumerate(self.layers)}
+        norm_x2 = self.norms[:n].cpu().numpy().copy()
+        errs = [[] for _ in range(n)]
+        active = everyone
+        it = 0
+        ph.mark('hooi')
+        while active and it < self.n_iter_max:
+            rt.gemm(self._tab('p0', active))
+            s0 = self.eig.run(self._eig_tabs('sweep0', active))
+            rt.gemm(self._tab('p1', active))
+            s1 = self.eig.run(self._eig_tabs('sweep1', active))
+            rt.gemm(self._tab('core', active))
+            out = self.norms[n:n + len(active)]
+            out.zero_()
+            rt.sqnorm(self._tab('nc', active), out)
+            norm_c2 = out.cpu().numpy()
+            stop = []
+            for q, li in enumerate(active):
+                jac[self.layers[li].name] += [int(s0[q]), int(s1[q])]
+                nx = math.sqrt(float(norm_x2[li]))
+                err = math.sqrt(abs(float(norm_x2[li]) - float(norm_c2[q]))) / nx if nx > 0 else 0.0
+                errs[li].append(err)
+                if (it > 1 and abs(errs[li][-2] - errs[li][-1]) < self.hooi_tol) or it == self.n_iter_max - 1:
+                    stop.append(li)
+            if stop:
+                stop = tuple(stop)
+                rt.gemm(self._tab('rec1', stop))
+                rt.gemm(self._tab('rec2', stop))
+                rt.fold_store(self._tab('fold', stop))
+                for li in stop:
+                    self.hooi_sweeps[self.layers[li].name] = it + 1
+                active = tuple(li for li in active if li not in stop)
+            it += 1
+        ph.finish()
+        self.sweeps = jac
+        self.errors = {L.name: errs[i] for i, L in enumerate(self.layers)}
