@@ -86,14 +86,15 @@ __global__ void __launch_bounds__(kJacThreads) jacobi_step_kernel(const JacItem*
   __syncthreads();
 
   const float fl = floor2[it.prob];
+  float* nrm = cols + 2 * bw * ld;     // cached squared norms (2*bw floats behind the columns)
   int nrot;
   const int nv = (ld + 127) >> 7;
   switch (nv) {
-    case 1: nrot = jacobi_block<1>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
-    case 2: nrot = jacobi_block<2>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
-    case 3: nrot = jacobi_block<3>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
-    case 4: nrot = jacobi_block<4>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
-    default: nrot = jacobi_block<0>(cols, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    case 1: nrot = jacobi_block<1>(cols, nrm, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    case 2: nrot = jacobi_block<2>(cols, nrm, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    case 3: nrot = jacobi_block<3>(cols, nrm, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    case 4: nrot = jacobi_block<4>(cols, nrm, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
+    default: nrot = jacobi_block<0>(cols, nrm, it.kind, nblk, bw, ld, warp, lane, tol2, fl); break;
   }
   if (lane == 0 && nrot) atomicAdd(&s_rot, nrot);
   __syncthreads();
@@ -257,7 +258,7 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
       return TTA_E_INVALID;
     }
     ++n_legacy;
-    const size_t need = (size_t)2 * tk.bw * tk.ld * sizeof(float);
+    const size_t need = (size_t)2 * tk.bw * (tk.ld + 1) * sizeof(float);
     smem = need > smem ? need : smem;
   }
   if (smem > 227 * 1024) {

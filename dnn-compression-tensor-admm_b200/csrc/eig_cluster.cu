@@ -59,6 +59,7 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
   const int64_t blk = (int64_t)bw * ld;            // floats per block
   float* top = cols;
   float* bot = cols + blk;
+  float* nrm = cols + 2 * blk;                     // cached squared norms of the 2*bw resident columns
 
   // block slots in global X: top row 0..P-1, bottom row P..2P-1
   cl_copy_block(top, tk.x + (int64_t)c * blk, blk4, tid, nthreads, true);
@@ -77,9 +78,9 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
   if (tid == 0) printf("[cl] blk %d P %d c %d prob %d bw %d ld %d top_dst %d bot_dst %d\n", (int)blockIdx.x, P, c, prob, bw, ld, top_dst, bot_dst);
 #endif
   while (sweep < max_sweeps) {
-    int nrot = jacobi_block<NV>(cols, 0, 2, bw, ld, warp, lane, tol2, fl);     // pairs inside both blocks
+    int nrot = jacobi_block<NV>(cols, nrm, 0, 2, bw, ld, warp, lane, tol2, fl);     // pairs inside both blocks
     for (int round = 0; round < 2 * P - 1; ++round) {
-      nrot += jacobi_block<NV>(cols, 1, 2, bw, ld, warp, lane, tol2, fl);      // top x bottom pairs
+      nrot += jacobi_block<NV>(cols, nrm, 1, 2, bw, ld, warp, lane, tol2, fl);      // top x bottom pairs
       if (P > 1) {
         // jacobi_block ends with __syncthreads(): shared columns are final for this round
         if (c != 0) cl_copy_block(tk.x + (int64_t)top_dst * blk, top, blk4, tid, nthreads, false);
@@ -230,7 +231,7 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
   }
   size_t smem_all = 0;
   for (int p : probs) {
-    const size_t need = (size_t)2 * th[p].bw * th[p].ld * sizeof(float);
+    const size_t need = (size_t)2 * th[p].bw * (th[p].ld + 1) * sizeof(float);
     smem_all = need > smem_all ? need : smem_all;
   }
   rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -248,7 +249,7 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
     size_t smem = 0;
     int bwmax = 2;
     for (int p : grouped[g]) {
-      const size_t need = (size_t)2 * th[p].bw * th[p].ld * sizeof(float);
+      const size_t need = (size_t)2 * th[p].bw * (th[p].ld + 1) * sizeof(float);
       smem = need > smem ? need : smem;
       bwmax = th[p].bw > bwmax ? th[p].bw : bwmax;
     }

@@ -33,15 +33,15 @@ __device__ __forceinline__ float mufu_rsqrt(float x) {  // single MUFU.RSQ
   return r;
 }
 
+// t = tan(theta) is returned too: the squared norms after the rotation are a - t*c and b + t*c.
 __device__ __forceinline__ bool jacobi_params(float a, float b, float c, float tol2, float floor2, float& sn,
-                                              float& tau) {
+                                              float& tau, float& t) {
   if (!(a > floor2) || !(b > floor2)) return false;
   if (!(c * c > (tol2 * a) * b)) return false;
   const float zeta = (b - a) * mufu_rcp(2.f * c);
   const float h = fmaf(zeta, zeta, 1.f);
   // |zeta| < ~1e15 here (c passed the threshold test), so h is finite and rsqrt is safe
-  float t = mufu_rcp(fabsf(zeta) + h * mufu_rsqrt(h));
-  t = copysignf(t, zeta);
+  t = copysignf(mufu_rcp(fabsf(zeta) + h * mufu_rsqrt(h)), zeta);
   const float cs = mufu_rsqrt(fmaf(t, t, 1.f));
   sn = cs * t;
   tau = sn * mufu_rcp(1.f + cs);
@@ -54,6 +54,16 @@ __device__ __forceinline__ bool jacobi_params(float a, float b, float c, float t
 __device__ __forceinline__ void rot2(float sn, float tau, float x, float y, float& xn, float& yn) {
   xn = fmaf(-sn, fmaf(tau, x, y), x);
   yn = fmaf(sn, fmaf(-tau, y, x), y);
+}
+
+// Blackwell packed fp32 FMA (FFMA2): two lanes of d = a*b + c per instruction.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
 }
 
 template <int NV>
@@ -74,40 +84,46 @@ __device__ __forceinline__ void store_col(float* __restrict__ col, int ld, int l
   }
 }
 
-// One column pair held in registers (NV float4 per lane per column).  Returns 1 if rotated.
+// warp-wide inner product of two register-resident columns (every lane gets the result)
+template <int NV>
+__device__ __forceinline__ float dot_regs(const float4 (&x)[NV], const float4 (&y)[NV]) {
+  float2 p = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    p = ffma2(make_float2(x[j].x, x[j].y), make_float2(y[j].x, y[j].y), p);
+    q = ffma2(make_float2(x[j].z, x[j].w), make_float2(y[j].z, y[j].w), q);
+  }
+  float c = (p.x + p.y) + (q.x + q.y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  return c;
+}
+
+// One column pair held in registers (NV float4 per lane per column) with cached squared norms a, b
+// (recomputed exactly at the start of every block round, then updated as a - t*c / b + t*c): only the
+// cross product needs a reduction in the step's critical path.  Returns 1 if rotated.
 // (No de Rijk column swap: with the parallel tournament orderings used here, moving the larger
 // column to `x` makes pairs chase each other across blocks and the sweep count explodes.)
 template <int NV>
-__device__ __forceinline__ int rotate_regs(float4 (&x)[NV], float4 (&y)[NV], float tol2, float floor2) {
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f;
+__device__ __forceinline__ int rotate_regs(float4 (&x)[NV], float4 (&y)[NV], float& a, float& b, float tol2,
+                                           float floor2) {
+  const float c = dot_regs<NV>(x, y);
+  float sn, tau, t;
+  if (!jacobi_params(a, b, c, tol2, floor2, sn, tau, t)) return 0;
+  const float2 sp = make_float2(sn, sn), sm = make_float2(-sn, -sn);
+  const float2 tp = make_float2(tau, tau), tm = make_float2(-tau, -tau);
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    a0 = fmaf(x[j].x, x[j].x, a0); a1 = fmaf(x[j].y, x[j].y, a1);
-    b0 = fmaf(y[j].x, y[j].x, b0); b1 = fmaf(y[j].y, y[j].y, b1);
-    c0 = fmaf(x[j].x, y[j].x, c0); c1 = fmaf(x[j].y, y[j].y, c1);
-    a0 = fmaf(x[j].z, x[j].z, a0); a1 = fmaf(x[j].w, x[j].w, a1);
-    b0 = fmaf(y[j].z, y[j].z, b0); b1 = fmaf(y[j].w, y[j].w, b1);
-    c0 = fmaf(x[j].z, y[j].z, c0); c1 = fmaf(x[j].w, y[j].w, c1);
+    const float2 x0 = make_float2(x[j].x, x[j].y), x1 = make_float2(x[j].z, x[j].w);
+    const float2 y0 = make_float2(y[j].x, y[j].y), y1 = make_float2(y[j].z, y[j].w);
+    const float2 xn0 = ffma2(sm, ffma2(tp, x0, y0), x0), xn1 = ffma2(sm, ffma2(tp, x1, y1), x1);
+    const float2 yn0 = ffma2(sp, ffma2(tm, y0, x0), y0), yn1 = ffma2(sp, ffma2(tm, y1, x1), y1);
+    x[j] = make_float4(xn0.x, xn0.y, xn1.x, xn1.y);
+    y[j] = make_float4(yn0.x, yn0.y, yn1.x, yn1.y);
   }
-  float a = a0 + a1, b = b0 + b1, c = c0 + c1;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {   // three interleaved butterflies
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-    c += __shfl_xor_sync(0xffffffffu, c, o);
-  }
-  float sn, tau;
-  if (!jacobi_params(a, b, c, tol2, floor2, sn, tau)) return 0;
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    float4 xn, yn;
-    rot2(sn, tau, x[j].x, y[j].x, xn.x, yn.x);
-    rot2(sn, tau, x[j].y, y[j].y, xn.y, yn.y);
-    rot2(sn, tau, x[j].z, y[j].z, xn.z, yn.z);
-    rot2(sn, tau, x[j].w, y[j].w, xn.w, yn.w);
-    x[j] = xn;
-    y[j] = yn;
-  }
+  const float d = t * c;
+  a = fmaxf(a - d, 0.f);
+  b = fmaxf(b + d, 0.f);
   return 1;
 }
 
@@ -125,8 +141,8 @@ __device__ __forceinline__ int rotate_smem(float* __restrict__ x, float* __restr
   a = warp_sum(a);
   b = warp_sum(b);
   c = warp_sum(c);
-  float sn, tau;
-  if (!jacobi_params(a, b, c, tol2, floor2, sn, tau)) return 0;
+  float sn, tau, t;
+  if (!jacobi_params(a, b, c, tol2, floor2, sn, tau, t)) return 0;
   for (int e = lane * 4; e < ld; e += 128) {
     const float4 xv = *reinterpret_cast<const float4*>(x + e);
     const float4 yv = *reinterpret_cast<const float4*>(y + e);
@@ -141,18 +157,28 @@ __device__ __forceinline__ int rotate_smem(float* __restrict__ x, float* __restr
   return 1;
 }
 
-// All pair rotations of one staged block pair.  NV > 0: register-resident columns (ld <= 128*NV).
+// All pair rotations of one staged block pair.  NV > 0: register-resident columns (ld <= 128*NV) with
+// cached squared norms in `nrm` (2*bw floats of shared memory behind the columns).
 template <int NV>
-__device__ __forceinline__ int jacobi_block(float* __restrict__ cols, int kind, int nblk, int bw, int ld, int warp,
-                                            int lane, float tol2, float fl) {
+__device__ __forceinline__ int jacobi_block(float* __restrict__ cols, float* __restrict__ nrm, int kind, int nblk,
+                                            int bw, int ld, int warp, int lane, float tol2, float fl) {
   constexpr int N = NV > 0 ? NV : 1;
   int nrot = 0;
   if (kind == 1) {
     // cross pairs: warp w keeps column w of block A in registers for the whole block step and meets
     // column (w+s)%bw of block B at step s (disjoint pairs within a step).
     float4 x[N];
+    float xa = 0.f;
     float* xcol = cols + warp * ld;
-    if (NV > 0 && warp < bw) load_col<N>(xcol, ld, lane, x);
+    if (NV > 0 && warp < bw) {
+      load_col<N>(xcol, ld, lane, x);
+      xa = dot_regs<N>(x, x);
+      float4 y[N];
+      load_col<N>(cols + (bw + warp) * ld, ld, lane, y);
+      const float yb = dot_regs<N>(y, y);
+      if (lane == 0) nrm[bw + warp] = yb;
+    }
+    if (NV > 0) __syncthreads();
     int yslot = warp;                       // (warp + s) % bw without the integer division
     for (int s = 0; s < bw; ++s, ++yslot) {
       if (warp < bw) {
@@ -161,8 +187,10 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, int kind, 
         if (NV > 0) {
           float4 y[N];
           load_col<N>(ycol, ld, lane, y);
-          if (rotate_regs<N>(x, y, tol2, fl)) {
+          float yb = nrm[bw + yslot];
+          if (rotate_regs<N>(x, y, xa, yb, tol2, fl)) {
             store_col<N>(ycol, ld, lane, y);
+            if (lane == 0) nrm[bw + yslot] = yb;
             ++nrot;
           }
         } else {
@@ -175,20 +203,35 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, int kind, 
     __syncthreads();   // the block in shared memory is complete for every reader after this point
   } else {
     const int half = bw >> 1;
+    if (NV > 0) {
+      for (int col = warp; col < nblk * bw; col += (int)(blockDim.x >> 5)) {
+        float4 v[N];
+        load_col<N>(cols + col * ld, ld, lane, v);
+        const float vv = dot_regs<N>(v, v);
+        if (lane == 0) nrm[col] = vv;
+      }
+      __syncthreads();
+    }
     for (int r = 0; r < bw - 1; ++r) {
       if (warp < half * nblk) {
         const int h = warp / half, q = warp - h * half;
         int p0, p1;
         rr_pair(bw, r, q, p0, p1);
-        float* xcol = cols + (h * bw + (p0 < p1 ? p0 : p1)) * ld;
-        float* ycol = cols + (h * bw + (p0 < p1 ? p1 : p0)) * ld;
+        const int xi = h * bw + (p0 < p1 ? p0 : p1), yi = h * bw + (p0 < p1 ? p1 : p0);
+        float* xcol = cols + xi * ld;
+        float* ycol = cols + yi * ld;
         if (NV > 0) {
           float4 x[N], y[N];
           load_col<N>(xcol, ld, lane, x);
           load_col<N>(ycol, ld, lane, y);
-          if (rotate_regs<N>(x, y, tol2, fl)) {
+          float xa = nrm[xi], yb = nrm[yi];
+          if (rotate_regs<N>(x, y, xa, yb, tol2, fl)) {
             store_col<N>(xcol, ld, lane, x);
             store_col<N>(ycol, ld, lane, y);
+            if (lane == 0) {
+              nrm[xi] = xa;
+              nrm[yi] = yb;
+            }
             ++nrot;
           }
         } else {
@@ -200,7 +243,6 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, int kind, 
   }
   return nrot;
 }
-
 
 // host-side entry of the cluster solver (eig_cluster.cu)
 bool jacobi_cluster_eligible(const tta_eig_task& tk);
