@@ -226,8 +226,13 @@ class TTProjectionPlan:
         self.t_unfold = rt.TaskTable(unfold, dev)
 
         self.waves = []
-        for i in range(self.max_order() - 1):
-            idx = [li for li, L in enumerate(self.layers) if L.d - 1 > i]
+        # Wave w runs TT step (w - offset_l) of layer l.  Layers with fewer steps are centred in the wave
+        # sequence so that their big eigenproblems (k = O of a 1x1 conv) share a wave with the big
+        # middle steps of the k x k convs instead of adding a wave-long critical path of their own.
+        nwaves = self.max_order() - 1
+        offset = [(nwaves - (L.d - 1)) // 2 for L in self.layers]
+        for wv in range(nwaves):
+            idx = [li for li, L in enumerate(self.layers) if 0 <= wv - offset[li] < L.d - 1]
             g = np.zeros(len(idx), dtype=rt.GRAM_TASK)
             e = np.zeros(len(idx), dtype=rt.EIG_TASK)
             s = np.zeros(len(idx), dtype=rt.SELECT_TASK)
@@ -235,7 +240,7 @@ class TTProjectionPlan:
             rf = np.zeros(len(idx), dtype=rt.REFINE_TASK)
             dg = [np.zeros(len(idx), dtype=rt.GEMM_TASK) for _ in range(4)]
             for q, li in enumerate(idx):
-                st = self.ws[li]['steps'][i]
+                st = self.ws[li]['steps'][wv - offset[li]]
                 m, n, k, r = st['m'], st['n'], st['k'], st['r']
                 a = st['A'].ptr
                 g64 = st['g64'].ptr if self.refine else 0
