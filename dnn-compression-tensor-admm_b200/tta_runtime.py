@@ -48,7 +48,7 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
            'tta_jacobi_scratch_bytes', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
-           'tta_refine_finalize_batched']
+           'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16']
 
 
 class TtaError(RuntimeError):
@@ -106,6 +106,10 @@ def _load():
     for nm in ('tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
                'tta_refine_finalize_batched'):
         getattr(lib, nm).argtypes = [vp, vp, ci, vp]
+    i64 = ctypes.c_int64
+    lib.tta_gemm_bf16_tc.argtypes = [vp, i64, vp, i64, vp, i64, ci, ci, ci, vp, ci, vp]
+    lib.tta_small_gemm.argtypes = [vp, ci, vp, vp, ci, vp, i64, ci, ci, i64, i64, i64, i64, i64, i64, vp]
+    lib.tta_cast_bf16.argtypes = [vp, vp, i64, vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch'):
@@ -240,6 +244,29 @@ def refine_coeff(tab):
 def refine_finalize(tab):
     _check(lib().tta_refine_finalize_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()),
            'tta_refine_finalize_batched')
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def gemm_bf16_tc(a, b, c, M, N, K, lda=None, ldb=None, ldc=None, bias=None):
+    """c[M,N] = a[M,K] @ b[N,K]^T (+bias) on tcgen05; a, b bf16 tensors, c bf16 or fp32."""
+    _check(lib().tta_gemm_bf16_tc(_p(a), lda if lda is not None else K, _p(b), ldb if ldb is not None else K, _p(c),
+                                  ldc if ldc is not None else N, int(M), int(N), int(K), _p(bias),
+                                  int(c.dtype == torch.float32), stream_handle()), 'tta_gemm_bf16_tc')
+
+
+def small_gemm(a, b, c, M, N, K, m_inner=None, s_outer=None, s_inner=0, s_col=1, bias=None, bias_inner=0, bias_col=1):
+    if m_inner is None:
+        m_inner, s_outer, s_inner = 1, N, 0
+    _check(lib().tta_small_gemm(_p(a), int(a.dtype == torch.float32), _p(b), _p(c), int(c.dtype == torch.float32),
+                                _p(bias), int(M), int(N), int(K), int(m_inner), int(s_outer), int(s_inner), int(s_col),
+                                int(bias_inner), int(bias_col), stream_handle()), 'tta_small_gemm')
+
+
+def cast_bf16(x, y):
+    _check(lib().tta_cast_bf16(_p(x), _p(y), x.numel(), stream_handle()), 'tta_cast_bf16')
 
 
 def launch_count():

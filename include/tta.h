@@ -222,6 +222,24 @@ typedef struct {
 int tta_sqnorm_batched(const tta_sqnorm_task* tasks_dev, const tta_sqnorm_task* tasks_host,
                        int n_tasks, double* out_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Decomposed-layer forward building blocks (TTLinear.py:75-93, TTConv.py:130-153): bf16 operands,
+ * fp32 accumulation.  Single-problem calls (one layer at a time, as the modules' forward() runs).
+ * ------------------------------------------------------------------------------------------- */
+/* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) on the tcgen05 tensor cores.  A, B bf16 K-major (leading
+ * dimensions lda, ldb in elements), C bf16 (out_fp32 == 0) or fp32, row-major with leading dim ldc.
+ * K, lda, ldb multiples of 8; A, B 16-byte aligned. */
+int tta_gemm_bf16_tc(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int M,
+                     int N, int K, const float* bias, int out_fp32, void* stream);
+/* Skinny contraction (K, N <= 96), one thread per row: C(i, j) = sum_k A[i*K + k] * B[j*K + k], stored at
+ * c + (i / m_inner) * s_outer + (i % m_inner) * s_inner + j * s_col, plus
+ * bias[(i % m_inner) * bias_inner + j * bias_col] when bias != NULL.  A is fp32 or bf16, B bf16. */
+int tta_small_gemm(const void* a, int a_is_f32, const void* b_bf16, void* c, int c_is_f32, const float* bias,
+                   int64_t M, int N, int K, int64_t m_inner, int64_t s_outer, int64_t s_inner, int64_t s_col,
+                   int64_t bias_inner, int64_t bias_col, void* stream);
+/* y (bf16) = x (fp32), n elements */
+int tta_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

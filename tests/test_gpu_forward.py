@@ -1,0 +1,67 @@
+"""Decomposed-layer forward building blocks and drop-in layer modules on a B200.
+Tolerance (BASELINE.json north_star): forward outputs within 1e-2 relative error in bf16."""
+import numpy as np
+import pytest
+import torch
+
+import tta_runtime as rt
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+FWD_TOL = 1e-2
+
+
+def _rel(a, b):
+    a = a.double()
+    b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 64, 64), (256, 128, 128), (300, 320, 368), (1000, 1120, 320),
+                                   (128, 800, 256), (77, 23, 24), (4096, 352, 1344), (130, 129, 72)])
+@pytest.mark.parametrize('out_f32', [False, True])
+def test_tcgen05_gemm_matches_torch(M, N, K, out_f32):
+    g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    b = torch.randn(N, K, generator=g).to(DEV).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    c = torch.full((M, N), 7.0, device=DEV, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    rt.gemm_bf16_tc(a, b, c, M, N, K, bias=bias)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias
+    tol = 2e-6 * K if out_f32 else 6e-3          # fp32 out: accumulation order only; bf16 out: output rounding
+    assert _rel(c.float(), ref) <= tol, (_rel(c.float(), ref), tol)
+
+
+def test_tcgen05_gemm_strided_operands():
+    g = torch.Generator(device='cpu').manual_seed(5)
+    M, N, K = 512, 192, 96
+    a_full = torch.randn(M, K + 40, generator=g).to(DEV).to(torch.bfloat16)
+    b_full = torch.randn(N, K + 8, generator=g).to(DEV).to(torch.bfloat16)
+    c_full = torch.zeros(M, N + 16, device=DEV, dtype=torch.bfloat16)
+    rt.gemm_bf16_tc(a_full, b_full, c_full, M, N, K, lda=K + 40, ldb=K + 8, ldc=N + 16)
+    ref = a_full[:, :K].float() @ b_full[:, :K].float().t()
+    assert _rel(c_full[:, :N].float(), ref) <= 6e-3
+    assert float(c_full[:, N:].abs().max()) == 0.0
+
+
+def test_small_gemm_and_cast():
+    g = torch.Generator(device='cpu').manual_seed(6)
+    T, m1, r1, m0 = 50, 32, 35, 36
+    z = torch.randn(T * m1, r1, generator=g).to(DEV).to(torch.bfloat16)
+    core = torch.randn(m0, r1, generator=g).to(DEV).to(torch.bfloat16)
+    bias = torch.randn(m0 * m1, generator=g).to(DEV)
+    y = torch.zeros(T, m0 * m1, device=DEV)
+    # y[t, o0*m1 + o1] = sum_a z[(t,o1), a] core[o0, a] + bias[o0*m1 + o1]
+    rt.small_gemm(z, core, y, T * m1, m0, r1, m_inner=m1, s_outer=m0 * m1, s_inner=1, s_col=m1, bias=bias,
+                  bias_inner=1, bias_col=m1)
+    ref = torch.einsum('tia,oa->toi', z.float().view(T, m1, r1), core.float()).reshape(T, m0 * m1) + bias
+    assert _rel(y, ref) <= 1e-5
+    x = torch.randn(1000 * 16, 24, generator=g).to(DEV)
+    h = torch.randn(23, 24, generator=g).to(DEV).to(torch.bfloat16)
+    u = torch.zeros(1000 * 16, 23, device=DEV, dtype=torch.bfloat16)
+    rt.small_gemm(x, h, u, x.shape[0], 23, 24)
+    assert _rel(u.float(), x @ h.float().t()) <= 6e-3
+    xb = torch.empty(x.numel(), device=DEV, dtype=torch.bfloat16)
+    rt.cast_bf16(x.reshape(-1), xb)
+    assert torch.equal(xb, x.reshape(-1).to(torch.bfloat16))
