@@ -30,7 +30,8 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(kSgThreads) small_gemm_kernel(const TIn* __restrict__ A, const __nv_bfloat16* __restrict__ B,
                                                                 TOut* __restrict__ C, const float* __restrict__ bias,
-                                                                int64_t M, int N, int K, int64_t m_inner,
+                                                                int64_t M, int N, int K, int64_t a_inner,
+                                                                int64_t a_outer, int64_t m_inner,
                                                                 int64_t s_outer, int64_t s_inner, int64_t s_col,
                                                                 int64_t bias_inner, int64_t bias_col) {
   __shared__ float Bs[kSgMaxN * kSgMaxK];
@@ -38,7 +39,8 @@ __global__ void __launch_bounds__(kSgThreads) small_gemm_kernel(const TIn* __res
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * kSgThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kSgThreads) {
     float a[kSgMaxK];
-    const TIn* arow = A + i * K;
+    const int64_t ao = i / a_inner;
+    const TIn* arow = A + ao * a_outer + (i - ao * a_inner) * K;
 #pragma unroll 8
     for (int k = 0; k < K; ++k) a[k] = to_f32<TIn>(arow[k]);
     const int64_t io = i / m_inner, ii = i - io * m_inner;
@@ -71,13 +73,13 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 
 template <typename TIn, typename TOut>
 static int launch_small(const void* a, const void* b, void* c, const float* bias, int64_t M, int N, int K,
-                        int64_t m_inner, int64_t s_outer, int64_t s_inner, int64_t s_col, int64_t bias_inner,
+                        int64_t a_inner, int64_t a_outer, int64_t m_inner, int64_t s_outer, int64_t s_inner, int64_t s_col, int64_t bias_inner,
                         int64_t bias_col, cudaStream_t st) {
   int64_t blocks = (M + kSgThreads - 1) / kSgThreads;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   small_gemm_kernel<TIn, TOut><<<(int)blocks, kSgThreads, 0, st>>>(
       reinterpret_cast<const TIn*>(a), reinterpret_cast<const __nv_bfloat16*>(b), reinterpret_cast<TOut*>(c), bias, M, N,
-      K, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col);
+      K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col);
   TTA_CHECK_LAUNCH("small_gemm launch");
   return TTA_OK;
 }
@@ -87,22 +89,22 @@ static int launch_small(const void* a, const void* b, void* c, const float* bias
 extern "C" {
 
 int tta_small_gemm(const void* a, int a_is_f32, const void* b_bf16, void* c, int c_is_f32, const float* bias, int64_t M,
-                   int N, int K, int64_t m_inner, int64_t s_outer, int64_t s_inner, int64_t s_col, int64_t bias_inner,
-                   int64_t bias_col, void* stream) {
+                   int N, int K, int64_t a_inner, int64_t a_outer, int64_t m_inner, int64_t s_outer, int64_t s_inner,
+                   int64_t s_col, int64_t bias_inner, int64_t bias_col, void* stream) {
   using namespace tta;
   if (M <= 0) return TTA_OK;
-  if (!a || !b_bf16 || !c || N <= 0 || K <= 0 || N > kSgMaxN || K > kSgMaxK || m_inner <= 0) {
+  if (!a || !b_bf16 || !c || N <= 0 || K <= 0 || N > kSgMaxN || K > kSgMaxK || m_inner <= 0 || a_inner <= 0) {
     set_error("small_gemm: needs 0 < K <= %d, 0 < N <= %d (got N=%d K=%d)", kSgMaxK, kSgMaxN, N, K);
     return TTA_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (a_is_f32 && c_is_f32)
-    return launch_small<float, float>(a, b_bf16, c, bias, M, N, K, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
+    return launch_small<float, float>(a, b_bf16, c, bias, M, N, K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
   if (a_is_f32)
-    return launch_small<float, __nv_bfloat16>(a, b_bf16, c, bias, M, N, K, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
+    return launch_small<float, __nv_bfloat16>(a, b_bf16, c, bias, M, N, K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
   if (c_is_f32)
-    return launch_small<__nv_bfloat16, float>(a, b_bf16, c, bias, M, N, K, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
-  return launch_small<__nv_bfloat16, __nv_bfloat16>(a, b_bf16, c, bias, M, N, K, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
+    return launch_small<__nv_bfloat16, float>(a, b_bf16, c, bias, M, N, K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
+  return launch_small<__nv_bfloat16, __nv_bfloat16>(a, b_bf16, c, bias, M, N, K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, st);
 }
 
 int tta_cast_bf16(const float* x, void* y, int64_t n, void* stream) {

@@ -1,0 +1,226 @@
+"""Shared machinery of the decomposed-layer forwards (TTConv / TTLinear / TKConv / TKLinear drop-ins).
+
+Inference path (no autograd): activations are kept row-major over "rows" (tokens or pixels) in bf16,
+every contraction of a TT / Tucker chain is one kernel of libtta.so:
+
+  * big contractions (K or N > 96): `tta_gemm_bf16_tc` -- tcgen05 + TMEM tensor-core GEMM;
+  * skinny contractions (outer TT cores, K, N <= 96): `tta_small_gemm` (HBM-bound, one thread per row,
+    output written through a split-row address map so chains end in their final layout);
+  * k x k core convolution: `tta_im2col_bf16` + tensor-core GEMM.
+
+Weights are re-packed to bf16 (K padded to a multiple of 8, TT cores permuted so each chain step is a
+plain K-major GEMM) once and cached until a parameter's version counter changes.
+
+Training path (autograd enabled and something requires grad): the reference's own op chain restated
+with torch ops -- the fused backward is SURVEY 8(f) "next".
+"""
+from __future__ import annotations
+
+import torch
+
+import tta_runtime as rt
+
+SMALL_MAX = 96
+
+
+def pad8(n):
+    return (int(n) + 7) // 8 * 8
+
+
+def needs_autograd(x, params):
+    if not torch.is_grad_enabled():
+        return False
+    return x.requires_grad or any(p is not None and p.requires_grad for p in params)
+
+
+class Workspace:
+    """Zero-initialised scratch tensors cached by (tag, numel, dtype): padding columns are never
+    written by the producers, so they stay zero across calls."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, tag, numel, dtype, device):
+        key = (tag, int(numel), dtype, str(device))
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.zeros(int(numel), dtype=dtype, device=device)
+            self.bufs[key] = t
+        return t
+
+
+class PackedWeight:
+    """A (N x K) weight matrix cached as bf16 with row stride pad8(K) (zero padded)."""
+
+    def __init__(self, builder, params):
+        self.builder = builder
+        self.params = [p for p in params if p is not None]
+        self.key = None
+        self.mat = None
+        self.N = self.K = self.ld = 0
+
+    def get(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.params)
+        if key != self.key:
+            with torch.no_grad():
+                w = self.builder().detach().to(torch.float32)
+                n, k = w.shape
+                ld = pad8(k)
+                m = torch.zeros(n, ld, dtype=torch.bfloat16, device=w.device)
+                m[:, :k] = w.to(torch.bfloat16)
+            self.mat, self.N, self.K, self.ld, self.key = m, n, k, ld, key
+            self.small = m if ld == k else w.to(torch.bfloat16).contiguous()
+        return self
+
+
+def contract(a, M, K, w, out, *, a_inner=1, a_outer=None, lda=None, m_inner=1, s_outer=None, s_inner=0, s_col=1,
+             bias=None, bias_inner=0, bias_col=1):
+    """out = a (M rows of K) . w^T with the skinny or the tensor-core kernel.
+
+    Row i of `a` starts at (i // a_inner) * a_outer + (i % a_inner) * K (elements); result (i, j) goes to
+    (i // m_inner) * s_outer + (i % m_inner) * s_inner + j * s_col.
+    """
+    w = w.get()
+    assert w.K == K, (w.K, K)
+    N = w.N
+    if a_outer is None:
+        a_outer = lda if (lda is not None and a_inner == 1) else K * a_inner
+    if s_outer is None:
+        s_outer = N
+    plain_in = (a_inner == 1)
+    plain_out = (m_inner == 1 and s_col == 1 and s_inner == 0)
+    if K <= SMALL_MAX and N <= SMALL_MAX:
+        rt.small_gemm(a, w.small, out, M, N, K, m_inner=m_inner, s_outer=s_outer, s_inner=s_inner, s_col=s_col, bias=bias,
+                      bias_inner=bias_inner, bias_col=bias_col, a_inner=a_inner, a_outer=a_outer)
+        return
+    if not (plain_in and plain_out):
+        raise NotImplementedError('tensor-core contraction needs plain row-major operands (K={}, N={})'.format(K, N))
+    if a.dtype != torch.bfloat16:
+        raise NotImplementedError('tensor-core contraction needs a bf16 activation')
+    if a_outer % 8 or a_outer < w.ld:
+        raise NotImplementedError('activation row stride {} not usable with K padded to {}'.format(a_outer, w.ld))
+    # K is padded to w.ld: the activation's padding columns are zero by construction (Workspace)
+    rt.gemm_bf16_tc(a, w.mat, out, M, N, w.ld, lda=a_outer, ldb=w.ld, ldc=s_outer,
+                    bias=bias if bias_col == 1 and bias_inner == 0 else None)
+    if bias is not None and not (bias_col == 1 and bias_inner == 0):
+        raise NotImplementedError('bias map not supported on the tensor-core path')
+
+
+class TTRowsEngine:
+    """TT-matrix applied to row vectors: the in-core chain, an optional middle operator, the out-core
+    chain (TTLinear.py:79-88, TTConv.py:133-147), token-major.
+
+    in_cores[i]  : Parameter (rho_i, n_i, rho_{i+1}), rho_q = 1          (contracted last factor first)
+    out_cores[i] : Parameter (r_i, m_i, r_{i+1}),   r_0 = 1
+    Supports len(out_cores) <= 2 (all the reference's tables); otherwise the caller uses the op chain.
+    """
+
+    def __init__(self, in_cores, out_cores):
+        self.in_cores = list(in_cores)
+        self.out_cores = list(out_cores)
+        self.ws = Workspace()
+        self.w_in = [PackedWeight((lambda c=c: c.reshape(c.shape[0], -1)), [c]) for c in self.in_cores]
+        p = len(self.out_cores)
+        self.w_out = []
+        if p >= 1:
+            g0 = self.out_cores[0]
+            self.w_out.append(PackedWeight((lambda c=g0: c.reshape(c.shape[1], c.shape[2])), [g0]))      # (m_0 x r_1)
+        if p == 2:
+            g1 = self.out_cores[1]
+            self.w_out.append(PackedWeight((lambda c=g1: c.permute(1, 0, 2).reshape(-1, c.shape[2])), [g1]))  # ((o1,a1) x r_2)
+
+    def supported(self):
+        return len(self.out_cores) in (1, 2)
+
+    def in_chain(self, x, R, ldx, device):
+        """x: (R rows, row stride ldx) fp32 or bf16 -> (z, ld_z) with z (R x rho_0) bf16."""
+        q = len(self.in_cores)
+        if q == 0:
+            return x, ldx
+        shapes = [int(c.shape[1]) for c in self.in_cores]
+        cur, ld_cur = x, ldx
+        for i in range(q - 1, -1, -1):
+            c = self.in_cores[i]
+            rho_i, n_i, rho_n = int(c.shape[0]), int(c.shape[1]), int(c.shape[2])
+            K, N = n_i * rho_n, rho_i
+            lead = 1
+            for j in range(i):
+                lead *= shapes[j]
+            ld_out = pad8(lead * N)
+            out = self.ws.get(('in', i), R * ld_out, torch.bfloat16, device)
+            if lead == 1:
+                contract(cur, R, K, self.w_in[i], out, lda=ld_cur, a_outer=ld_cur, s_outer=ld_out)
+            else:
+                contract(cur, R * lead, K, self.w_in[i], out, a_inner=lead, a_outer=ld_cur, m_inner=lead,
+                         s_outer=ld_out, s_inner=N, s_col=1)
+            cur, ld_cur = out, ld_out
+        return cur, ld_cur
+
+    def out_chain(self, z, R, ldz, y, bias, device):
+        """z (R x r_p, stride ldz) bf16 -> y (R x prod m) fp32 contiguous (+ bias)."""
+        p = len(self.out_cores)
+        if p == 1:
+            g0 = self.out_cores[0]
+            m0, r1 = int(g0.shape[1]), int(g0.shape[2])
+            contract(z, R, r1, self.w_out[0], y, lda=ldz, a_outer=ldz, s_outer=m0, bias=bias, bias_inner=0, bias_col=1)
+            return
+        g0, g1 = self.out_cores
+        m0, r1 = int(g0.shape[1]), int(g0.shape[2])
+        m1, r2 = int(g1.shape[1]), int(g1.shape[2])
+        ldv = pad8(m1 * r1)
+        v = self.ws.get(('out', 1), R * ldv, torch.bfloat16, device)
+        contract(z, R, r2, self.w_out[1], v, lda=ldz, a_outer=ldz, s_outer=ldv)
+        # y[t, o0*m1 + o1] = sum_a v[t, o1, a] G0[o0, a]
+        contract(v, R * m1, r1, self.w_out[0], y, a_inner=m1, a_outer=ldv, m_inner=m1, s_outer=m0 * m1, s_inner=1,
+                 s_col=m1, bias=bias, bias_inner=1, bias_col=m1)
+
+
+def conv_rows(engine_ws, x_nhwc, B, H, W, C, ldx, weight, ksize, stride, padding, dilation, device, tag='conv',
+              out_dtype=torch.bfloat16, bias=None):
+    """k x k convolution of an NHWC bf16 activation as im2col + tensor-core GEMM.
+    `weight`: PackedWeight of the (C_out x kh*kw*C) matrix.  Returns (out, Ho, Wo, ld_out)."""
+    kh, kw = ksize
+    Ho = (H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+    Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
+    w = weight.get()
+    rows = B * Ho * Wo
+    if kh == 1 and kw == 1 and stride == (1, 1) and padding == (0, 0):
+        cols, ldo = x_nhwc, ldx
+    else:
+        ldo = w.ld
+        cols = engine_ws.get((tag, 'im2col'), rows * ldo, torch.bfloat16, device)
+        rt.im2col_bf16(x_nhwc, cols, B, H, W, C, ldx, kh, kw, stride[0], stride[1], padding[0], padding[1],
+                       dilation[0], dilation[1], Ho, Wo, ldo)
+    ld_out = pad8(w.N) if out_dtype == torch.bfloat16 else w.N
+    out = engine_ws.get((tag, 'out'), rows * ld_out, out_dtype, device)
+    contract(cols, rows, w.K, weight, out, lda=ldo, a_outer=ldo, s_outer=ld_out, bias=bias)
+    return out, Ho, Wo, ld_out
+
+
+def tt_apply_torch(x2d, in_cores, out_cores):
+    """Autograd-capable statement of the same TT-matrix product (training path): x2d (R x in) ->
+    (R x out) with out-features in natural (o_0, ..., o_{p-1}) order."""
+    R = x2d.shape[0]
+    cur = x2d
+    for c in reversed(list(in_cores)):
+        k = c.shape[1] * c.shape[2]
+        cur = cur.reshape(-1, k) @ c.reshape(c.shape[0], k).t()
+    acc = cur.reshape(R, 1, -1)
+    for g in reversed(list(out_cores)):
+        acc = torch.einsum('tpb,aob->topa', acc, g).reshape(R, -1, g.shape[0])
+    return acc.reshape(R, -1)
+
+
+def split_tt(tt_shapes, out_channels, conv):
+    """TTConv.py:49-68 / TTLinear.py:31-40: the first prefix of tt_shapes whose product equals the
+    number of outputs is the 'out' part; for convs the next entry is kh*kw."""
+    prod = 1
+    for i, s in enumerate(tt_shapes):
+        prod *= s
+        if prod == out_channels:
+            out_order = i + 1
+            break
+    else:
+        raise ValueError('tt_shapes {} do not factor {} outputs'.format(tt_shapes, out_channels))
+    in_order = len(tt_shapes) - out_order - (1 if conv else 0)
+    return out_order, in_order

@@ -48,7 +48,8 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
            'tta_jacobi_scratch_bytes', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
-           'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16']
+           'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
+           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16']
 
 
 class TtaError(RuntimeError):
@@ -108,8 +109,11 @@ def _load():
         getattr(lib, nm).argtypes = [vp, vp, ci, vp]
     i64 = ctypes.c_int64
     lib.tta_gemm_bf16_tc.argtypes = [vp, i64, vp, i64, vp, i64, ci, ci, ci, vp, ci, vp]
-    lib.tta_small_gemm.argtypes = [vp, ci, vp, vp, ci, vp, i64, ci, ci, i64, i64, i64, i64, i64, i64, vp]
+    lib.tta_small_gemm.argtypes = [vp, ci, vp, vp, ci, vp, i64, ci, ci, i64, i64, i64, i64, i64, i64, i64, i64, vp]
     lib.tta_cast_bf16.argtypes = [vp, vp, i64, vp]
+    lib.tta_nchw_to_nhwc_bf16.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    lib.tta_nhwc_to_nchw_f32.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp]
+    lib.tta_im2col_bf16.argtypes = [vp, vp] + [ci] * 16 + [vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch'):
@@ -257,16 +261,34 @@ def gemm_bf16_tc(a, b, c, M, N, K, lda=None, ldb=None, ldc=None, bias=None):
                                   int(c.dtype == torch.float32), stream_handle()), 'tta_gemm_bf16_tc')
 
 
-def small_gemm(a, b, c, M, N, K, m_inner=None, s_outer=None, s_inner=0, s_col=1, bias=None, bias_inner=0, bias_col=1):
+def small_gemm(a, b, c, M, N, K, m_inner=None, s_outer=None, s_inner=0, s_col=1, bias=None, bias_inner=0, bias_col=1,
+               a_inner=1, a_outer=None):
     if m_inner is None:
         m_inner, s_outer, s_inner = 1, N, 0
+    if a_outer is None:
+        a_outer = K * a_inner
     _check(lib().tta_small_gemm(_p(a), int(a.dtype == torch.float32), _p(b), _p(c), int(c.dtype == torch.float32),
-                                _p(bias), int(M), int(N), int(K), int(m_inner), int(s_outer), int(s_inner), int(s_col),
+                                _p(bias), int(M), int(N), int(K), int(a_inner), int(a_outer), int(m_inner),
+                                int(s_outer), int(s_inner), int(s_col),
                                 int(bias_inner), int(bias_col), stream_handle()), 'tta_small_gemm')
 
 
 def cast_bf16(x, y):
     _check(lib().tta_cast_bf16(_p(x), _p(y), x.numel(), stream_handle()), 'tta_cast_bf16')
+
+
+def nchw_to_nhwc_bf16(x, y, B, C, HW, ldc):
+    _check(lib().tta_nchw_to_nhwc_bf16(_p(x), _p(y), B, C, HW, ldc, stream_handle()), 'tta_nchw_to_nhwc_bf16')
+
+
+def nhwc_to_nchw_f32(x, y, bias, B, C, HW, ldc):
+    _check(lib().tta_nhwc_to_nchw_f32(_p(x), int(x.dtype == torch.float32), _p(y), _p(bias), B, C, HW, ldc,
+                                      stream_handle()), 'tta_nhwc_to_nchw_f32')
+
+
+def im2col_bf16(x, out, B, H, W, C, ldx, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo, ldo):
+    _check(lib().tta_im2col_bf16(_p(x), _p(out), B, H, W, C, ldx, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo, ldo,
+                                 stream_handle()), 'tta_im2col_bf16')
 
 
 def launch_count():

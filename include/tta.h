@@ -231,14 +231,24 @@ int tta_sqnorm_batched(const tta_sqnorm_task* tasks_dev, const tta_sqnorm_task* 
  * K, lda, ldb multiples of 8; A, B 16-byte aligned. */
 int tta_gemm_bf16_tc(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int M,
                      int N, int K, const float* bias, int out_fp32, void* stream);
-/* Skinny contraction (K, N <= 96), one thread per row: C(i, j) = sum_k A[i*K + k] * B[j*K + k], stored at
+/* Skinny contraction (K, N <= 96), one thread per row: C(i, j) = sum_k arow_i[k] * B[j*K + k] with
+ * arow_i = a + (i / a_inner) * a_outer + (i % a_inner) * K, stored at
  * c + (i / m_inner) * s_outer + (i % m_inner) * s_inner + j * s_col, plus
  * bias[(i % m_inner) * bias_inner + j * bias_col] when bias != NULL.  A is fp32 or bf16, B bf16. */
 int tta_small_gemm(const void* a, int a_is_f32, const void* b_bf16, void* c, int c_is_f32, const float* bias,
-                   int64_t M, int N, int K, int64_t m_inner, int64_t s_outer, int64_t s_inner, int64_t s_col,
-                   int64_t bias_inner, int64_t bias_col, void* stream);
+                   int64_t M, int N, int K, int64_t a_inner, int64_t a_outer, int64_t m_inner, int64_t s_outer,
+                   int64_t s_inner, int64_t s_col, int64_t bias_inner, int64_t bias_col, void* stream);
 /* y (bf16) = x (fp32), n elements */
 int tta_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+/* Activation layouts of the conv forwards (TTConv.py:132-149, TKConv.py:205-222).
+ * x (B, C, HW) fp32 -> y (B, HW, ldc) bf16; and back (bf16 or fp32 source) with the bias add fused. */
+int tta_nchw_to_nhwc_bf16(const float* x, void* y, int B, int C, int HW, int ldc, void* stream);
+int tta_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* y, const float* bias, int B, int C, int HW, int ldc,
+                         void* stream);
+/* im2col rows of a (B, H, W, ldx) bf16 activation for the k x k core convolution (TTConv.py:139,
+ * TKConv.py:95): out is (B*Ho*Wo) x ldo, column (kh*KW + kw)*C + c, zero padded. */
+int tta_im2col_bf16(const void* x, void* out, int B, int H, int W, int C, int ldx, int KH, int KW, int sh, int sw,
+                    int ph, int pw, int dh, int dw, int Ho, int Wo, int ldo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,3 +65,39 @@ def test_small_gemm_and_cast():
     xb = torch.empty(x.numel(), device=DEV, dtype=torch.bfloat16)
     rt.cast_bf16(x.reshape(-1), xb)
     assert torch.equal(xb, x.reshape(-1).to(torch.bfloat16))
+
+
+def _deit_hp():
+    import hp_tables
+    return hp_tables.tt_deit_small_2x()
+
+
+@pytest.mark.parametrize('name,fin,fout', [('blocks.0.attn.qkv.weight', 384, 1152), ('blocks.1.attn.proj.weight', 384, 384),
+                                            ('blocks.0.mlp.fc1.weight', 384, 1536), ('blocks.1.mlp.fc2.weight', 1536, 384)])
+def test_ttlinear_m_forward_matches_dense(name, fin, fout):
+    """SURVEY 3.4 identity: TTLinearM(dense_w=W)(x) == F.linear(x, Proj_TT(W)); bf16 tolerance 1e-2."""
+    import TTLinear
+    from oracle import port
+    hp = _deit_hp()
+    g = torch.Generator(device='cpu').manual_seed(3)
+    w = torch.randn(fout, fin, generator=g) * 0.02
+    b = torch.randn(fout, generator=g) * 0.1
+    layer = TTLinear.TTLinearM(fin, fout, bias=True, hp_dict=hp.fresh(), name=name, dense_w=w, dense_b=b).to(DEV)
+    x = torch.randn(4, 197, fin, generator=g).to(DEV)
+    with torch.no_grad():
+        y = layer(x)
+    z = torch.from_numpy(port.project_linear_tt(w.numpy(), hp.tt_shapes[name], list(hp.ranks[name]))).to(DEV)
+    ref = torch.nn.functional.linear(x, z, b.to(DEV))
+    assert y.shape == ref.shape
+    assert _rel(y, ref) <= FWD_TOL, _rel(y, ref)
+    # training path (autograd) agrees with the fused path and produces gradients for every core
+    xg = x.clone().requires_grad_(True)
+    yt = layer(xg)
+    assert _rel(yt.detach(), ref) <= 1e-4
+    yt.square().mean().backward()
+    assert all(c.grad is not None for c in layer.tt_cores) and xg.grad is not None
+    layer_r = TTLinear.TTLinearR(fin, fout, bias=True, hp_dict=hp.fresh(), name=name, dense_w=w, dense_b=b).to(DEV)
+    with torch.no_grad():
+        yr = layer_r(x)
+    assert _rel(yr, ref) <= FWD_TOL
+    assert set(dict(layer.named_parameters())) == {'tt_cores.0', 'tt_cores.1', 'tt_cores.2', 'tt_cores.3', 'bias'}
