@@ -224,3 +224,24 @@ def split_tt(tt_shapes, out_channels, conv):
         raise ValueError('tt_shapes {} do not factor {} outputs'.format(tt_shapes, out_channels))
     in_order = len(tt_shapes) - out_order - (1 if conv else 0)
     return out_order, in_order
+
+
+def to_rows(ws, x, tag='rows'):
+    """NCHW fp32 -> pixel-major bf16 rows (B*H*W x pad8(C)); returns (rows, ld)."""
+    B, C, H, W = x.shape
+    ld = pad8(C)
+    rows = ws.get((tag, 'nhwc'), B * H * W * ld, torch.bfloat16, x.device)
+    rt.nchw_to_nhwc_bf16(x.contiguous().to(torch.float32), rows, B, C, H * W, ld)
+    return rows, ld
+
+
+def from_rows(rows, ld, B, C, Ho, Wo, bias, device):
+    """pixel-major rows (bf16 or fp32) -> NCHW fp32 with the bias add fused."""
+    y = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=device)
+    rt.nhwc_to_nchw_f32(rows, y, bias, B, C, Ho * Wo, ld)
+    return y
+
+
+def conv_weight_matrix(w4d):
+    """(O, I, kh, kw) -> (O, kh*kw*I) matching the im2col column order (kh, kw, c)."""
+    return w4d.permute(0, 2, 3, 1).reshape(w4d.shape[0], -1)

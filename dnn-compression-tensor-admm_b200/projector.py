@@ -581,3 +581,23 @@ class TKProjectionPlan:
         ph.finish()
         self.sweeps = jac
         self.errors = {L.name: errs[i] for i, L in enumerate(self.layers)}
+
+
+def tucker2_decompose(w, ranks, device=None):
+    """`partial_tucker(w, modes=[0, 1], rank=ranks, init='svd')` on the B200 kernels (the `dense_w`
+    constructor paths of TKConv.py:79-83,192-196,294-298 and TKLinear.py:47-48,98-99).
+    Returns (core, [last_factor (O x r_out), first_factor (I x r_in)]) as torch tensors on `device`."""
+    if device is None:
+        device = w.device if w.is_cuda or rt.backend_is_emulated() else torch.device('cuda', torch.cuda.current_device())
+    wt = w.detach().to(device=device, dtype=torch.float32).contiguous()
+    layer = TKLayer('tucker2', wt.shape, list(ranks))
+    plan = TKProjectionPlan([layer], device)
+    z = torch.empty_like(wt)
+    plan.run([wt], [None], [z])
+    ws = plan.ws[0]
+    O, I, KK, r0, r1 = layer.O, layer.I, layer.KK, layer.r0, layer.r1
+    core = ws['core'].t[:r0 * KK * r1].view(r0, KK, r1).permute(0, 2, 1).contiguous()
+    e0 = ws['e0']['E'].t[:r0 * O].view(r0, O)
+    e1 = ws['e1']['E'].t[:r1 * I].view(r1, I)
+    core = core.view((r0, r1) + tuple(wt.shape[2:])) if wt.dim() == 4 else core.view(r0, r1)
+    return core.clone(), [e0.t().contiguous(), e1.t().contiguous()]
