@@ -317,6 +317,10 @@ def run_ours(args):
                         'sample': '{} distinct layer signatures timed once, weighted by multiplicity (34 layers); best of 2'
                         .format(len(sample))}
 
+    forward = None
+    if world == 1 and not args.no_forward:
+        forward = forward_bench(dev, peaks)
+
     sweeps = [s for v in admm.sweeps.values() for s in v]
     line = {'metric': METRIC, 'value': n_layers / (ms / 1e3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
@@ -328,10 +332,110 @@ def run_ours(args):
             'clocks': clocks,
             'e2e': {'value': n_layers / (e2e_ms / 1e3), 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': 4 * numel, 'd2h_bytes_per_step': 4 * numel},
-            'gpu_launches': int(launches), 'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu_baseline}
+            'gpu_launches': int(launches), 'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu_baseline,
+            'forward': forward}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time_cuda(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def forward_bench(dev, peaks):
+    """Secondary metric of BASELINE.json ("TT-conv img/s"): decomposed-layer forwards, TT layers only.
+
+    fused  = this repo's inference path (libtta.so kernels, bf16);
+    chain  = the same contraction as an unfused torch op chain in fp32/TF32 on the same GPU (the
+             reference's algorithm restated; the reference modules themselves cannot travel).
+    """
+    import hp_tables
+    import tta_runtime as rt
+    import TTConv
+    import TTLinear
+    out = {}
+    torch.manual_seed(0)
+    # ---- ttm_resnet32 TT layers, batch 128, 32x32 (config 2) ----
+    hp = hp_tables.tt_resnet32_3x()
+    planes = {1: 16, 2: 32, 3: 64}
+    size = {1: 32, 2: 16, 3: 8}
+    layers = []
+    for name in hp.ranks:
+        s, b, c = int(name[5]), int(name[7]), int(name[13])
+        cout = planes[s]
+        first = (b == 0 and c == 1 and s > 1)
+        cin = planes[s - 1] if first else cout
+        stride = 2 if first else 1
+        hw = size[s - 1] if first else size[s]
+        layer = TTConv.TTConv2dM(cin, cout, 3, stride=stride, padding=1, bias=False, hp_dict=hp, name=name).to(dev)
+        layers.append((layer, torch.randn(128, cin, hw, hw, device=dev)))
+
+    def run_fused():
+        with torch.no_grad():
+            for layer, x in layers:
+                layer(x)
+
+    def run_chain():
+        with torch.no_grad():
+            for layer, x in layers:
+                layer._forward_torch(x)
+
+    ms_f, ms_c = _time_cuda(run_fused), _time_cuda(run_chain)
+    out['ttm_resnet32_tt_layers'] = {'batch': 128, 'fused_img_s': 128 / (ms_f / 1e3), 'fused_ms': ms_f,
+                                     'torch_op_chain_img_s': 128 / (ms_c / 1e3), 'torch_op_chain_ms': ms_c}
+    del layers
+    # ---- DeiT-small TTLinearM layers, batch 256 x 197 tokens (config 4) ----
+    hp = hp_tables.tt_deit_small_2x()
+    d = 384
+    dims = {'attn.qkv.weight': (d, 3 * d), 'attn.proj.weight': (d, d), 'mlp.fc1.weight': (d, 4 * d), 'mlp.fc2.weight': (4 * d, d)}
+    tokens = 256 * 197
+    xs = {d: torch.randn(tokens, d, device=dev), 4 * d: torch.randn(tokens, 4 * d, device=dev)}
+    lin = []
+    for name in hp.ranks:
+        fin, fout = dims[name.split('.', 2)[2]]
+        lin.append((TTLinear.TTLinearM(fin, fout, bias=True, hp_dict=hp, name=name).to(dev), xs[fin]))
+
+    def lin_fused():
+        with torch.no_grad():
+            for layer, x in lin:
+                layer(x)
+
+    def lin_chain():
+        with torch.no_grad():
+            for layer, x in lin:
+                import fwd_common as fc
+                fc.tt_apply_torch(x, list(layer.tt_cores)[layer.out_tt_order:], list(layer.tt_cores)[:layer.out_tt_order])
+
+    ms_f, ms_c = _time_cuda(lin_fused, iters=3, warm=1), _time_cuda(lin_chain, iters=3, warm=1)
+    macs = 0
+    for layer, _ in lin:
+        r, sh, o = layer.tt_ranks, layer.tt_shapes, layer.out_tt_order
+        # per-token MACs of the 4-step chain (SURVEY 8(d) TTLinearM accounting)
+        macs += sh[2] * sh[3] * r[3] + sh[2] * r[3] * r[2] + r[2] * sh[1] * r[1] + sh[1] * r[1] * sh[0]
+    out['deit_small_ttlinear_layers'] = {'batch': 256, 'tokens': tokens, 'fused_img_s': 256 / (ms_f / 1e3), 'fused_ms': ms_f,
+                                         'torch_op_chain_img_s': 256 / (ms_c / 1e3), 'torch_op_chain_ms': ms_c,
+                                         'fused_tflops': 2.0 * macs * tokens / (ms_f / 1e3) / 1e12}
+    # ---- the tcgen05 GEMM alone: the two big contractions of the block-0 qkv chain ----
+    tc = {}
+    for (M, N, K) in ((tokens, 1120, 320), (tokens, 320, 368)):
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        b = torch.randn(N, K, device=dev).to(torch.bfloat16)
+        c = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ms = _time_cuda(lambda: rt.gemm_bf16_tc(a, b, c, M, N, K), iters=10, warm=3)
+        tf = 2.0 * M * N * K / (ms / 1e3) / 1e12
+        tc['{}x{}x{}'.format(M, N, K)] = {'ms': ms, 'tflops': tf, 'frac_of_bf16_peak': tf / peaks['bf16_tflops']}
+    out['gemm_bf16_tc_kernel'] = {'bound': 'tensor', 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'shapes': tc}
+    return out
 
 
 def main():
@@ -341,6 +445,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-forward', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

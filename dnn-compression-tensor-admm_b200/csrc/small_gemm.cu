@@ -27,29 +27,60 @@ __device__ __forceinline__ void store_out<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
-template <typename TIn, typename TOut>
+// 16-byte row loads (rows are contiguous runs of K elements; alignment is checked on the host)
+template <typename TIn, int KMAX>
+__device__ __forceinline__ void load_row(const TIn* __restrict__ arow, int K, bool vec, float (&a)[KMAX]) {
+  constexpr int kPerVec = 16 / sizeof(TIn);
+  if (vec) {
+#pragma unroll
+    for (int v = 0; v < KMAX / kPerVec; ++v) {
+      if (v * kPerVec < K) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(arow + v * kPerVec);
+        const TIn* e = reinterpret_cast<const TIn*>(&raw);
+#pragma unroll
+        for (int q = 0; q < kPerVec; ++q) a[v * kPerVec + q] = to_f32<TIn>(e[q]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) a[k] = k < K ? to_f32<TIn>(arow[k]) : 0.f;
+  }
+}
+
+// KMAX: compile-time bound of K (row held in registers, loops fully unrolled and guarded).
+template <typename TIn, typename TOut, int KMAX>
 __global__ void __launch_bounds__(kSgThreads) small_gemm_kernel(const TIn* __restrict__ A, const __nv_bfloat16* __restrict__ B,
                                                                 TOut* __restrict__ C, const float* __restrict__ bias,
                                                                 int64_t M, int N, int K, int64_t a_inner,
                                                                 int64_t a_outer, int64_t m_inner,
                                                                 int64_t s_outer, int64_t s_inner, int64_t s_col,
-                                                                int64_t bias_inner, int64_t bias_col) {
-  __shared__ float Bs[kSgMaxN * kSgMaxK];
-  for (int e = threadIdx.x; e < N * K; e += kSgThreads) Bs[e] = __bfloat162float(B[e]);
+                                                                int64_t bias_inner, int64_t bias_col, int vec) {
+  __shared__ float Bs[kSgMaxN * KMAX];       // row j at Bs + j*KMAX, zero padded to KMAX
+  for (int e = threadIdx.x; e < N * KMAX; e += kSgThreads) {
+    const int j = e / KMAX, k = e - j * KMAX;
+    Bs[e] = k < K ? __bfloat162float(B[j * K + k]) : 0.f;
+  }
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * kSgThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kSgThreads) {
-    float a[kSgMaxK];
+    float a[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) a[k] = 0.f;
     const int64_t ao = i / a_inner;
-    const TIn* arow = A + ao * a_outer + (i - ao * a_inner) * K;
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) a[k] = to_f32<TIn>(arow[k]);
+    load_row<TIn, KMAX>(A + ao * a_outer + (i - ao * a_inner) * K, K, vec != 0, a);
     const int64_t io = i / m_inner, ii = i - io * m_inner;
     TOut* crow = C + io * s_outer + ii * s_inner;
     for (int j = 0; j < N; ++j) {
-      const float* b = Bs + j * K;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < K; ++k) acc = fmaf(a[k], b[k], acc);
+      const float4* b4 = reinterpret_cast<const float4*>(Bs + j * KMAX);
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX / 4; ++k) {
+        const float4 bv = b4[k];            // warp-uniform address: shared-memory broadcast
+        acc0 = fmaf(a[4 * k], bv.x, acc0);
+        acc1 = fmaf(a[4 * k + 1], bv.y, acc1);
+        acc0 = fmaf(a[4 * k + 2], bv.z, acc0);
+        acc1 = fmaf(a[4 * k + 3], bv.w, acc1);
+      }
+      float acc = acc0 + acc1;
       if (bias) acc += __ldg(bias + ii * bias_inner + j * bias_col);
       store_out<TOut>(crow + (int64_t)j * s_col, acc);
     }
@@ -71,17 +102,36 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     y[i] = __float2bfloat16(x[i]);
 }
 
-template <typename TIn, typename TOut>
-static int launch_small(const void* a, const void* b, void* c, const float* bias, int64_t M, int N, int K,
-                        int64_t a_inner, int64_t a_outer, int64_t m_inner, int64_t s_outer, int64_t s_inner, int64_t s_col, int64_t bias_inner,
-                        int64_t bias_col, cudaStream_t st) {
+template <typename TIn, typename TOut, int KMAX>
+static int launch_small_k(const void* a, const void* b, void* c, const float* bias, int64_t M, int N, int K,
+                          int64_t a_inner, int64_t a_outer, int64_t m_inner, int64_t s_outer, int64_t s_inner,
+                          int64_t s_col, int64_t bias_inner, int64_t bias_col, cudaStream_t st) {
   int64_t blocks = (M + kSgThreads - 1) / kSgThreads;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  small_gemm_kernel<TIn, TOut><<<(int)blocks, kSgThreads, 0, st>>>(
+  // 16-byte loads need every row start aligned: base, row length and the outer stride
+  const int per = 16 / (int)sizeof(TIn);
+  const int vec = (((uintptr_t)a & 15) == 0) && (K % per == 0) && (a_outer % per == 0);
+  small_gemm_kernel<TIn, TOut, KMAX><<<(int)blocks, kSgThreads, 0, st>>>(
       reinterpret_cast<const TIn*>(a), reinterpret_cast<const __nv_bfloat16*>(b), reinterpret_cast<TOut*>(c), bias, M, N,
-      K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col);
+      K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, bias_inner, bias_col, vec);
   TTA_CHECK_LAUNCH("small_gemm launch");
   return TTA_OK;
+}
+
+template <typename TIn, typename TOut>
+static int launch_small(const void* a, const void* b, void* c, const float* bias, int64_t M, int N, int K,
+                        int64_t a_inner, int64_t a_outer, int64_t m_inner, int64_t s_outer, int64_t s_inner,
+                        int64_t s_col, int64_t bias_inner, int64_t bias_col, cudaStream_t st) {
+#define TTA_SG(KM)                                                                                                  \
+  return launch_small_k<TIn, TOut, KM>(a, b, c, bias, M, N, K, a_inner, a_outer, m_inner, s_outer, s_inner, s_col, \
+                                       bias_inner, bias_col, st)
+  if (K <= 8) TTA_SG(8);
+  if (K <= 16) TTA_SG(16);
+  if (K <= 32) TTA_SG(32);
+  if (K <= 48) TTA_SG(48);
+  if (K <= 64) TTA_SG(64);
+  TTA_SG(96);
+#undef TTA_SG
 }
 
 }  // namespace tta
