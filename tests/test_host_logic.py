@@ -157,3 +157,50 @@ def test_admm_tucker_flow_matches_oracle(emulated_backend, key):
     assert rel_fro(b.z['fc.weight'].numpy(), port.project_tk(lin['fc.weight'].numpy(), [9, 11])) <= 1e-5
     out = b.prune_linear_rank_tk(lin['fc.weight'].numpy(), 'fc.weight')
     assert rel_fro(out, port.project_tk(lin['fc.weight'].numpy(), [9, 11])) <= 1e-5
+
+
+def test_layer_modules_autograd_path_on_cpu(emulated_backend):
+    """Drop-in layer modules: constructor surface, state-dict names and the torch (training) path,
+    checked on CPU against the oracle identities of SURVEY 3.4."""
+    import TKConv
+    import TKLinear
+    import TTConv
+    import TTLinear
+    g = torch.Generator().manual_seed(21)
+    hp = hp_tables.tt_deit_small_2x()
+    name = 'blocks.1.attn.proj.weight'
+    w = torch.randn(384, 384, generator=g) * 0.02
+    lin = TTLinear.TTLinearM(384, 384, bias=True, hp_dict=hp.fresh(), name=name, dense_w=w, dense_b=torch.zeros(384))
+    x = torch.randn(5, 384, generator=g, requires_grad=True)
+    z = torch.from_numpy(port.project_linear_tt(w.numpy(), hp.tt_shapes[name], list(hp.ranks[name])))
+    assert rel_fro(lin(x).detach().numpy(), torch.nn.functional.linear(x, z).detach().numpy()) <= 1e-4
+    assert [tuple(c.shape) for c in lin.tt_cores] == [(1, 24, 18), (18, 16, 256), (256, 16, 18), (18, 24, 1)]
+    hp32 = hp_tables.tt_resnet32_3x()
+    cname = 'layer2.0.conv1.weight'
+    wc = torch.randn(32, 16, 3, 3, generator=g) * 0.1
+    conv = TTConv.TTConv2dM(16, 32, 3, stride=2, padding=1, bias=False, hp_dict=hp32.fresh(), name=cname, dense_w=wc)
+    xc = torch.randn(2, 16, 8, 8, generator=g, requires_grad=True)
+    zc = torch.from_numpy(port.project_conv_tt(wc.numpy(), hp32.tt_shapes[cname], list(hp32.ranks[cname])))
+    ref = torch.nn.functional.conv2d(xc, zc, stride=2, padding=1)
+    assert rel_fro(conv(xc).detach().numpy(), ref.detach().numpy()) <= 1e-4
+    assert tuple(conv.core_kernel.shape) == (32, 16, 3, 3) and len(conv.in_tt_cores) == 2 and len(conv.out_tt_cores) == 2
+    hpk = hp_tables.tk_resnet32('3')
+    for cls in (TKConv.TKConv2dC, TKConv.TKConv2dM, TKConv.TKConv2dR):
+        tk = cls(16, 32, 3, stride=2, padding=1, bias=False, hp_dict=hpk, name=cname, dense_w=wc)
+        zk = torch.from_numpy(port.project_tk(wc.numpy(), hpk.ranks[cname]))
+        refk = torch.nn.functional.conv2d(xc, zk, stride=2, padding=1)
+        assert rel_fro(tk(xc).detach().numpy(), refk.detach().numpy()) <= 1e-4, cls.__name__
+    with pytest.raises(ValueError):
+        TKConv.TKConv2dC(16, 32, 3, groups=2, hp_dict=hpk, name=cname)
+    hpl = hp_tables.HpTable('tkl', {'fc.weight': [6, 7]})
+    wl = torch.randn(20, 24, generator=g)
+    tkl = TKLinear.TKLinearM(24, 20, bias=True, hp_dict=hpl, name='fc.weight', dense_w=wl, dense_b=torch.zeros(20))
+    xl = torch.randn(3, 24, generator=g, requires_grad=True)
+    zl = torch.from_numpy(port.project_tk(wl.numpy(), [6, 7]))
+    assert rel_fro(tkl(xl).detach().numpy(), torch.nn.functional.linear(xl, zl).detach().numpy()) <= 1e-4
+    # inference path without a GPU must fail loudly, not fall back (emulator off)
+    import tta_runtime as rt
+    rt.set_backend_for_tests(None)
+    with pytest.raises(rt.TtaError):
+        with torch.no_grad():
+            lin(x.detach())
