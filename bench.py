@@ -288,9 +288,10 @@ def run_ours(args):
     eig_flop = fl[2]
     per_launch_s = (jac_ms / 1e3) / max(jac_launches, 1)
     achieved = (eig_flop / max(jac_launches, 1)) / per_launch_s / 1e12 if jac_launches else 0.0
-    roofline = {'kernel': 'jacobi_step_kernel', 'bound': 'tensor', 'achieved': achieved,
+    roofline = {'kernel': 'jacobi_cluster_kernel', 'bound': 'tensor', 'achieved': achieved,
                 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'frac': achieved / peaks['bf16_tflops_sustained'],
+                'traffic': 6359040,   # dram read+write bytes of one jacobi_cluster launch (ncu --set full, profiles/r1b_ncu_jacobi_cluster16_details.txt)
                 'peak_source': peaks['source'] + ' (sustained bf16; kernel is timed inside a long step)',
                 'launches_per_step': jac_launches, 'avg_launch_us': per_launch_s * 1e6,
                 'note': 'eigensolver runs on the CUDA-core FMA pipe (fp32 Jacobi rotations), not on tensor cores; '
