@@ -182,7 +182,14 @@ static unsigned long long g_prof_launches = 0;
 
 static bool g_force_legacy = false;   // test hook: route every problem through the multi-launch solver
 
-static bool use_cluster(const tta_eig_task& tk) { return !g_force_legacy && jacobi_cluster_eligible(tk); }
+static bool g_allow_gra = true;       // test hook: 0 keeps every cluster problem on the column-rotation kernel
+static float g_stop_rel = 3e-4f;      // gram-rotate-apply solver: stop after a sweep whose largest relative
+                                      // off-diagonal (seen before rotating) is below this
+
+static bool use_cluster(const tta_eig_task& tk) {
+  if (g_force_legacy) return false;
+  return (g_allow_gra && jacobi_gra_eligible(tk)) || jacobi_cluster_eligible(tk);
+}
 
 static void build_schedule(const tta_eig_task* th, int n, std::vector<std::vector<JacItem>>& launches) {
   launches.clear();
@@ -212,6 +219,8 @@ extern "C" {
 
 void tta_jacobi_profile_enable(int on) { tta::g_prof_on = on != 0; }
 void tta_jacobi_force_multilaunch(int on) { tta::g_force_legacy = on != 0; }
+void tta_jacobi_enable_gra(int on) { tta::g_allow_gra = on != 0; }
+void tta_jacobi_set_stop_rel(float stop_rel) { tta::g_stop_rel = stop_rel > 0.f ? stop_rel : 0.f; }
 void tta_jacobi_profile_read(double* step_ms, unsigned long long* step_launches) {
   if (step_ms) *step_ms = tta::g_prof_ms;
   if (step_launches) *step_launches = tta::g_prof_launches;
@@ -312,7 +321,8 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     cudaEventCreate(&cev1);
     cudaEventRecord(cev0, st);
   }
-  rc = jacobi_cluster_run(tasks_dev, tasks_host, cl_probs, tol * tol, max_sweeps, cl_ids, sweeps, cl_status, floor2, st);
+  rc = jacobi_cluster_run(tasks_dev, tasks_host, cl_probs, tol * tol, g_stop_rel * g_stop_rel, max_sweeps, g_allow_gra,
+                          cl_ids, sweeps, cl_status, floor2, st);
   if (rc) return rc;
   if (cev0) cudaEventRecord(cev1, st);
 
@@ -360,6 +370,11 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }
+  if (!sweeps_out && n_legacy == 0 && !cev0) {
+    // asynchronous mode: nothing is read back here; the caller inspects the scratch buffer later
+    // (tta_jacobi_read_results) -- a network step then has no host synchronisation between waves.
+    return TTA_OK;
+  }
   std::vector<int32_t> status_h(n_tasks, 0);
   rc = check_cuda(cudaMemcpyAsync(sweeps_h.data(), sweeps, n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
                   "jacobi sweeps readback");
@@ -385,6 +400,28 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     int bad = 0;
     for (int p = 0; p < n_tasks; ++p)
       if (!done_h[p]) bad = p;
+    set_error("jacobi: problem %d (k=%d) not converged after %d sweeps", bad, tasks_host[bad].k, max_sweeps);
+    return TTA_E_NOCONV;
+  }
+  return TTA_OK;
+}
+
+int tta_jacobi_read_results(const int32_t* scratch_host, const tta_eig_task* tasks_host, int n_tasks, int max_sweeps,
+                            int32_t* sweeps_out) {
+  using namespace tta;
+  if (n_tasks <= 0) return TTA_OK;
+  if (!scratch_host || !tasks_host) {
+    set_error("jacobi results: bad argument");
+    return TTA_E_INVALID;
+  }
+  const int32_t* sweeps = scratch_host + 2 * n_tasks;
+  const int32_t* status = scratch_host + 5 * n_tasks;
+  int bad = -1;
+  for (int p = 0; p < n_tasks; ++p) {
+    if (sweeps_out) sweeps_out[p] = sweeps[p];
+    if (!status[p]) bad = p;
+  }
+  if (bad >= 0) {
     set_error("jacobi: problem %d (k=%d) not converged after %d sweeps", bad, tasks_host[bad].k, max_sweeps);
     return TTA_E_NOCONV;
   }

@@ -15,6 +15,7 @@
 //     go to concurrent internal streams).
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -158,10 +159,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
   }
 }
 
+constexpr int kPoolStreams = 8;
+
 struct StreamPool {
-  cudaStream_t s[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s[kPoolStreams] = {};
   cudaEvent_t fork = nullptr;
-  cudaEvent_t join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t join[kPoolStreams] = {};
 };
 
 static StreamPool* pool_for_device(int dev) {
@@ -169,7 +172,7 @@ static StreamPool* pool_for_device(int dev) {
   auto it = pools.find(dev);
   if (it != pools.end()) return it->second;
   StreamPool* p = new StreamPool();
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < kPoolStreams; ++i) {
     if (cudaStreamCreateWithFlags(&p->s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
@@ -185,41 +188,13 @@ bool jacobi_cluster_eligible(const tta_eig_task& tk) {
   return P == 1 || P == 2 || P == 4 || P == 8 || P == 16;
 }
 
-// Enqueue the cluster solver for the problems listed in `probs` (indices into the task table).
-// `ids_dev` must hold probs.size() int32.  Work is forked from / joined back into `st`.
-int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs,
-                       float tol2, int max_sweeps, int32_t* ids_dev, int32_t* sweeps_dev, int32_t* status_dev,
-                       const float* floor2, cudaStream_t st) {
-  if (probs.empty()) return TTA_OK;
-  int dev = 0;
-  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-  if (rc) return rc;
-  StreamPool* pool = pool_for_device(dev);
-  if (!pool) {
-    set_error("jacobi cluster: cannot create internal streams");
-    return TTA_E_CUDA;
-  }
-  // group by cluster size
-  const int sizes[5] = {1, 2, 4, 8, 16};
-  std::vector<int> grouped[5];
-  for (int p : probs) {
-    const int P = th[p].kpad / (2 * th[p].bw);
-    for (int g = 0; g < 5; ++g)
-      if (sizes[g] == P) grouped[g].push_back(p);
-  }
-  std::vector<int32_t> flat;
-  int offs[5];
-  for (int g = 0; g < 5; ++g) {
-    offs[g] = (int)flat.size();
-    flat.insert(flat.end(), grouped[g].begin(), grouped[g].end());
-  }
-  rc = check_cuda(cudaMemcpyAsync(ids_dev, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st),
-                  "jacobi cluster ids upload");
-  if (rc) return rc;
-  rc = check_cuda(cudaEventRecord(pool->fork, st), "jacobi cluster fork");
-  if (rc) return rc;
-
+// One launch (on `gs`) of the column-rotation cluster kernel for problems that all use cluster size P.
+static int cluster_enqueue(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs, int P,
+                           float tol2, int max_sweeps, const int32_t* ids_dev, int32_t* sweeps_dev,
+                           int32_t* status_dev, const float* floor2, cudaStream_t gs) {
   static bool attr_set = false;
+  static size_t smem_set[2] = {0, 0};
+  int rc;
   if (!attr_set) {
     rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
                     "jacobi cluster non-portable attribute");
@@ -229,59 +204,108 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
     if (rc) return rc;
     attr_set = true;
   }
-  size_t smem_all = 0;
+  size_t smem = 0;
+  int bwmax = 2;
   for (int p : probs) {
     const size_t need = (size_t)2 * th[p].bw * (th[p].ld + 1) * sizeof(float);
-    smem_all = need > smem_all ? need : smem_all;
+    smem = need > smem ? need : smem;
+    bwmax = th[p].bw > bwmax ? th[p].bw : bwmax;
   }
-  rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_all),
-                  "jacobi cluster smem attribute");
+  const int big = bwmax > 16 ? 1 : 0;
+  if (smem > smem_set[big]) {
+    rc = big ? check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem), "jacobi cluster smem attribute")
+             : check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem), "jacobi cluster smem attribute");
+    if (rc) return rc;
+    smem_set[big] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(probs.size() * P), 1, 1);
+  cfg.blockDim = dim3((unsigned)(bwmax * 32), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = gs;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)P;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!big)
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<512>, tasks_dev, ids_dev, sweeps_dev, status_dev,
+                                       floor2, tol2, max_sweeps),
+                    "jacobi cluster launch");
+  else
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<1024>, tasks_dev, ids_dev, sweeps_dev, status_dev,
+                                       floor2, tol2, max_sweeps),
+                    "jacobi cluster launch");
   if (rc) return rc;
-  rc = check_cuda(cudaFuncSetAttribute(jacobi_cluster_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_all),
-                  "jacobi cluster smem attribute");
-  if (rc) return rc;
+  count_launch();
+  return TTA_OK;
+}
 
-  for (int g = 4; g >= 0; --g) {   // largest clusters first: they are the critical path
-    if (grouped[g].empty()) continue;
-    const int P = sizes[g];
-    size_t smem = 0;
-    int bwmax = 2;
-    for (int p : grouped[g]) {
-      const size_t need = (size_t)2 * th[p].bw * (th[p].ld + 1) * sizeof(float);
-      smem = need > smem ? need : smem;
-      bwmax = th[p].bw > bwmax ? th[p].bw : bwmax;
-    }
-    cudaStream_t gs = pool->s[g];
-    rc = check_cuda(cudaStreamWaitEvent(gs, pool->fork, 0), "jacobi cluster stream wait");
-    if (rc) return rc;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(grouped[g].size() * P), 1, 1);
-    cfg.blockDim = dim3((unsigned)(bwmax * 32), 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = gs;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)P;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const int32_t* ids = ids_dev + offs[g];
-    if (bwmax <= 16)
-      rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<512>, tasks_dev, ids, sweeps_dev, status_dev,
-                                         floor2, tol2, max_sweeps),
-                      "jacobi cluster launch");
+// Enqueue the persistent solvers for the problems listed in `probs` (indices into the task table):
+// problems are grouped by (solver, cluster size); every group is one launch on an internal stream,
+// forked from / joined back into `st`, largest clusters first (they are the critical path).
+// `ids_dev` must hold probs.size() int32.
+int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs,
+                       float tol2, float stop2, int max_sweeps, bool allow_gra, int32_t* ids_dev, int32_t* sweeps_dev,
+                       int32_t* status_dev, const float* floor2, cudaStream_t st) {
+  if (probs.empty()) return TTA_OK;
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  StreamPool* pool = pool_for_device(dev);
+  if (!pool) {
+    set_error("jacobi cluster: cannot create internal streams");
+    return TTA_E_CUDA;
+  }
+  // key = P (column-rotation kernel) or 100 + P (gram-rotate-apply kernel); iterate descending P
+  std::map<int, std::vector<int>> groups;
+  for (int p : probs) {
+    if (allow_gra && jacobi_gra_eligible(th[p]))
+      groups[100 + th[p].kpad / 32].push_back(p);
     else
-      rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<1024>, tasks_dev, ids, sweeps_dev, status_dev,
-                                         floor2, tol2, max_sweeps),
-                      "jacobi cluster launch");
+      groups[th[p].kpad / (2 * th[p].bw)].push_back(p);
+  }
+  std::vector<int> order;
+  for (auto& kv : groups) order.push_back(kv.first);
+  std::sort(order.begin(), order.end(), [](int a, int b) { return (a % 100) > (b % 100) || ((a % 100) == (b % 100) && a > b); });
+  std::vector<int32_t> flat;
+  std::map<int, int> offs;
+  for (int key : order) {
+    offs[key] = (int)flat.size();
+    flat.insert(flat.end(), groups[key].begin(), groups[key].end());
+  }
+  rc = check_cuda(cudaMemcpyAsync(ids_dev, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+                  "jacobi cluster ids upload");
+  if (rc) return rc;
+  rc = check_cuda(cudaEventRecord(pool->fork, st), "jacobi cluster fork");
+  if (rc) return rc;
+  bool used[kPoolStreams] = {};
+  int gi = 0;
+  for (int key : order) {
+    const int si = gi++ % kPoolStreams;
+    cudaStream_t gs = pool->s[si];
+    if (!used[si]) {
+      rc = check_cuda(cudaStreamWaitEvent(gs, pool->fork, 0), "jacobi cluster stream wait");
+      if (rc) return rc;
+      used[si] = true;
+    }
+    const std::vector<int>& g = groups[key];
+    const int32_t* ids = ids_dev + offs[key];
+    if (key >= 100)
+      rc = jacobi_gra_enqueue(tasks_dev, th, g, key - 100, tol2, stop2, max_sweeps, ids, sweeps_dev, status_dev, floor2, gs);
+    else
+      rc = cluster_enqueue(tasks_dev, th, g, key, tol2, max_sweeps, ids, sweeps_dev, status_dev, floor2, gs);
     if (rc) return rc;
-    count_launch();
-    rc = check_cuda(cudaEventRecord(pool->join[g], gs), "jacobi cluster join record");
+  }
+  for (int si = 0; si < kPoolStreams; ++si) {
+    if (!used[si]) continue;
+    rc = check_cuda(cudaEventRecord(pool->join[si], pool->s[si]), "jacobi cluster join record");
     if (rc) return rc;
-    rc = check_cuda(cudaStreamWaitEvent(st, pool->join[g], 0), "jacobi cluster join wait");
+    rc = check_cuda(cudaStreamWaitEvent(st, pool->join[si], 0), "jacobi cluster join wait");
     if (rc) return rc;
   }
   return TTA_OK;

@@ -244,10 +244,14 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, float* __r
   return nrot;
 }
 
-// host-side entry of the cluster solver (eig_cluster.cu)
+// host-side entries of the persistent cluster solvers (eig_cluster.cu, eig_gra.cu)
 bool jacobi_cluster_eligible(const tta_eig_task& tk);
+bool jacobi_gra_eligible(const tta_eig_task& tk);
+int jacobi_gra_enqueue(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs, int P,
+                       float tol2, float stop2, int max_sweeps, const int32_t* ids_dev, int32_t* sweeps_dev,
+                       int32_t* status_dev, const float* floor2, cudaStream_t gs);
 int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs,
-                       float tol2, int max_sweeps, int32_t* ids_dev, int32_t* sweeps_dev, int32_t* status_dev,
-                       const float* floor2, cudaStream_t st);
+                       float tol2, float stop2, int max_sweeps, bool allow_gra, int32_t* ids_dev, int32_t* sweeps_dev,
+                       int32_t* status_dev, const float* floor2, cudaStream_t st);
 
 }  // namespace tta

@@ -1,0 +1,597 @@
+// Gram-rotate-apply cluster Jacobi eigensolver (32 < k <= 512): the one-sided Jacobi sweep of
+// eig_cluster.cu with its bulk work recast as small dense contractions.
+//
+// One cluster of P = kpad/32 CTAs owns one eigenproblem for all of its sweeps; every CTA holds two
+// blocks of 16 columns (column-major, padded stride `lds`) in shared memory.  One round of the block
+// tournament used to be 16 lock-step steps of "load y column, dot, rotate, store y column" -- 64 KB
+// of shared-memory traffic and a ~1 us dependent chain per step.  Here a round is
+//   1. Gram    C = [T B]^T [T B]   (only the 16 x 16 cross block T^T B is contracted over the k rows;
+//                                   the diagonal blocks T^T T, B^T B travel with their blocks and are
+//                                   refreshed once per sweep)                       FFMA2, k*256 FMA
+//   2. rotate  the same 16 x 16 cross pairs in the same order, but as a two-sided Jacobi on the
+//              32 x 32 matrix C in shared memory (one thread per 2 x 2 block, one barrier per step),
+//              accumulating the rotations in V (32 x 32)                            latency, tiny
+//   3. apply   [T' B'] = [T B] V, each lane two rows in registers, written STRAIGHT into the shared
+//              memory of the CTAs that own the blocks in the next round (distributed shared memory,
+//              other-parity buffer), then ONE cluster barrier                       FFMA2, k*1024 FMA
+// so the column state is read twice and written once per round instead of 16 times, and the
+// arithmetic is identical to the rotation sequence of the column-wise solver (rotating the columns of
+// M by J is the congruence J^T C J of its Gram matrix).
+//
+// Stopping rule: a sweep whose largest |c_pq| / sqrt(c_pp c_qq) (seen before rotating) is below
+// `stop_rel` leaves off-diagonals of order stop_rel^2 (quadratic convergence), so the solver stops
+// after that sweep instead of spending one or two more sweeps to see zero rotations; the fp64
+// refinement (refine.cu) works on the result either way.
+#include <cooperative_groups.h>
+
+#include <stdlib.h>
+
+#include <vector>
+
+#include "eig_device.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tta {
+
+constexpr int kGraThreads = 512;
+constexpr int kGraCs = 48;                 // row stride of C in shared memory (rows r, r+1 in disjoint bank halves)
+constexpr int kGraCsz = 32 * kGraCs;
+constexpr int kGraVs = 40;                 // row stride of V (rows r, r+2 in disjoint bank halves; 16-byte aligned)
+
+// padded column stride: lds/4 odd, so that 8 columns' float4 at one row offset hit 8 distinct
+// 16-byte bank groups
+__host__ __device__ inline int gra_lds(int ld) { return (((ld >> 2) + 1) | 1) << 2; }
+__host__ __device__ inline int gra_buf_floats(int ld) { return 32 * gra_lds(ld) + 512; }
+inline size_t gra_smem_bytes(int ld) { return (size_t)(2 * gra_buf_floats(ld) + 4096 + 2 * kGraCsz + 32 * kGraVs + 128 + 32) * sizeof(float); }
+
+__device__ __forceinline__ void gra_cluster_sync() {
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Rotation of the column pair (x, y) with x.x = a, y.y = b, x.y = c:
+//   x' = cs x - sn y,  y' = sn x + cs y,  new squared norms a - t c and b + t c.
+__device__ __forceinline__ bool gra_params(float a, float b, float c, float tol2, float fl, float& cs, float& sn,
+                                           float& t) {
+  cs = 1.f;
+  sn = 0.f;
+  t = 0.f;
+  if (!(a > fl) || !(b > fl)) return false;
+  if (!(c * c > (tol2 * a) * b)) return false;
+  // With al = (b - a)/2 and hyp = sqrt(al^2 + c^2):  cs^2 = (1 + |al|/hyp)/2,  sn = sign(al) c / (2 hyp cs),
+  // t = sn/cs -- the same inner rotation as t = sign(z)/(|z| + sqrt(1 + z^2)), z = al/c, but with two
+  // dependent MUFU ops instead of four.  One Newton step on each rsqrt keeps cs^2 + sn^2 = 1 to rounding.
+  const float al = 0.5f * (b - a);
+  const float h2 = fmaf(al, al, c * c);
+  float ih = mufu_rsqrt(h2);
+  ih = ih * fmaf(-0.5f * h2, ih * ih, 1.5f);
+  const float cs2 = fmaf(0.5f * fabsf(al), ih, 0.5f);
+  float rc = mufu_rsqrt(cs2);
+  rc = rc * fmaf(-0.5f * cs2, rc * rc, 1.5f);
+  cs = cs2 * rc;
+  sn = copysignf(0.5f * c * ih * rc, al * c);
+  t = sn * rc;
+  return true;
+}
+
+// part[warp][i*16 + j] = sum over this warp's rows of x_i * y_j   (i, j in 0..15)
+__device__ __forceinline__ void gra_gram16(const float* __restrict__ xb, const float* __restrict__ yb,
+                                           float* __restrict__ part, int ld4, int lds, int warp, int lane) {
+  const int li = lane & 7, lj = lane >> 3;
+  float2 acc[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[a][m] = make_float2(0.f, 0.f);
+  const float* x0p = xb + li * lds;
+  const float* x1p = xb + (li + 8) * lds;
+  const float* yp = yb + lj * lds;
+  for (int r4 = warp; r4 < ld4; r4 += 16) {
+    const float4 x0 = *reinterpret_cast<const float4*>(x0p + 4 * r4);
+    const float4 x1 = *reinterpret_cast<const float4*>(x1p + 4 * r4);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float4 y = *reinterpret_cast<const float4*>(yp + 4 * m * lds + 4 * r4);
+      const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
+      acc[0][m] = ffma2(make_float2(x0.x, x0.y), ylo, acc[0][m]);
+      acc[1][m] = ffma2(make_float2(x1.x, x1.y), ylo, acc[1][m]);
+      acc[0][m] = ffma2(make_float2(x0.z, x0.w), yhi, acc[0][m]);
+      acc[1][m] = ffma2(make_float2(x1.z, x1.w), yhi, acc[1][m]);
+    }
+  }
+  float* out = part + warp * 256;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    out[li * 16 + lj + 4 * m] = acc[0][m].x + acc[0][m].y;
+    out[(li + 8) * 16 + lj + 4 * m] = acc[1][m].x + acc[1][m].y;
+  }
+}
+
+// [T' B'] = [T B] V.  Lane tile RL rows x 8 columns (the balanced shared-memory / FFMA2 shape: per
+// contraction index 2 (1) 128-bit loads of M and 2 of V feed 8*RL FMAs), warp tile 8*RL rows x all 32
+// columns, accumulators packed along row pairs so that M pairs and the float4 stores are natural.
+// T' goes to dstT, B' to dstB (possibly another CTA's shared memory).
+template <int RL>
+__device__ __forceinline__ void gra_apply(const float* __restrict__ src, const float* __restrict__ Vm,
+                                          float* __restrict__ dstT, float* __restrict__ dstB, int ld, int lds,
+                                          int warp, int lane) {
+  // lane (cg, rg): columns 8cg..8cg+7; rows row0..row0+3 and (RL == 8) row0+32..row0+35, so that the
+  // 8 lanes of a quarter-warp touch 128 contiguous bytes of a column in every 128-bit access
+  const int cg = lane & 3, rg = lane >> 2;
+  const int row0 = warp * (8 * RL) + rg * 4;
+  if (row0 >= ld) return;
+  float2 acc[8][RL / 2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < RL / 2; ++q) acc[j][q] = make_float2(0.f, 0.f);
+  const float* mp = src + row0;
+  const float* vp = Vm + 8 * cg;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    float2 m[RL / 2];
+    {
+      const float4 t = *reinterpret_cast<const float4*>(mp + i * lds);
+      m[0] = make_float2(t.x, t.y);
+      m[1] = make_float2(t.z, t.w);
+      if constexpr (RL == 8) {
+        const float4 u = *reinterpret_cast<const float4*>(mp + i * lds + 32);
+        m[2] = make_float2(u.x, u.y);
+        m[3] = make_float2(u.z, u.w);
+      }
+    }
+    const float4 v0 = *reinterpret_cast<const float4*>(vp + i * kGraVs);
+    const float4 v1 = *reinterpret_cast<const float4*>(vp + i * kGraVs + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 vv = make_float2(v[j], v[j]);
+#pragma unroll
+      for (int q = 0; q < RL / 2; ++q) acc[j][q] = ffma2(m[q], vv, acc[j][q]);
+    }
+  }
+  float* dst = (cg < 2 ? dstT + (8 * cg) * lds : dstB + (8 * cg - 16) * lds) + row0;
+  const bool hi = (RL == 8) && (row0 + 32 < ld);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<float4*>(dst + j * lds) = make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y);
+    if constexpr (RL == 8) {
+      if (hi) *reinterpret_cast<float4*>(dst + j * lds + 32) = make_float4(acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y);
+    }
+  }
+}
+
+// rotation record of one pair for one step: cs, sn, and the diagonal entries after the rotation
+// (unchanged values and sn == 0 when the pair is skipped)
+__device__ __forceinline__ float4 gra_record(float a, float b, float c, float tol2, float fl, int& nrot,
+                                             float& maxrel2) {
+  float cs, sn, t;
+  if (a > fl && b > fl) maxrel2 = fmaxf(maxrel2, c * c * mufu_rcp(a * b));
+  if (gra_params(a, b, c, tol2, fl, cs, sn, t)) {
+    ++nrot;
+    const float d = t * c;
+    return make_float4(cs, sn, fmaxf(a - d, 0.f), fmaxf(b + d, 0.f));
+  }
+  return make_float4(1.f, 0.f, a, b);
+}
+
+// One step for the thread that owns the 2 x 2 block (rows pa, qa) x (columns pb, qb) of C.
+// Returns the new C[pa][qb].
+__device__ __forceinline__ float gra_block(const float* __restrict__ Cc, float* __restrict__ Cn, int pa, int qa,
+                                           int pb, int qb, const float4 ra, const float4 rb, bool diag) {
+  const float b00 = Cc[pa * kGraCs + pb], b01 = Cc[pa * kGraCs + qb];
+  const float b10 = Cc[qa * kGraCs + pb], b11 = Cc[qa * kGraCs + qb];
+  float n00, n01, n10, n11;
+  if (diag) {
+    const bool rot = ra.y != 0.f;
+    n00 = ra.z;
+    n11 = ra.w;
+    n01 = rot ? 0.f : b01;
+    n10 = rot ? 0.f : b10;
+  } else {
+    const float t00 = fmaf(rb.x, b00, -rb.y * b01), t01 = fmaf(rb.y, b00, rb.x * b01);
+    const float t10 = fmaf(rb.x, b10, -rb.y * b11), t11 = fmaf(rb.y, b10, rb.x * b11);
+    n00 = fmaf(ra.x, t00, -ra.y * t10);
+    n01 = fmaf(ra.x, t01, -ra.y * t11);
+    n10 = fmaf(ra.y, t00, ra.x * t10);
+    n11 = fmaf(ra.y, t01, ra.x * t11);
+  }
+  Cn[pa * kGraCs + pb] = n00;
+  Cn[pa * kGraCs + qb] = n01;
+  Cn[qa * kGraCs + pb] = n10;
+  Cn[qa * kGraCs + qb] = n11;
+  return n01;
+}
+
+__device__ __forceinline__ void gra_vrot(float* __restrict__ Vm, int i0, int pb, int qb, const float4 rb) {
+  if (rb.y == 0.f) return;
+#pragma unroll
+  for (int i = i0; i < i0 + 2; ++i) {
+    const float x = Vm[i * kGraVs + pb], y = Vm[i * kGraVs + qb];
+    Vm[i * kGraVs + pb] = fmaf(rb.x, x, -rb.y * y);
+    Vm[i * kGraVs + qb] = fmaf(rb.y, x, rb.x * y);
+  }
+}
+
+// The 16 cross steps (pair w of step s = column w of T against column (w+s)%16 of B) on C (double
+// buffered) and V, one barrier per step: the thread that produces the new C[w][16+(w+s+1)%16] --
+// the pivot of pair w in the next step -- also computes that pair's rotation record, so the
+// parameter chain of step s+1 is off the barrier path.  Returns the buffer index of the final C.
+__device__ __forceinline__ int gra_rotate_cross(float* __restrict__ Cb, float* __restrict__ Vm, float4* __restrict__ rec,
+                                                int tid, float tol2, float fl, int& nrot, float& maxrel2) {
+  if (tid < 16) {
+    const int p = tid, q = 16 + tid;
+    rec[tid] = gra_record(Cb[p * kGraCs + p], Cb[q * kGraCs + q], Cb[p * kGraCs + q], tol2, fl, nrot, maxrel2);
+  }
+  __syncthreads();
+  int cur = 0;
+#pragma unroll 1
+  for (int s = 0; s < 16; ++s) {
+    const float* Cc = Cb + cur * kGraCsz;
+    float* Cn = Cb + (cur ^ 1) * kGraCsz;
+    const float4* rc = rec + cur * 16;
+    if (tid < 256) {
+      const int a = tid >> 4, b = tid & 15;
+      const int qa = 16 + ((a + s) & 15), qb = 16 + ((b + s) & 15);
+      const float4 ra = rc[a], rb = rc[b];
+      const float n01 = gra_block(Cc, Cn, a, qa, b, qb, ra, rb, a == b);
+      if (b == ((a + 1) & 15) && s < 15)
+        rec[(cur ^ 1) * 16 + a] = gra_record(ra.z, rb.w, n01, tol2, fl, nrot, maxrel2);
+    } else {
+      const int u = tid - 256, b = u & 15;
+      gra_vrot(Vm, (u >> 4) * 2, b, 16 + ((b + s) & 15), rc[b]);
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+  return cur;
+}
+
+// The 15 tournament steps inside T and inside B (once per sweep): two barriers per step.
+__device__ __forceinline__ int gra_rotate_intra(float* __restrict__ Cb, float* __restrict__ Vm, float4* __restrict__ rec,
+                                                int* __restrict__ pq, int tid, float tol2, float fl, int& nrot,
+                                                float& maxrel2) {
+  int cur = 0;
+#pragma unroll 1
+  for (int s = 0; s < 15; ++s) {
+    const float* Cc = Cb + cur * kGraCsz;
+    float* Cn = Cb + (cur ^ 1) * kGraCsz;
+    if (tid < 16) {
+      int p0, p1;
+      rr_pair(16, s, tid & 7, p0, p1);
+      const int base = (tid >> 3) << 4;
+      const int p = base + (p0 < p1 ? p0 : p1), q = base + (p0 < p1 ? p1 : p0);
+      pq[2 * tid] = p;
+      pq[2 * tid + 1] = q;
+      rec[tid] = gra_record(Cc[p * kGraCs + p], Cc[q * kGraCs + q], Cc[p * kGraCs + q], tol2, fl, nrot, maxrel2);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      const int a = tid >> 4, b = tid & 15;
+      gra_block(Cc, Cn, pq[2 * a], pq[2 * a + 1], pq[2 * b], pq[2 * b + 1], rec[a], rec[b], a == b);
+    } else {
+      const int u = tid - 256, b = u & 15;
+      gra_vrot(Vm, (u >> 4) * 2, pq[2 * b], pq[2 * b + 1], rec[b]);
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+  return cur;
+}
+
+template <int RL>
+__global__ void __launch_bounds__(kGraThreads, 1)
+    jacobi_gra_kernel(const tta_eig_task* __restrict__ tasks, const int32_t* __restrict__ prob_ids,
+                      int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
+                      const float* __restrict__ floor2, float tol2, float stop2, int max_sweeps,
+                      unsigned long long* __restrict__ prof) {
+  extern __shared__ __align__(16) float smem[];
+  long long pc[4] = {0, 0, 0, 0};   // phase cycles (gram, rotate, apply, barrier) when `prof` is given
+  long long t0 = 0;
+#define GRA_TICK(i)                         \
+  if (prof) {                               \
+    const long long t1 = clock64();         \
+    pc[i] += t1 - t0;                       \
+    t0 = t1;                                \
+  }
+  __shared__ int s_rot;
+  __shared__ unsigned s_max;
+  __shared__ int s_counts[16];
+  __shared__ unsigned s_maxes[16];
+  __shared__ int s_total;
+  __shared__ unsigned s_maxall;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int P = (int)cluster.num_blocks();
+  const int c = (int)cluster.block_rank();
+  const int prob = prob_ids[blockIdx.x / P];
+  const tta_eig_task tk = tasks[prob];
+  const float fl = floor2[prob];
+  const int ld = tk.ld, ld4 = ld >> 2, lds = gra_lds(ld);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bufsz = gra_buf_floats(ld);
+  float* part = smem + 2 * bufsz;       // 16 x 256 Gram partials
+  float* Cb = part + 4096;              // 2 x (32 x 33)
+  float* Vm = Cb + 2 * kGraCsz;         // 32 x 32 (stride kGraVs)
+  float4* rec = reinterpret_cast<float4*>(Vm + 32 * kGraVs);   // 2 x 16 rotation records
+  int* pq = reinterpret_cast<int*>(rec + 32);                  // 16 pairs (intra steps)
+  const int blkf = 16 * lds;            // floats per block of columns
+
+  // initial state: block slot c -> top, slot P + c -> bottom of parity 0
+  {
+    float* buf = smem;
+    for (int e = tid; e < 32 * ld4; e += kGraThreads) {
+      const int col = e / ld4, r4 = e - col * ld4;
+      const int slot = col < 16 ? c : P + c;
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(tk.x + ((int64_t)slot * 16 + (col & 15)) * ld) + r4);
+      *reinterpret_cast<float4*>(buf + col * lds + 4 * r4) = v;
+    }
+  }
+  if (tid == 0) {
+    s_rot = 0;
+    s_max = 0u;
+  }
+  __syncthreads();
+
+  // circle-method rotation of the block slots: t0 fixed; t_c -> t_{c+1}; t_{P-1} -> b_{P-1};
+  // b_c -> b_{c-1}; b_0 -> t_1   (slot index < P: top of CTA index; >= P: bottom of CTA index - P)
+  const int top_dst = (c == 0) ? 0 : (c == P - 1 ? (2 * P - 1) : c + 1);
+  const int bot_dst = (c == 0) ? 1 : (P + c - 1);
+
+  int par = 0;
+  int sweep = 0, converged = 0;
+  int nrot = 0;
+  float maxrel2 = 0.f;
+  while (sweep < max_sweeps) {
+    for (int round = -1; round < 2 * P - 1; ++round) {
+      float* buf = smem + par * bufsz;
+      float* nbuf = smem + (par ^ 1) * bufsz;
+      float* C0 = Cb;   // gram results go to buffer 0 of C
+      if (prof) t0 = clock64();
+      // ---- 1. Gram ----
+      if (round < 0) {
+        // pairs inside T and inside B: refresh both diagonal blocks from the columns
+        gra_gram16(buf, buf, part, ld4, lds, warp, lane);
+        __syncthreads();
+        if (tid < 256) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < 16; ++w) v += part[w * 256 + tid];
+          const int i = tid >> 4, j = tid & 15;
+          C0[i * kGraCs + j] = v;
+          C0[i * kGraCs + 16 + j] = 0.f;
+          C0[(16 + i) * kGraCs + j] = 0.f;
+        }
+        __syncthreads();
+        gra_gram16(buf + blkf, buf + blkf, part, ld4, lds, warp, lane);
+        __syncthreads();
+        if (tid < 256) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < 16; ++w) v += part[w * 256 + tid];
+          const int i = tid >> 4, j = tid & 15;
+          C0[(16 + i) * kGraCs + 16 + j] = v;
+        }
+      } else {
+        gra_gram16(buf, buf + blkf, part, ld4, lds, warp, lane);
+        __syncthreads();
+        if (tid < 256) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < 16; ++w) v += part[w * 256 + tid];
+          const int i = tid >> 4, j = tid & 15;
+          C0[i * kGraCs + 16 + j] = v;
+          C0[(16 + j) * kGraCs + i] = v;
+        } else {
+          // carried diagonal blocks
+          const int u = tid - 256, i = u >> 4, j = u & 15;
+          C0[i * kGraCs + j] = buf[32 * lds + u];
+          C0[(16 + i) * kGraCs + 16 + j] = buf[32 * lds + 256 + u];
+        }
+      }
+      for (int e = tid; e < 1024; e += kGraThreads) Vm[(e >> 5) * kGraVs + (e & 31)] = ((e >> 5) == (e & 31)) ? 1.f : 0.f;
+      __syncthreads();
+
+      GRA_TICK(0)
+      // ---- 2. rotate ----
+      const int cur = (round < 0) ? gra_rotate_intra(Cb, Vm, rec, pq, tid, tol2, fl, nrot, maxrel2)
+                                  : gra_rotate_cross(Cb, Vm, rec, tid, tol2, fl, nrot, maxrel2);
+      const float* Cf = Cb + cur * kGraCsz;
+      // Renormalise the columns of V.  cs and sn are rounded to fp32, so every plane rotation scales its
+      // two columns by 1 + O(6e-8) -- coherently over all k rows, unlike the per-element rounding of a
+      // column-wise rotation.  Without this the column norms (the eigenvalue estimates) drift by ~1e-4
+      // over the ~300 rounds of a solve.
+      if (tid < 32) {
+        float ss = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) ss = fmaf(Vm[i * kGraVs + tid], Vm[i * kGraVs + tid], ss);
+        float rn = mufu_rsqrt(ss);
+        rn = rn * fmaf(-0.5f * ss, rn * rn, 1.5f);
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) Vm[i * kGraVs + tid] *= rn;
+      }
+      __syncthreads();
+      GRA_TICK(1)
+
+      // ---- 3. apply, straight into the next owners' other-parity buffers ----
+      float* tbuf = nbuf;   // destination buffers (base of the other-parity buffer of the next owner)
+      float* bbuf = nbuf;
+      int tslot = 0, bslot = 1;   // 0: top half, 1: bottom half of that buffer
+      if (round >= 0 && P > 1) {
+        tslot = top_dst < P ? 0 : 1;
+        bslot = bot_dst < P ? 0 : 1;
+        tbuf = cluster.map_shared_rank(nbuf, top_dst - tslot * P);
+        bbuf = cluster.map_shared_rank(nbuf, bot_dst - bslot * P);
+      }
+      gra_apply<RL>(buf, Vm, tbuf + tslot * blkf, bbuf + bslot * blkf, ld, lds, warp, lane);
+      // the diagonal Gram blocks travel with their columns
+      if (tid < 256) {
+        const int i = tid >> 4, j = tid & 15;
+        tbuf[32 * lds + tslot * 256 + tid] = Cf[i * kGraCs + j];
+      } else {
+        const int u = tid - 256, i = u >> 4, j = u & 15;
+        bbuf[32 * lds + bslot * 256 + u] = Cf[(16 + i) * kGraCs + 16 + j];
+      }
+      __syncthreads();
+      GRA_TICK(2)
+      gra_cluster_sync();
+      GRA_TICK(3)
+      par ^= 1;
+    }
+    ++sweep;
+    // ---- convergence vote over the cluster ----
+    if (nrot) atomicAdd(&s_rot, nrot);
+    if (maxrel2 > 0.f) atomicMax(&s_max, __float_as_uint(maxrel2));
+    nrot = 0;
+    maxrel2 = 0.f;
+    __syncthreads();
+    int total;
+    unsigned mx;
+    if (P == 1) {
+      total = s_rot;
+      mx = s_max;
+      __syncthreads();
+      if (tid == 0) {
+        s_rot = 0;
+        s_max = 0u;
+      }
+    } else {
+      if (tid == 0) {
+        int* rc = cluster.map_shared_rank(s_counts, 0);
+        unsigned* rm = cluster.map_shared_rank(s_maxes, 0);
+        rc[c] = s_rot;
+        rm[c] = s_max;
+        s_rot = 0;
+        s_max = 0u;
+      }
+      gra_cluster_sync();
+      if (tid == 0) {
+        const int* rc = cluster.map_shared_rank(s_counts, 0);
+        const unsigned* rm = cluster.map_shared_rank(s_maxes, 0);
+        int t = 0;
+        unsigned m = 0u;
+        for (int i = 0; i < P; ++i) {
+          t += rc[i];
+          m = rm[i] > m ? rm[i] : m;
+        }
+        s_total = t;
+        s_maxall = m;
+      }
+      __syncthreads();
+      total = s_total;
+      mx = s_maxall;
+      gra_cluster_sync();   // CTA 0's vote arrays may be rewritten after this point
+    }
+    if (total == 0 || __uint_as_float(mx) < stop2) {
+      converged = 1;
+      break;
+    }
+  }
+
+  // final state back to global X (column order is irrelevant to the selection stage)
+  {
+    const float* buf = smem + par * bufsz;
+    for (int e = tid; e < 32 * ld4; e += kGraThreads) {
+      const int col = e / ld4, r4 = e - col * ld4;
+      const int slot = col < 16 ? c : P + c;
+      const float4 v = *reinterpret_cast<const float4*>(buf + col * lds + 4 * r4);
+      __stcg(reinterpret_cast<float4*>(tk.x + ((int64_t)slot * 16 + (col & 15)) * ld) + r4, v);
+    }
+  }
+  if (c == 0 && tid == 0) {
+    sweeps_out[prob] = sweep;
+    status_out[prob] = converged;
+  }
+  if (prof && tid == 0 && c == P - 1)
+    for (int i = 0; i < 4; ++i) atomicAdd(prof + i, (unsigned long long)pc[i]);
+#undef GRA_TICK
+}
+
+bool jacobi_gra_eligible(const tta_eig_task& tk) {
+  if (tk.bw != 16 || tk.ld > 512 || tk.ld < 4 || (tk.ld & 3)) return false;
+  if (tk.kpad % 32) return false;
+  const int P = tk.kpad / 32;
+  return P >= 2 && P <= 16;
+}
+
+static int gra_rl(int ld) { return ld <= 256 ? 4 : 8; }
+
+template <int RL>
+static int gra_launch(int P, int nprob, size_t smem, cudaStream_t gs, const tta_eig_task* tasks_dev, const int32_t* ids,
+                      int32_t* sweeps_dev, int32_t* status_dev, const float* floor2, float tol2, float stop2,
+                      int max_sweeps, unsigned long long* prof) {
+  static size_t smem_set = 0;
+  static bool np_set = false;
+  int rc;
+  if (!np_set) {
+    rc = check_cuda(cudaFuncSetAttribute(jacobi_gra_kernel<RL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
+                    "jacobi gra non-portable attribute");
+    if (rc) return rc;
+    np_set = true;
+  }
+  if (smem > smem_set) {
+    rc = check_cuda(cudaFuncSetAttribute(jacobi_gra_kernel<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "jacobi gra smem attribute");
+    if (rc) return rc;
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nprob * P), 1, 1);
+  cfg.blockDim = dim3(kGraThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = gs;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)P;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_gra_kernel<RL>, tasks_dev, ids, sweeps_dev, status_dev, floor2, tol2,
+                                     stop2, max_sweeps, prof),
+                  "jacobi gra launch");
+  if (rc) return rc;
+  count_launch();
+  return TTA_OK;
+}
+
+// Enqueue one launch (on `gs`) for the problems `ids` (device array, all with the same cluster size P
+// and the same output-column split).
+int jacobi_gra_enqueue(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs, int P,
+                       float tol2, float stop2, int max_sweeps, const int32_t* ids_dev, int32_t* sweeps_dev,
+                       int32_t* status_dev, const float* floor2, cudaStream_t gs) {
+  if (probs.empty()) return TTA_OK;
+  int ldmax = 0;
+  for (int p : probs) ldmax = th[p].ld > ldmax ? th[p].ld : ldmax;
+  const int rl = gra_rl(ldmax);
+  for (int p : probs)
+    if (gra_rl(th[p].ld) != rl) {
+      set_error("jacobi gra: mixed column lengths in one launch group");
+      return TTA_E_INVALID;
+    }
+  const size_t smem = gra_smem_bytes(ldmax);
+  const int n = (int)probs.size();
+  // TTA_GRA_PROF=1: per-phase cycle counts of the last CTA of every cluster, printed by the next call
+  static unsigned long long* prof = nullptr;
+  static bool prof_init = false;
+  if (!prof_init) {
+    prof_init = true;
+    const char* e = getenv("TTA_GRA_PROF");
+    if (e && e[0] == '1' && cudaMalloc(&prof, 4 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(prof, 0, 4 * sizeof(unsigned long long));
+  }
+  if (prof) {
+    unsigned long long h[4];
+    cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+    if (h[0] | h[1] | h[2] | h[3])
+      fprintf(stderr, "[gra prof] cycles gram %llu rotate %llu apply %llu barrier %llu\n", h[0], h[1], h[2], h[3]);
+    cudaMemset(prof, 0, sizeof(h));
+  }
+  if (rl == 4)
+    return gra_launch<4>(P, n, smem, gs, tasks_dev, ids_dev, sweeps_dev, status_dev, floor2, tol2, stop2, max_sweeps, prof);
+  return gra_launch<8>(P, n, smem, gs, tasks_dev, ids_dev, sweeps_dev, status_dev, floor2, tol2, stop2, max_sweeps, prof);
+}
+
+}  // namespace tta

@@ -6,7 +6,11 @@
 //   E_ij     = R_ij / 2                                            unresolved cluster (span-neutral)
 //   E_jj     = R_jj / 2
 //   q_j'     = q_j + sum_i q_i E_ij                                (Ogita & Aishima 2018, one step)
-// Only the r dominant columns j are formed (the truncation of ttd.py:21-23 / admm.py:132-134).
+// Only the r dominant columns j are formed (the truncation of ttd.py:21-23 / admm.py:132-134), so only
+// the rows j of S and T that can be selected are needed: refine_prepare sorts the vectors by their
+// fp32 eigenvalue estimate ||x_j|| (descending) and the caller's GEMMs form the first `wnd` rows of S
+// and T only (wnd = r + a safety margin far wider than the fp32 ordering error).  Eigenvalues of
+// vectors behind the window enter the gap denominators as their fp32 estimates.
 #include "tta_common.cuh"
 
 namespace tta {
@@ -16,60 +20,71 @@ constexpr double kRefCutRel = 4e-7;     // eigenvalues below cut_rel * lambda_ma
 constexpr double kRefGapRel = 1e-6;     // |lambda_i - lambda_j| below gap_rel * lambda_max: cluster
 constexpr double kRefMaxCorr = 0.05;    // first-order correction must stay small
 
+// qt row p = the unit vector of the p-th largest column of X; lam0[p] = its norm (0 for null columns)
 __global__ void __launch_bounds__(kRefThreads) refine_prepare_kernel(const tta_refine_task* __restrict__ tasks) {
-  __shared__ double s_max[kRefThreads / 32];
-  __shared__ double s_cut;
+  extern __shared__ double s_nrm[];   // k squared norms, then k ints (rank position)
   const tta_refine_task tk = tasks[blockIdx.x];
+  const int k = tk.k;
+  int* s_pos = reinterpret_cast<int*>(s_nrm + k);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarp = kRefThreads / 32;
-  // pass 1: largest column norm
+  for (int j = warp; j < k; j += nwarp) {
+    const float* x = tk.x + (int64_t)j * tk.ld;
+    double a = 0.0;
+    for (int e = lane; e < k; e += 32) a = fma((double)x[e], (double)x[e], a);
+    a = warp_sum(a);
+    if (lane == 0) s_nrm[j] = a;
+  }
+  __syncthreads();
   double mx = 0.0;
-  for (int j = warp; j < tk.k; j += nwarp) {
-    const float* x = tk.x + (int64_t)j * tk.ld;
-    double a = 0.0;
-    for (int e = lane; e < tk.k; e += 32) a = fma((double)x[e], (double)x[e], a);
-    a = warp_sum(a);
-    mx = a > mx ? a : mx;
-  }
-  if (lane == 0) s_max[warp] = mx;
-  __syncthreads();
-  if (tid == 0) {
-    double m = 0.0;
-    for (int i = 0; i < nwarp; ++i) m = s_max[i] > m ? s_max[i] : m;
-    s_cut = m * (kRefCutRel * kRefCutRel);
+  for (int j = 0; j < k; ++j) mx = fmax(mx, s_nrm[j]);
+  const double cut = mx * (kRefCutRel * kRefCutRel);
+  for (int j = tid; j < k; j += kRefThreads) {
+    const double aj = s_nrm[j];
+    int pos = 0;
+    for (int i = 0; i < k; ++i) {
+      const double ai = s_nrm[i];
+      pos += (ai > aj) || (ai == aj && i < j);
+    }
+    s_pos[j] = pos;
   }
   __syncthreads();
-  const double cut = s_cut;
-  // pass 2: qt row j = x_j / ||x_j||  (zero row for numerically-null columns)
-  for (int j = warp; j < tk.k; j += nwarp) {
+  for (int j = warp; j < k; j += nwarp) {
     const float* x = tk.x + (int64_t)j * tk.ld;
-    double a = 0.0;
-    for (int e = lane; e < tk.k; e += 32) a = fma((double)x[e], (double)x[e], a);
-    a = warp_sum(a);
-    const double inv = (a > cut && a > 0.0) ? 1.0 / sqrt(a) : 0.0;
-    double* q = tk.qt + (int64_t)j * tk.k;
-    for (int e = lane; e < tk.k; e += 32) q[e] = (double)x[e] * inv;
+    const double a = s_nrm[j];
+    const bool live = a > cut && a > 0.0;
+    const double inv = live ? 1.0 / sqrt(a) : 0.0;
+    const int p = s_pos[j];
+    double* q = tk.qt + (int64_t)p * k;
+    for (int e = lane; e < k; e += 32) q[e] = (double)x[e] * inv;
+    if (lane == 0) tk.lam0[p] = live ? sqrt(a) : 0.0;
   }
 }
 
+// s, t: the first wnd rows of S = Qt G Qt^T and T = Qt Qt^T (wnd x k, row-major)
 __global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_refine_task* __restrict__ tasks) {
-  extern __shared__ double s_lam[];  // k eigenvalues, then k ints (rank), then k ints (live flag)
+  extern __shared__ double s_lam[];  // k eigenvalues, then k ints (rank inside the window), r ints (selection)
   const tta_refine_task tk = tasks[blockIdx.x];
-  const int k = tk.k;
+  const int k = tk.k, wnd = tk.wnd;
   int* s_pos = reinterpret_cast<int*>(s_lam + k);
-  int* s_sel = s_pos + k;            // s_sel[p] = column index holding rank p
+  int* s_sel = s_pos + k;            // s_sel[p] = row holding rank p
   const int tid = threadIdx.x;
   for (int j = tid; j < k; j += kRefThreads) {
-    const double tjj = tk.t[(int64_t)j * k + j];
-    s_lam[j] = tjj > 0.5 ? tk.s[(int64_t)j * k + j] / tjj : 0.0;
+    if (j < wnd) {
+      const double tjj = tk.t[(int64_t)j * k + j];
+      s_lam[j] = tjj > 0.5 ? tk.s[(int64_t)j * k + j] / tjj : 0.0;
+    } else {
+      s_lam[j] = tk.lam0[j];
+    }
   }
   __syncthreads();
   double lmax = 0.0;
   for (int j = 0; j < k; ++j) lmax = fmax(lmax, s_lam[j]);
-  for (int j = tid; j < k; j += kRefThreads) {
+  // descending rank of the window rows (rows behind the window are smaller by construction)
+  for (int j = tid; j < wnd; j += kRefThreads) {
     const double lj = s_lam[j];
     int pos = 0;
-    for (int i = 0; i < k; ++i) {
+    for (int i = 0; i < wnd; ++i) {
       const double li = s_lam[i];
       pos += (li > lj) || (li == lj && i < j);
     }
@@ -83,11 +98,11 @@ __global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_ref
     const int j = s_sel[p];
     const double lj = s_lam[j], li = s_lam[i];
     const double tij = tk.t[(int64_t)j * k + i];
-    const double tii = tk.t[(int64_t)i * k + i];
+    const bool live_i = (i < wnd) ? (tk.t[(int64_t)i * k + i] > 0.5) : (li > 0.0);
     double c;
     if (i == j) {
       c = 1.0 + 0.5 * (1.0 - tij);
-    } else if (!(tii > 0.5)) {
+    } else if (!live_i) {
       c = 0.0;                                   // null direction: nothing to mix in
     } else {
       const double rij = -tij;
@@ -101,9 +116,6 @@ __global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_ref
     tk.c[idx] = c;
   }
   for (int p = tid; p < tk.r; p += kRefThreads) tk.lam[p] = s_lam[s_sel[p]];
-  if (tid == 0 && tk.r > 0) {
-    // stash lambda_max behind the r selected values? -- no: finalize recomputes the cut from lam[0]
-  }
 }
 
 // One warp per selected row: renormalise the corrected vector in fp64 (the first-order update leaves
@@ -142,9 +154,9 @@ static int validate(const tta_refine_task* th, int n, const char* what) {
   }
   for (int t = 0; t < n; ++t) {
     const tta_refine_task& tk = th[t];
-    if (tk.k <= 0 || tk.r <= 0 || tk.r > tk.k || tk.ld < tk.k || !tk.x || !tk.qt || !tk.s || !tk.t || !tk.c ||
-        !tk.lam || !tk.e64 || !tk.e) {
-      set_error("%s: task %d invalid (k=%d r=%d ld=%d)", what, t, tk.k, tk.r, tk.ld);
+    if (tk.k <= 0 || tk.r <= 0 || tk.r > tk.k || tk.wnd < tk.r || tk.wnd > tk.k || tk.ld < tk.k || !tk.x || !tk.qt ||
+        !tk.s || !tk.t || !tk.c || !tk.lam || !tk.lam0 || !tk.e64 || !tk.e) {
+      set_error("%s: task %d invalid (k=%d r=%d wnd=%d ld=%d)", what, t, tk.k, tk.r, tk.wnd, tk.ld);
       return TTA_E_INVALID;
     }
   }
@@ -160,7 +172,17 @@ int tta_refine_prepare_batched(const tta_refine_task* tasks_dev, const tta_refin
   using namespace tta;
   int rc = validate(tasks_host, n_tasks, "refine_prepare");
   if (rc || n_tasks == 0) return rc;
-  refine_prepare_kernel<<<n_tasks, kRefThreads, 0, (cudaStream_t)stream>>>(tasks_dev);
+  size_t smem = 0;
+  for (int t = 0; t < n_tasks; ++t) {
+    const size_t need = (size_t)tasks_host[t].k * 12;
+    smem = need > smem ? need : smem;
+  }
+  if (smem > 48 * 1024) {
+    rc = check_cuda(cudaFuncSetAttribute(refine_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "refine_prepare smem attribute");
+    if (rc) return rc;
+  }
+  refine_prepare_kernel<<<n_tasks, kRefThreads, smem, (cudaStream_t)stream>>>(tasks_dev);
   TTA_CHECK_LAUNCH("refine_prepare launch");
   return TTA_OK;
 }

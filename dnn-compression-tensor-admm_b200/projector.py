@@ -48,15 +48,20 @@ def clip_tt_ranks(shapes, ranks):
 def eig_geometry(k, pmax=None):
     """Column-state geometry (ld, kpad, bw) of the Jacobi solver for a k x k Gram matrix.
 
-    k <= 512: persistent cluster solver -- kpad = 2 * P * bw with P (CTAs per problem) the smallest
-    power of two such that a CTA's block width bw = ceil(k / 2P) is <= 16 (one warp per column, 512
-    threads), P <= pmax (default 16; TTA_JACOBI_PMAX overrides, then bw grows up to 32).
+    k <= 32: one CTA of the column-rotation cluster solver (P = 1, bw = ceil(k/2) rounded to even).
+    32 < k <= 512: gram-rotate-apply cluster solver -- blocks of bw = 16 columns, two blocks per CTA,
+    P = ceil(k / 32) CTAs per problem (2..16), kpad = 32 * P.
+    `pmax` (tests only) selects the geometry of the column-rotation solver for every k <= 512:
+    kpad = 2 * P * bw with P the smallest power of two <= pmax such that bw = ceil(k / 2P) <= 16.
     k > 512 (Tucker sweep): multi-launch solver, blocks of 16 (8 if shared memory is short).
     """
     ld = _round_up(k, 4)
     if ld <= 512:
+        if pmax is None and k > 32:
+            p = (k + 31) // 32
+            return ld, 32 * p, 16
         if pmax is None:
-            pmax = int(os.environ.get('TTA_JACOBI_PMAX', '16'))
+            pmax = 1
         p = 1
         while (k + 2 * p - 1) // (2 * p) > 16 and p < pmax:
             p *= 2
@@ -64,6 +69,32 @@ def eig_geometry(k, pmax=None):
         return ld, 2 * p * bw, bw
     bw = 16 if 2 * 16 * ld * 4 <= 200 * 1024 else 8
     return ld, _round_up(k, bw), bw
+
+
+_EIG_TIME_TABLE = ((8, 0.03), (32, 0.10), (64, 0.31), (130, 0.74), (256, 1.45), (512, 4.2), (1024, 40.0), (2048, 320.0))
+
+
+def eig_time_ms(k):
+    """Measured duration of one Jacobi eigensolve on B200 (log-log interpolation; scheduling model only)."""
+    tab = _EIG_TIME_TABLE
+    if k <= tab[0][0]:
+        return tab[0][1]
+    for (k0, t0), (k1, t1) in zip(tab[:-1], tab[1:]):
+        if k <= k1:
+            f = (math.log(k) - math.log(k0)) / (math.log(k1) - math.log(k0))
+            return math.exp(math.log(t0) + f * (math.log(t1) - math.log(t0)))
+    return tab[-1][1] * (k / tab[-1][0]) ** 3
+
+
+def eig_ctas(k):
+    """CTAs (= SMs) one eigenproblem occupies."""
+    return 1 if k <= 32 else min((k + 31) // 32, 16) if k <= 512 else 148
+
+
+def refine_window(k, r):
+    """Rows of S / T the refinement forms: the r selectable vectors plus a margin that is far wider
+    than the ordering error of the fp32 eigenvalue estimates (include/tta.h, tta_refine_task)."""
+    return min(k, r + max(16, (r + 7) // 8))
 
 
 def gram_splits(k, red_len):
@@ -156,12 +187,17 @@ class TTLayer:
 class TTProjectionPlan:
     """Batched TT-SVD projection of a list of layers: Z_l = Proj_TT(W_l + U_l)."""
 
-    def __init__(self, layers, device, tol=5e-7, max_sweeps=40, refine=True):
+    def __init__(self, layers, device, tol=5e-7, max_sweeps=40, refine=True, skip_full_rank=True):
         self.layers = list(layers)
         self.device = torch.device(device)
         self.tol = float(tol)
         self.max_sweeps = int(max_sweeps)
         self.refine = bool(refine)
+        # A step that keeps r == min(m, n) singular triplets truncates nothing: U S V^T is the
+        # unfolding itself, so the step is served by the exact factorisation A = I * A (m <= n) or
+        # A = A * I (m > n) without an eigensolve.  ttd.ten2tt switches this off to hand out
+        # orthonormal cores like the reference's SVD does; the product of the cores is the same.
+        self.skip_full_rank = bool(skip_full_rank)
         self.sweeps = {}
         self.profile = None
         self._bound = None
@@ -171,6 +207,7 @@ class TTProjectionPlan:
     def _alloc(self):
         dev = self.device
         self.ws = []
+        self._eyes = {}
         for L in self.layers:
             w = {'T': _Buf(L.numel, dev), 'steps': [], 'acc': {}}
             carry = w['T']
@@ -179,9 +216,17 @@ class TTProjectionPlan:
                 n = _prod(L.shapes[i + 1:])
                 k = min(m, n)
                 r = L.ranks[i + 1]
+                if self.skip_full_rank and r == k:
+                    eye = self._eye(k)
+                    # m <= n: core = I_m, carry' = A;   m > n: core = A, carry' = I_n
+                    st = dict(m=m, n=n, k=k, r=r, identity=True, A=carry,
+                              core=eye if m <= n else carry, carry=carry if m <= n else eye)
+                    w['steps'].append(st)
+                    carry = st['carry']
+                    continue
                 ld, kpad, bw = eig_geometry(k)
                 nsplit = gram_splits(k, max(m, n))
-                st = dict(m=m, n=n, k=k, r=r, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, A=carry,
+                st = dict(m=m, n=n, k=k, r=r, identity=False, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, A=carry,
                           X=_Buf(ld * kpad, dev), part=_Buf(nsplit * k * k, dev, torch.float64),
                           E=_Buf(r * k, dev), core=_Buf(m * r, dev), carry=_Buf(r * n, dev))
                 if m > n:
@@ -189,11 +234,16 @@ class TTProjectionPlan:
                     st['isigma'] = _Buf(r, dev)
                 if self.refine:
                     f64 = torch.float64
-                    for nm in ('g64', 'qt', 'y', 's', 't'):
-                        st[nm] = _Buf(k * k, dev, f64)
+                    wnd = refine_window(k, r)
+                    st['wnd'] = wnd
+                    st['g64'] = _Buf(k * k, dev, f64)
+                    st['qt'] = _Buf(k * k, dev, f64)
+                    for nm in ('y', 's', 't'):
+                        st[nm] = _Buf(wnd * k, dev, f64)
                     st['c'] = _Buf(r * k, dev, f64)
                     st['e64'] = _Buf(r * k, dev, f64)
                     st['lam'] = _Buf(r, dev, f64)
+                    st['lam0'] = _Buf(k, dev, f64)
                 w['steps'].append(st)
                 carry = st['carry']
             # reconstruction accumulators acc_j, j = 1..d-1 ; acc_0 is core_0
@@ -201,6 +251,62 @@ class TTProjectionPlan:
                 rows = _prod(L.shapes[:j + 1])
                 w['acc'][j] = _Buf(rows * L.ranks[j + 1], dev)
             self.ws.append(w)
+
+    def _eye(self, k):
+        if k not in self._eyes:
+            b = _Buf(k * k, self.device)
+            b.t[:k * k].view(k, k).copy_(torch.eye(k, dtype=torch.float32, device=self.device))
+            self._eyes[k] = b
+        return self._eyes[k]
+
+    def _schedule(self):
+        """Wave index of every real (non-identity) step.  Steps of one layer keep their order; a layer
+        with fewer real steps than the longest one may start at any offset.  A wave lasts as long as
+        its slowest eigenproblem, or as long as its total eigensolver work keeps the SMs busy, whichever
+        is longer (`eig_time_ms`, `eig_ctas`: measured on B200); flexible layers are placed, costliest
+        first, where they lengthen the sum of the wave durations least -- e.g. the k = 512 problems of
+        the 1x1 convolutions are split between the two waves that hold the big middle steps of the
+        k x k convolutions instead of adding a wave-long critical path of their own."""
+        real = [[i for i, st in enumerate(w['steps']) if not st['identity']] for w in self.ws]
+        nwaves = max((len(r) for r in real), default=0)
+        tmax = [0.0] * max(nwaves, 1)
+        work = [0.0] * max(nwaves, 1)
+        cap = 148 * 0.7      # SMs, derated for cluster packing
+
+        def dur(t, w):
+            return max(t, w / cap)
+
+        def cost(li, i):
+            k = self.ws[li]['steps'][i]['k']
+            return eig_time_ms(k), eig_time_ms(k) * eig_ctas(k)
+
+        sched = [None] * len(self.ws)
+        order = sorted(range(len(self.ws)),
+                       key=lambda li: (-len(real[li]), -sum(cost(li, i)[1] for i in real[li]), li))
+        for li in order:
+            n = len(real[li])
+            if n == 0:
+                sched[li] = {}
+                continue
+            best, best_key = 0, None
+            for off in range(nwaves - n + 1):
+                total = 0.0
+                for wv in range(nwaves):
+                    t, w = tmax[wv], work[wv]
+                    if off <= wv < off + n:
+                        ct, cw = cost(li, real[li][wv - off])
+                        t, w = max(t, ct), w + cw
+                    total += dur(t, w)
+                # ties: prefer the centre of the sequence (the long middle waves)
+                key = (round(total, 6), abs(2 * off + n - nwaves))
+                if best_key is None or key < best_key:
+                    best, best_key = off, key
+            sched[li] = {i: best + q for q, i in enumerate(real[li])}
+            for q, i in enumerate(real[li]):
+                ct, cw = cost(li, i)
+                tmax[best + q] = max(tmax[best + q], ct)
+                work[best + q] += cw
+        return nwaves, sched
 
     def max_order(self):
         return max((L.d for L in self.layers), default=0)
@@ -226,21 +332,18 @@ class TTProjectionPlan:
         self.t_unfold = rt.TaskTable(unfold, dev)
 
         self.waves = []
-        # Wave w runs TT step (w - offset_l) of layer l.  Layers with fewer steps are centred in the wave
-        # sequence so that their big eigenproblems (k = O of a 1x1 conv) share a wave with the big
-        # middle steps of the k x k convs instead of adding a wave-long critical path of their own.
-        nwaves = self.max_order() - 1
-        offset = [(nwaves - (L.d - 1)) // 2 for L in self.layers]
+        nwaves, sched = self._schedule()
         for wv in range(nwaves):
-            idx = [li for li, L in enumerate(self.layers) if 0 <= wv - offset[li] < L.d - 1]
+            members = [(li, i) for li in range(nL) for i, w_ in sched[li].items() if w_ == wv]
+            idx = [li for li, _ in members]
             g = np.zeros(len(idx), dtype=rt.GRAM_TASK)
             e = np.zeros(len(idx), dtype=rt.EIG_TASK)
             s = np.zeros(len(idx), dtype=rt.SELECT_TASK)
             mm = np.zeros(len(idx), dtype=rt.GEMM_TASK)
             rf = np.zeros(len(idx), dtype=rt.REFINE_TASK)
             dg = [np.zeros(len(idx), dtype=rt.GEMM_TASK) for _ in range(4)]
-            for q, li in enumerate(idx):
-                st = self.ws[li]['steps'][wv - offset[li]]
+            for q, (li, si) in enumerate(members):
+                st = self.ws[li]['steps'][si]
                 m, n, k, r = st['m'], st['n'], st['k'], st['r']
                 a = st['A'].ptr
                 g64 = st['g64'].ptr if self.refine else 0
@@ -258,13 +361,14 @@ class TTProjectionPlan:
                 e[q] = (st['X'].ptr, k, st['ld'], st['kpad'], st['bw'])
                 if self.refine:
                     sel = s[q]
+                    wnd = st['wnd']
                     rf[q] = (st['X'].ptr, st['qt'].ptr, st['s'].ptr, st['t'].ptr, st['c'].ptr, st['lam'].ptr,
-                             st['e64'].ptr, sel['e'], sel['et'], sel['se'], sel['sigma'], sel['isigma'],
-                             k, st['ld'], r, 0)
+                             st['lam0'].ptr, st['e64'].ptr, sel['e'], sel['et'], sel['se'], sel['sigma'],
+                             sel['isigma'], k, st['ld'], r, wnd)
                     qt = st['qt'].ptr
-                    dg[0][q] = (qt, st['g64'].ptr, st['y'].ptr, 0, k, 1, k, 1, k, k, k, k, 0)      # y = qt * g64
-                    dg[1][q] = (st['y'].ptr, qt, st['s'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)        # s = y * qt^T
-                    dg[2][q] = (qt, qt, st['t'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)                 # t = qt * qt^T
+                    dg[0][q] = (qt, st['g64'].ptr, st['y'].ptr, 0, k, 1, k, 1, k, wnd, k, k, 0)    # y = qt[:wnd] * g64
+                    dg[1][q] = (st['y'].ptr, qt, st['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)      # s = y * qt^T
+                    dg[2][q] = (qt, qt, st['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)               # t = qt[:wnd] * qt^T
                     dg[3][q] = (st['c'].ptr, qt, st['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)      # e64 = c * qt
             wave = dict(idx=idx, gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev),
                         select=rt.TaskTable(s, dev), gemm=rt.TaskTable(mm, dev))
@@ -312,9 +416,7 @@ class TTProjectionPlan:
             ph.mark('gram')
             rt.gram(wave['gram'])
             ph.mark('eig')
-            sw = rt.jacobi_eigh(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
-            for q, li in enumerate(wave['idx']):
-                self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
+            rt.jacobi_eigh_async(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
             ph.mark('select')
             if self.refine:
                 rt.refine_prepare(wave['refine'])
@@ -334,6 +436,11 @@ class TTProjectionPlan:
         if self.t_fold.n:
             rt.fold_store(self.t_fold)
         ph.finish()
+        # one host synchronisation per update: sweep counts / convergence status of every wave
+        for wave in self.waves:
+            sw = rt.jacobi_results(wave['eig'], wave['scratch'], self.max_sweeps)
+            for q, li in enumerate(wave['idx']):
+                self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
 
     def cores(self, li):
         """Cores of layer `li` after `run()` as tensors shaped (r_i, s_i, r_{i+1}) (ten2tt's return)."""
@@ -372,12 +479,13 @@ class EigBatch:
         ld, kpad, bw = eig_geometry(k)
         nsplit = gram_splits(k, red_len)
         f64 = torch.float64
-        b = dict(k=k, r=r, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, X=_Buf(ld * kpad, dev),
+        wnd = refine_window(k, r)
+        b = dict(k=k, r=r, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, wnd=wnd, X=_Buf(ld * kpad, dev),
                  part=_Buf(nsplit * k * k, dev, f64), E=_Buf(r * k, dev),
                  ET=_Buf(r * k, dev) if want_et else None,
-                 g64=_Buf(k * k, dev, f64), qt=_Buf(k * k, dev, f64), y=_Buf(k * k, dev, f64),
-                 s=_Buf(k * k, dev, f64), t=_Buf(k * k, dev, f64), c=_Buf(r * k, dev, f64),
-                 e64=_Buf(r * k, dev, f64), lam=_Buf(r, dev, f64))
+                 g64=_Buf(k * k, dev, f64), qt=_Buf(k * k, dev, f64), y=_Buf(wnd * k, dev, f64),
+                 s=_Buf(wnd * k, dev, f64), t=_Buf(wnd * k, dev, f64), c=_Buf(r * k, dev, f64),
+                 e64=_Buf(r * k, dev, f64), lam=_Buf(r, dev, f64), lam0=_Buf(k, dev, f64))
         self.bufs[key] = b
         return b
 
@@ -396,12 +504,13 @@ class EigBatch:
             g[q] = (op['a'], b['part'].ptr, b['X'].ptr, b['g64'].ptr, op['si'], op['sb'], op['sc'], k,
                     op['nb'], op['nc'], b['nsplit'], b['ld'], b['kpad'])
             e[q] = (b['X'].ptr, k, b['ld'], b['kpad'], b['bw'])
-            rf[q] = (b['X'].ptr, b['qt'].ptr, b['s'].ptr, b['t'].ptr, b['c'].ptr, b['lam'].ptr, b['e64'].ptr,
-                     b['E'].ptr, b['ET'].ptr if b['ET'] is not None else 0, 0, 0, 0, k, b['ld'], r, 0)
+            wnd = b['wnd']
+            rf[q] = (b['X'].ptr, b['qt'].ptr, b['s'].ptr, b['t'].ptr, b['c'].ptr, b['lam'].ptr, b['lam0'].ptr,
+                     b['e64'].ptr, b['E'].ptr, b['ET'].ptr if b['ET'] is not None else 0, 0, 0, 0, k, b['ld'], r, wnd)
             qt = b['qt'].ptr
-            dg[0][q] = (qt, b['g64'].ptr, b['y'].ptr, 0, k, 1, k, 1, k, k, k, k, 0)
-            dg[1][q] = (b['y'].ptr, qt, b['s'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)
-            dg[2][q] = (qt, qt, b['t'].ptr, 0, k, 1, 1, k, k, k, k, k, 0)
+            dg[0][q] = (qt, b['g64'].ptr, b['y'].ptr, 0, k, 1, k, 1, k, wnd, k, k, 0)
+            dg[1][q] = (b['y'].ptr, qt, b['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
+            dg[2][q] = (qt, qt, b['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
             dg[3][q] = (b['c'].ptr, qt, b['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)
         tabs = dict(gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev), refine=rt.TaskTable(rf, dev),
                     d_yt=rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev), d_s=rt.TaskTable(dg[1], dev),

@@ -33,9 +33,9 @@ GEMM_TASK = np.dtype([('a', P), ('b', P), ('c', P), ('colscale', P), ('sai', np.
                       ('sbk', np.int64), ('sbj', np.int64), ('ldc', np.int64), ('M', np.int32),
                       ('N', np.int32), ('K', np.int32), ('pad_', np.int32)], align=True)
 SQNORM_TASK = np.dtype([('x', P), ('n', np.int64)], align=True)
-REFINE_TASK = np.dtype([('x', P), ('qt', P), ('s', P), ('t', P), ('c', P), ('lam', P), ('e64', P), ('e', P),
-                        ('et', P), ('se', P), ('sigma', P), ('isigma', P), ('k', np.int32), ('ld', np.int32),
-                        ('r', np.int32), ('pad_', np.int32)], align=True)
+REFINE_TASK = np.dtype([('x', P), ('qt', P), ('s', P), ('t', P), ('c', P), ('lam', P), ('lam0', P), ('e64', P),
+                        ('e', P), ('et', P), ('se', P), ('sigma', P), ('isigma', P), ('k', np.int32),
+                        ('ld', np.int32), ('r', np.int32), ('wnd', np.int32)], align=True)
 
 STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.itemsize,
                 'tta_gram_task': GRAM_TASK.itemsize, 'tta_eig_task': EIG_TASK.itemsize,
@@ -43,10 +43,11 @@ STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.item
                 'tta_sqnorm_task': SQNORM_TASK.itemsize, 'tta_refine_task': REFINE_TASK.itemsize}
 
 EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_device', 'tta_jacobi_profile_enable',
-           'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch', 'tta_dual_update_multi',
+           'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch', 'tta_jacobi_enable_gra',
+           'tta_jacobi_set_stop_rel', 'tta_dual_update_multi',
            'tta_penalty_fwd_multi', 'tta_penalty_bwd_multi', 'tta_unfold_add_batched',
            'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
-           'tta_jacobi_scratch_bytes', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
+           'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
            'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16']
@@ -89,6 +90,10 @@ def _load():
     lib.tta_jacobi_profile_enable.restype = None
     lib.tta_jacobi_force_multilaunch.argtypes = [ci]
     lib.tta_jacobi_force_multilaunch.restype = None
+    lib.tta_jacobi_enable_gra.argtypes = [ci]
+    lib.tta_jacobi_enable_gra.restype = None
+    lib.tta_jacobi_set_stop_rel.argtypes = [cf]
+    lib.tta_jacobi_set_stop_rel.restype = None
     lib.tta_jacobi_profile_read.argtypes = [vp, vp]
     lib.tta_jacobi_profile_read.restype = None
     lib.tta_check_device.argtypes = [ci]
@@ -101,6 +106,7 @@ def _load():
     lib.tta_jacobi_eigh_batched.argtypes = [vp, vp, ci, cf, ci, vp, cs, vp, vp]
     lib.tta_jacobi_scratch_bytes.argtypes = [vp, ci]
     lib.tta_jacobi_scratch_bytes.restype = cs
+    lib.tta_jacobi_read_results.argtypes = [vp, vp, ci, ci, vp]
     lib.tta_select_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_gemm_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_sqnorm_batched.argtypes = [vp, vp, ci, vp, vp]
@@ -116,7 +122,8 @@ def _load():
     lib.tta_im2col_bf16.argtypes = [vp, vp] + [ci] * 16 + [vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
-                        'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch'):
+                        'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
+                        'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel'):
             getattr(lib, name).restype = ci
     _LIB = lib
     return lib
@@ -213,6 +220,27 @@ def jacobi_scratch_bytes(tab):
     return int(lib().tta_jacobi_scratch_bytes(tab.host_ptr, tab.n))
 
 
+def jacobi_eigh_async(tab, scratch, tol=5e-7, max_sweeps=40):
+    """Enqueue only (no host synchronisation); collect with `jacobi_results` after a stream sync.
+    Problems that need the multi-launch solver (k > 512) still synchronise inside the call."""
+    _check(lib().tta_jacobi_eigh_batched(tab.dev_ptr, tab.host_ptr, tab.n, float(tol), int(max_sweeps),
+                                         ctypes.c_void_p(scratch.data_ptr()),
+                                         scratch.numel() * scratch.element_size(), None, stream_handle()),
+           'tta_jacobi_eigh_batched')
+
+
+def jacobi_results(tab, scratch, max_sweeps=40):
+    """Sweep counts of an earlier `jacobi_eigh_async` (raises TtaError if a problem did not converge)."""
+    sweeps = np.zeros(max(tab.n, 1), dtype=np.int32)
+    if tab.n == 0:
+        return sweeps[:0]
+    host = scratch[:6 * tab.n].cpu().numpy() if _FAKE is None else scratch[:6 * tab.n].numpy()
+    host = np.ascontiguousarray(host, dtype=np.int32)
+    _check(lib().tta_jacobi_read_results(ctypes.c_void_p(host.ctypes.data), tab.host_ptr, tab.n, int(max_sweeps),
+                                         ctypes.c_void_p(sweeps.ctypes.data)), 'tta_jacobi_read_results')
+    return sweeps[:tab.n]
+
+
 def jacobi_eigh(tab, scratch, tol=5e-7, max_sweeps=40):
     sweeps = np.zeros(max(tab.n, 1), dtype=np.int32)
     _check(lib().tta_jacobi_eigh_batched(tab.dev_ptr, tab.host_ptr, tab.n, float(tol), int(max_sweeps),
@@ -298,6 +326,17 @@ def launch_count():
 def jacobi_force_multilaunch(on):
     if _FAKE is None:
         lib().tta_jacobi_force_multilaunch(int(bool(on)))
+
+
+def jacobi_enable_gra(on):
+    """Test hook: False keeps 32 < k <= 512 problems on the column-rotation cluster kernel."""
+    if _FAKE is None:
+        lib().tta_jacobi_enable_gra(int(bool(on)))
+
+
+def jacobi_set_stop_rel(stop_rel):
+    if _FAKE is None:
+        lib().tta_jacobi_set_stop_rel(float(stop_rel))
 
 
 def jacobi_profile(enable):

@@ -128,6 +128,12 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
                             int n_tasks, float tol, int max_sweeps, int32_t* scratch_dev,
                             size_t scratch_bytes, int32_t* sweeps_out, void* stream);
 size_t tta_jacobi_scratch_bytes(const tta_eig_task* tasks_host, int n_tasks);
+/* Asynchronous use: with sweeps_out == NULL (and every problem on a persistent cluster solver, k <= 512)
+ * tta_jacobi_eigh_batched only enqueues work and returns without a host synchronisation.  After the
+ * stream has been synchronised, copy the first 6*n_tasks int32 of the scratch buffer to the host and
+ * pass them here: fills sweeps_out (nullable) and returns TTA_E_NOCONV if a problem did not converge. */
+int tta_jacobi_read_results(const int32_t* scratch_host, const tta_eig_task* tasks_host, int n_tasks,
+                            int max_sweeps, int32_t* sweeps_out);
 /* Profiling aid for bench.py: when enabled, every sweep's launch sequence is bracketed by CUDA events
  * on `stream` (no host sync inside the bracket) and the elapsed device time / number of
  * jacobi_step launches are accumulated.  `tta_jacobi_profile_read` returns and clears them. */
@@ -136,6 +142,13 @@ void tta_jacobi_profile_enable(int on);
  * ld <= 512 whose geometry is kpad == 2*P*bw, P in {1,2,4,8,16}, bw even <= 32, run on the persistent
  * thread-block-cluster solver; the rest -- k up to 2048 in the Tucker sweep -- on the multi-launch one). */
 void tta_jacobi_force_multilaunch(int on);
+/* Test hook: 0 keeps 32 < k <= 512 problems on the column-rotation cluster kernel instead of the
+ * gram-rotate-apply kernel (geometry bw == 16, kpad == 32*P, 2 <= P <= 16).  Default 1. */
+void tta_jacobi_enable_gra(int on);
+/* Gram-rotate-apply solver: stop after a sweep whose largest |c_pq|/sqrt(c_pp c_qq), seen before
+ * rotating, is below stop_rel (the sweep leaves off-diagonals ~ stop_rel^2).  Default 3e-4;
+ * 0 = stop only after a sweep without rotations. */
+void tta_jacobi_set_stop_rel(float stop_rel);
 void tta_jacobi_profile_read(double* step_ms, unsigned long long* step_launches);
 
 /* ---------------------------------------------------------------------------------------------
@@ -183,28 +196,34 @@ int tta_gemm_f64_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* ta
  * fp64 refinement of the fp32 Jacobi eigenvectors (one Ogita-Aishima step) fused with the dominant-r
  * selection.  Thousands of fp32 plane rotations leave an O(1e-5) error in the invariant subspace;
  * one first-order correction computed from S = Q^T G Q and T = Q^T Q in fp64 squares it away.
+ * Only the r dominant vectors are corrected, so only the rows of S and T that can be selected are
+ * formed: the vectors are first sorted by their fp32 eigenvalue estimate and the GEMMs compute the
+ * first `wnd` rows (wnd >= r plus a safety margin against the fp32 ordering error).
  * Sequence per problem (all batched):
- *   refine_prepare : qt (k x k fp64, row j = x_j / ||x_j||)               from the Jacobi state x
- *   3 x gemm_f64   : y = qt * g64 ; s = y * qt^T ; t = qt * qt^T           (caller enqueues these)
- *   refine_coeff   : lambda_j = s_jj / t_jj, descending rank, and for each of the r dominant j the
- *                    coefficient row c[p,:] = e_j + (first-order correction)  (r x k fp64)
+ *   refine_prepare : qt (k x k fp64, row p = unit vector of the p-th largest column of x) and
+ *                    lam0[p] = that column's norm                                from the Jacobi state x
+ *   3 x gemm_f64   : y = qt[0:wnd] * g64 ; s = y * qt^T ; t = qt[0:wnd] * qt^T   (caller enqueues these)
+ *   refine_coeff   : lambda_j = s_jj / t_jj inside the window (lam0 behind it), descending rank, and for
+ *                    each of the r dominant j the coefficient row c[p,:] = e_j + (first-order
+ *                    correction)  (r x k fp64)
  *   1 x gemm_f64   : e64 = c * qt                                          (caller enqueues)
  *   refine_finalize: e / et / se / sigma / isigma in fp32 -- same outputs as tta_select_batched
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* x;   /* Jacobi state: kpad columns of length ld                   */
   double* qt;       /* k x k                                                     */
-  const double* s;  /* k x k                                                     */
-  const double* t;  /* k x k                                                     */
+  const double* s;  /* wnd x k                                                   */
+  const double* t;  /* wnd x k                                                   */
   double* c;        /* r x k                                                     */
   double* lam;      /* r      refined eigenvalues of the selected vectors        */
+  double* lam0;     /* k      fp32 eigenvalue estimates in sorted order          */
   const double* e64;/* r x k                                                     */
   float* e;
   float* et;        /* nullable */
   float* se;        /* nullable */
   float* sigma;     /* nullable */
   float* isigma;    /* nullable */
-  int32_t k, ld, r, pad_;
+  int32_t k, ld, r, wnd;
 } tta_refine_task;
 
 int tta_refine_prepare_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host,

@@ -142,7 +142,17 @@ class FakeTTA:
             x[:k, :k] = (v[:, order] * lam[order]).T.astype(np.float32)
             if sw is not None:
                 sw[i] = 7
+        # asynchronous mode (sweeps_out == NULL): results are left in the scratch buffer
+        sc = _view(_val(scratch), 6 * n, np.int32)
+        sc[2 * n:3 * n] = 7
+        sc[5 * n:6 * n] = 1
         return 0
+
+    def tta_jacobi_read_results(self, scratch_host, thost, n, max_sweeps, sweeps_out):
+        sc = _view(_val(scratch_host), 6 * n, np.int32)
+        if _val(sweeps_out):
+            _view(_val(sweeps_out), n, np.int32)[:] = sc[2 * n:3 * n]
+        return 0 if np.all(sc[5 * n:6 * n] != 0) else -4
 
     def tta_select_batched(self, tdev, thost, n, stream):
         self.calls.append('select')
@@ -178,19 +188,27 @@ class FakeTTA:
             x = _view(tk['x'], ld * k).reshape(k, ld)[:, :k].astype(np.float64)
             nrm2 = np.sum(x * x, axis=1)
             cut = nrm2.max() * (4e-7) ** 2 if k else 0.0
-            inv = np.where((nrm2 > cut) & (nrm2 > 0), 1.0 / np.sqrt(np.where(nrm2 > 0, nrm2, 1.0)), 0.0)
-            _view(tk['qt'], k * k, np.float64).reshape(k, k)[:] = x * inv[:, None]
+            live = (nrm2 > cut) & (nrm2 > 0)
+            inv = np.where(live, 1.0 / np.sqrt(np.where(nrm2 > 0, nrm2, 1.0)), 0.0)
+            order = np.argsort(-nrm2, kind='stable')
+            _view(tk['qt'], k * k, np.float64).reshape(k, k)[:] = (x * inv[:, None])[order]
+            _view(tk['lam0'], k, np.float64)[:] = np.where(live, np.sqrt(nrm2), 0.0)[order]
         return 0
 
     def tta_refine_coeff_batched(self, tdev, thost, n, stream):
         self.calls.append('refine_coeff')
         for tk in _table(thost, n, rt.REFINE_TASK):
-            k, r = int(tk['k']), int(tk['r'])
-            S = _view(tk['s'], k * k, np.float64).reshape(k, k)
-            T = _view(tk['t'], k * k, np.float64).reshape(k, k)
-            tdiag = np.diag(T)
-            lam = np.where(tdiag > 0.5, np.diag(S) / np.where(tdiag > 0.5, tdiag, 1.0), 0.0)
-            order = np.argsort(-lam, kind='stable')[:r]
+            k, r, wnd = int(tk['k']), int(tk['r']), int(tk['wnd'])
+            S = _view(tk['s'], wnd * k, np.float64).reshape(wnd, k)
+            T = _view(tk['t'], wnd * k, np.float64).reshape(wnd, k)
+            lam0 = _view(tk['lam0'], k, np.float64)
+            tdiag = np.ones(k)
+            tdiag[:wnd] = T[np.arange(wnd), np.arange(wnd)]
+            sdiag = S[np.arange(wnd), np.arange(wnd)]
+            lam = lam0.copy()
+            lam[:wnd] = np.where(tdiag[:wnd] > 0.5, sdiag / np.where(tdiag[:wnd] > 0.5, tdiag[:wnd], 1.0), 0.0)
+            live = np.where(np.arange(k) < wnd, tdiag > 0.5, lam > 0.0)
+            order = np.argsort(-lam[:wnd], kind='stable')[:r]
             lmax = lam.max()
             C = np.zeros((r, k))
             for p, j in enumerate(order):
@@ -201,7 +219,7 @@ class FakeTTA:
                     e = (S[j] + lam[j] * rrow) / gap
                 use = (np.abs(gap) > 1e-6 * lmax) & (np.abs(e) <= 0.05)
                 c = np.where(use, e, c)
-                c = np.where(tdiag > 0.5, c, 0.0)
+                c = np.where(live, c, 0.0)
                 c[j] = 1.0 + 0.5 * (1.0 - T[j, j])
                 C[p] = c
             _view(tk['c'], r * k, np.float64).reshape(r, k)[:] = C

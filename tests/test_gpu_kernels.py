@@ -135,13 +135,14 @@ def _eig_problem(k, rng, spectrum='flat'):
 
 @pytest.mark.parametrize('ks', [[8], [64, 75, 16], [130, 240], [512], [256, 32, 480]])
 def test_jacobi_eigh_and_select(ks):
+    import projector
     rng = np.random.RandomState(5)
     Gs = [_eig_problem(k, rng, 'decay' if i % 2 else 'flat') for i, k in enumerate(ks)]
     etab = np.zeros(len(ks), dtype=rt.EIG_TASK)
     stab = np.zeros(len(ks), dtype=rt.SELECT_TASK)
     bufs = []
     for i, (k, G) in enumerate(zip(ks, Gs)):
-        ld, kpad, bw = (k + 3) // 4 * 4, (k + 15) // 16 * 16, 16
+        ld, kpad, bw = projector.eig_geometry(k)
         X = np.zeros((kpad, ld), dtype=np.float32)
         X[:k, :k] = G.T
         x = _t(X.reshape(-1))
@@ -165,7 +166,9 @@ def test_jacobi_eigh_and_select(ks):
         X = x.cpu().numpy().reshape(kpad, ld)[:k, :k].astype(np.float64)   # rows = columns x_j
         lam = np.linalg.norm(X, axis=1)
         ref = np.linalg.eigvalsh(G.astype(np.float64))[::-1]
-        assert np.max(np.abs(np.sort(lam)[::-1] - ref)) <= 2e-5 * ref[0]    # eigenvalues: 2e-5 * lambda_max
+        # column norms are the pre-refinement eigenvalue estimates: the rotations are applied as fp32
+        # 32 x 32 matrices, whose rounding is coherent over the rows of a column (5e-5 * lambda_max)
+        assert np.max(np.abs(np.sort(lam)[::-1] - ref)) <= 5e-5 * ref[0]
         E = e.cpu().numpy().reshape(r, k).astype(np.float64)
         assert np.max(np.abs(E @ E.T - np.eye(r))) <= 2e-5                   # orthonormal rows
         # invariant-subspace residual ||G E^T - E^T (E G E^T)|| relative to lambda_max
@@ -257,7 +260,9 @@ def test_refinement_reaches_fp64_subspace(k, r):
     rng = np.random.RandomState(9)
     A = rng.randn(k, 3 * k)
     G64 = A @ A.T
-    ld, kpad = (k + 3) // 4 * 4, (k + 15) // 16 * 16
+    import projector
+    ld, kpad, bw = projector.eig_geometry(k)
+    wnd = projector.refine_window(k, r)
     X = np.zeros((kpad, ld), dtype=np.float32)
     X[:k, :k] = G64.astype(np.float32).T
     x = _t(X.reshape(-1))
@@ -266,17 +271,18 @@ def test_refinement_reaches_fp64_subspace(k, r):
     qt, y, s, t = (torch.empty(k * k, **f64) for _ in range(4))
     c, e64 = torch.empty(r * k, **f64), torch.empty(r * k, **f64)
     lam = torch.empty(r, **f64)
+    lam0 = torch.empty(k, **f64)
     e = torch.empty(r * k, device=DEV)
     et = torch.empty(r * k, device=DEV)
     sg = torch.empty(r, device=DEV)
     etab = np.zeros(1, dtype=rt.EIG_TASK)
-    etab[0] = (x.data_ptr(), k, ld, kpad, 16)
+    etab[0] = (x.data_ptr(), k, ld, kpad, bw)
     tab = rt.TaskTable(etab, DEV)
     scratch = torch.empty(rt.jacobi_scratch_bytes(tab) // 4 + 16, dtype=torch.int32, device=DEV)
     rt.jacobi_eigh(tab, scratch, tol=2e-6, max_sweeps=40)
     rf = np.zeros(1, dtype=rt.REFINE_TASK)
-    rf[0] = (x.data_ptr(), qt.data_ptr(), s.data_ptr(), t.data_ptr(), c.data_ptr(), lam.data_ptr(), e64.data_ptr(),
-             e.data_ptr(), et.data_ptr(), 0, sg.data_ptr(), 0, k, ld, r, 0)
+    rf[0] = (x.data_ptr(), qt.data_ptr(), s.data_ptr(), t.data_ptr(), c.data_ptr(), lam.data_ptr(), lam0.data_ptr(),
+             e64.data_ptr(), e.data_ptr(), et.data_ptr(), 0, sg.data_ptr(), 0, k, ld, r, wnd)
     rtab = rt.TaskTable(rf, DEV)
 
     def dg(a, b, cc, sai, sak, sbk, sbj, ldc, M, N, K):
@@ -285,9 +291,9 @@ def test_refinement_reaches_fp64_subspace(k, r):
         rt.gemm_f64(rt.TaskTable(tb, DEV))
 
     rt.refine_prepare(rtab)
-    dg(qt, g64, y, k, 1, k, 1, k, k, k, k)
-    dg(y, qt, s, k, 1, 1, k, k, k, k, k)
-    dg(qt, qt, t, k, 1, 1, k, k, k, k, k)
+    dg(qt, g64, y, k, 1, k, 1, k, wnd, k, k)      # only the rows that can be selected (first wnd after sorting)
+    dg(y, qt, s, k, 1, 1, k, k, wnd, k, k)
+    dg(qt, qt, t, k, 1, 1, k, k, wnd, k, k)
     rt.refine_coeff(rtab)
     dg(c, qt, e64, k, 1, k, 1, k, r, k, k)
     rt.refine_finalize(rtab)
@@ -337,7 +343,7 @@ def test_jacobi_cluster_and_multilaunch_paths_agree(multilaunch):
         X = x.cpu().numpy().reshape(kpad, ld).astype(np.float64)
         lam = np.sort(np.linalg.norm(X, axis=1))[::-1]
         ref = np.linalg.eigvalsh(G.astype(np.float64))[::-1]
-        assert np.max(np.abs(lam[:k] - ref)) <= 2e-5 * ref[0], (k, multilaunch)
+        assert np.max(np.abs(lam[:k] - ref)) <= 5e-5 * ref[0], (k, multilaunch)
         assert np.all(lam[k:] <= 1e-6 * ref[0])                       # padded columns stay (numerically) zero
         Xn = X[np.argsort(-np.linalg.norm(X, axis=1))[:k]]
         Q = Xn / np.linalg.norm(Xn, axis=1, keepdims=True)
