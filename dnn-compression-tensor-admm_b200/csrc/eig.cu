@@ -35,16 +35,17 @@ struct JacItem {
 
 constexpr int kJacMaxBw = 16;
 constexpr int kJacThreads = kJacMaxBw * 32;
-constexpr float kJacFloorRel = 1e-7f;  // columns below floor_rel * max column norm are numerically zero
 
-// floor2[p] = (floor_rel * max_j ||x_j||)^2
+// floor2[p] = max_j ||x_j||^2 (raw bits of a non-negative float, so atomicMax on the integer view is the
+// float maximum); the solvers scale it by floor_rel^2 when they read it.  kFloorSplit CTAs per problem.
+constexpr int kFloorSplit = 8;
 __global__ void __launch_bounds__(256) jacobi_floor_kernel(const tta_eig_task* __restrict__ tasks,
                                                           float* __restrict__ floor2) {
   __shared__ float s_max[8];
   const tta_eig_task tk = tasks[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float mx = 0.f;
-  for (int j = warp; j < tk.k; j += 8) {
+  for (int j = blockIdx.y * 8 + warp; j < tk.k; j += 8 * kFloorSplit) {
     const float* x = tk.x + (int64_t)j * tk.ld;
     float a = 0.f;
     for (int e = lane; e < tk.k; e += 32) a = fmaf(x[e], x[e], a);
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) jacobi_floor_kernel(const tta_eig_task* _
   if (threadIdx.x == 0) {
     float m = 0.f;
     for (int i = 0; i < 8; ++i) m = fmaxf(m, s_max[i]);
-    floor2[blockIdx.x] = m * (kJacFloorRel * kJacFloorRel);
+    atomicMax(reinterpret_cast<unsigned*>(floor2) + blockIdx.x, __float_as_uint(m));
   }
 }
 
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(kJacThreads) jacobi_step_kernel(const JacItem*
   }
   __syncthreads();
 
-  const float fl = floor2[it.prob];
+  const float fl = floor2[it.prob] * (kJacFloorRel * kJacFloorRel);
   float* nrm = cols + 2 * bw * ld;     // cached squared norms (2*bw floats behind the columns)
   int nrot;
   const int nv = (ld + 127) >> 7;
@@ -312,7 +313,7 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     if (rc) return rc;
   }
 
-  jacobi_floor_kernel<<<n_tasks, 256, 0, st>>>(tasks_dev, floor2);
+  jacobi_floor_kernel<<<dim3(n_tasks, kFloorSplit), 256, 0, st>>>(tasks_dev, floor2);
   TTA_CHECK_LAUNCH("jacobi floor launch");
 
   cudaEvent_t cev0 = nullptr, cev1 = nullptr;

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
   cg::cluster_group cluster = cg::this_cluster();
   const int prob = prob_ids[blockIdx.x / cluster.num_blocks()];
   const tta_eig_task tk = tasks[prob];
-  const float fl = floor2[prob];
+  const float fl = floor2[prob] * (kJacFloorRel * kJacFloorRel);
   switch ((tk.ld + 127) >> 7) {
     case 1: cluster_body<1>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
     case 2: cluster_body<2>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
@@ -172,8 +172,15 @@ static StreamPool* pool_for_device(int dev) {
   auto it = pools.find(dev);
   if (it != pools.end()) return it->second;
   StreamPool* p = new StreamPool();
+  // Stream i serves the i-th largest cluster size of a call: descending priority, so that when SMs
+  // free up the block scheduler places the big clusters (the critical path of a wave) first and the
+  // small problems fill the SMs that are left.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // hi is numerically the smallest
   for (int i = 0; i < kPoolStreams; ++i) {
-    if (cudaStreamCreateWithFlags(&p->s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    int prio = prio_hi + i;
+    if (prio > prio_lo) prio = prio_lo;
+    if (cudaStreamCreateWithPriority(&p->s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
   if (cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;

@@ -6,6 +6,8 @@
 
 namespace tta {
 
+constexpr float kJacFloorRel = 1e-7f;  // columns below floor_rel * max column norm are numerically zero
+
 // round `r` of the circle-method tournament on n (even) players; pair q in [0, n/2)
 __host__ __device__ inline void rr_pair(int n, int r, int q, int& p0, int& p1) {
   if (q == 0) {

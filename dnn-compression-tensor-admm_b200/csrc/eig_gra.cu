@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kGraThreads, 1)
   const int c = (int)cluster.block_rank();
   const int prob = prob_ids[blockIdx.x / P];
   const tta_eig_task tk = tasks[prob];
-  const float fl = floor2[prob];
+  const float fl = floor2[prob] * (kJacFloorRel * kJacFloorRel);
   const int ld = tk.ld, ld4 = ld >> 2, lds = gra_lds(ld);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bufsz = gra_buf_floats(ld);

@@ -23,20 +23,35 @@ struct GramTable {
   int start[kGramMaxTasks + 1];
 };
 
+// tile class of a problem: 0 = 32 x 32 (k <= 32), 1 = 64 x 64, 2 = 128 x 128 (k > 64 and a reduction long
+// enough that the coarser tiling still yields enough work items)
+__host__ __device__ inline int gram_class(const tta_gram_task& tk) {
+  if (tk.k <= 32) return 0;
+  if (tk.k <= kGramT) return 1;
+  return ((int64_t)tk.nb * tk.nc >= 1536) ? 2 : 1;
+}
+__host__ __device__ inline int gram_tile(int cls) { return cls == 0 ? 32 : cls == 1 ? 64 : 128; }
+
 __device__ __forceinline__ int64_t gram_off(const tta_gram_task& tk, int64_t rho) {
   if (tk.nb == 1) return rho * tk.sc;
   const int64_t b = rho / tk.nc;
   return b * tk.sb + (rho - b * tk.nc) * tk.sc;
 }
 
+// TS x TS output tiles, TT x TT outputs per thread: <64, 4> for 32 < k <= 64, <32, 2> for k <= 32 (the
+// first and last TT steps of a k x k convolution have k = r <= 32 and a reduction length of up to
+// 73 728: a 64-wide tile would spend 3/4 .. 15/16 of its DFMAs on padding).
+template <int TS, int TT>
 __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task* __restrict__ tasks,
                                                             const __grid_constant__ GramTable tab) {
-  __shared__ __align__(16) double As[kGramBK][kGramT + 2];
-  __shared__ __align__(16) double Bs[kGramBK][kGramT + 2];
+  __shared__ __align__(16) double As[kGramBK][TS + 2];
+  __shared__ __align__(16) double Bs[kGramBK][TS + 2];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int r0 = (warp & 1) * 32 + (lane >> 2) * 4;  // rows of this thread inside the tile
-  const int c0 = (warp >> 1) * 16 + (lane & 3) * 4;  // cols
+  const int r0 = (warp & 1) * (TS / 2) + (lane >> 2) * TT;  // rows of this thread inside the tile
+  const int c0 = (warp >> 1) * (TS / 4) + (lane & 3) * TT;  // cols
+  constexpr int kLoads = TS * kGramBK / kGramThreads;
+  constexpr int kRowBits = TS == 64 ? 6 : 5;
 
   for (int item = blockIdx.x; item < tab.total; item += gridDim.x) {
     int lo = 0, hi = tab.n_tasks;
@@ -45,7 +60,7 @@ __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task
       if (tab.start[mid] <= item) lo = mid; else hi = mid;
     }
     const tta_gram_task tk = tasks[lo];
-    const int T = (tk.k + kGramT - 1) / kGramT;
+    const int T = (tk.k + TS - 1) / TS;
     const int npairs = T * (T + 1) / 2;
     const int local = item - tab.start[lo];
     const int split = local / npairs;
@@ -53,7 +68,7 @@ __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task
     int ti = 0;
     while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;  // ti >= tj, pair index = ti(ti+1)/2 + tj
     const int tj = pr - ti * (ti + 1) / 2;
-    const int i0 = ti * kGramT, j0 = tj * kGramT;
+    const int i0 = ti * TS, j0 = tj * TS;
     const bool diag = (ti == tj);
 
     const int64_t R = (int64_t)tk.nb * tk.nc;
@@ -62,18 +77,18 @@ __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task
     const int64_t rend = (rbeg + per) < R ? (rbeg + per) : R;
     const bool rowfast = (tk.si == 1);
 
-    double acc[4][4];
+    double acc[TT][TT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TT; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      for (int j = 0; j < TT; ++j) acc[i][j] = 0.0;
 
     for (int64_t rr = rbeg; rr < rend; rr += kGramBK) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kLoads; ++q) {
         const int e = q * kGramThreads + tid;
         int row, kk;
-        if (rowfast) { kk = e >> 6; row = e & 63; } else { row = e >> 4; kk = e & 15; }
+        if (rowfast) { kk = e >> kRowBits; row = e & (TS - 1); } else { row = e >> 4; kk = e & 15; }
         const int64_t rho = rr + kk;
         const bool rok = rho < rend;
         const int64_t off = rok ? gram_off(tk, rho) : 0;
@@ -86,31 +101,153 @@ __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task
         }
       }
       __syncthreads();
-      const double(*Bp)[kGramT + 2] = diag ? As : Bs;
+      const double(*Bp)[TS + 2] = diag ? As : Bs;
 #pragma unroll
       for (int kk = 0; kk < kGramBK; ++kk) {
-        const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][r0]);
-        const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][r0 + 2]);
-        const double2 b01 = *reinterpret_cast<const double2*>(&Bp[kk][c0]);
-        const double2 b23 = *reinterpret_cast<const double2*>(&Bp[kk][c0 + 2]);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+        double a[TT], b[TT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int h = 0; h < TT / 2; ++h) {
+          const double2 av = *reinterpret_cast<const double2*>(&As[kk][r0 + 2 * h]);
+          const double2 bv = *reinterpret_cast<const double2*>(&Bp[kk][c0 + 2 * h]);
+          a[2 * h] = av.x; a[2 * h + 1] = av.y;
+          b[2 * h] = bv.x; b[2 * h + 1] = bv.y;
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int i = 0; i < TT; ++i)
+#pragma unroll
+          for (int j = 0; j < TT; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
       }
       __syncthreads();
     }
 
     double* P = tk.part + (int64_t)split * tk.k * tk.k;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TT; ++i) {
       const int gi = i0 + r0 + i;
       if (gi >= tk.k) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < TT; ++j) {
         const int gj = j0 + c0 + j;
+        if (gj < tk.k) P[(int64_t)gi * tk.k + gj] = acc[i][j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k > 64: 128 x 128 lower-triangular tiles, 8 x 8 DFMA register tiles, double-buffered operands.
+// Per reduction index a thread reads 8 + 8 doubles from shared memory for 64 DFMAs (the 4 x 4 tiling
+// of the small-k kernel reads 4 + 4 for 16 and is shared-memory bound); the global loads of chunk
+// c+1 are in flight while chunk c is being multiplied.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGramT2 = 128;
+constexpr int kGramBK2 = 16;
+constexpr int kGramLd2 = kGramT2 + 2;
+constexpr size_t kGram2Smem = (size_t)2 * 2 * kGramBK2 * kGramLd2 * sizeof(double);
+
+__global__ void __launch_bounds__(kGramThreads, 1) gram_partial_big(const tta_gram_task* __restrict__ tasks,
+                                                                   const __grid_constant__ GramTable tab) {
+  extern __shared__ __align__(16) double gsm[];
+  // [buffer][operand][kk][row]
+  auto tile = [&](int buf, int op) { return gsm + ((size_t)(buf * 2 + op) * kGramBK2) * kGramLd2; };
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;      // 16 x 16 threads, 8 x 8 outputs each (rows ty*8.., cols tx*8..)
+
+  for (int item = blockIdx.x; item < tab.total; item += gridDim.x) {
+    int lo = 0, hi = tab.n_tasks;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (tab.start[mid] <= item) lo = mid; else hi = mid;
+    }
+    const tta_gram_task tk = tasks[lo];
+    const int T = (tk.k + kGramT2 - 1) / kGramT2;
+    const int npairs = T * (T + 1) / 2;
+    const int local = item - tab.start[lo];
+    const int split = local / npairs;
+    int pr = local - split * npairs;
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
+    const int tj = pr - ti * (ti + 1) / 2;
+    const int i0 = ti * kGramT2, j0 = tj * kGramT2;
+    const bool diag = (ti == tj);
+
+    const int64_t R = (int64_t)tk.nb * tk.nc;
+    const int64_t per = (R + tk.nsplit - 1) / tk.nsplit;
+    const int64_t rbeg = (int64_t)split * per;
+    const int64_t rend = (rbeg + per) < R ? (rbeg + per) : R;
+    const bool rowfast = (tk.si == 1);
+
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+    float ra[8], rb[8];
+    auto fetch = [&](int64_t rr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = q * kGramThreads + tid;     // 0..2047 = 128 rows x 16 reduction indices
+        int row, kk;
+        if (rowfast) { kk = e >> 7; row = e & 127; } else { row = e >> 4; kk = e & 15; }
+        const int64_t rho = rr + kk;
+        const bool rok = rho < rend;
+        const int64_t off = rok ? gram_off(tk, rho) : 0;
+        ra[q] = (rok && (i0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(i0 + row) * tk.si + off) : 0.f;
+        rb[q] = (!diag && rok && (j0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(j0 + row) * tk.si + off) : 0.f;
+      }
+    };
+    auto stash = [&](int buf) {
+      double* As = tile(buf, 0);
+      double* Bs = tile(buf, 1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = q * kGramThreads + tid;
+        int row, kk;
+        if (rowfast) { kk = e >> 7; row = e & 127; } else { row = e >> 4; kk = e & 15; }
+        As[kk * kGramLd2 + row] = (double)ra[q];
+        if (!diag) Bs[kk * kGramLd2 + row] = (double)rb[q];
+      }
+    };
+
+    __syncthreads();          // previous item's readers are done with both buffers
+    fetch(rbeg);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t rr = rbeg; rr < rend; rr += kGramBK2) {
+      const bool more = rr + kGramBK2 < rend;
+      if (more) fetch(rr + kGramBK2);
+      const double* As = tile(buf, 0);
+      const double* Bs = diag ? As : tile(buf, 1);
+#pragma unroll
+      for (int kk = 0; kk < kGramBK2; ++kk) {
+        double a[8], b[8];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const double2 av = *reinterpret_cast<const double2*>(As + kk * kGramLd2 + ty * 8 + 2 * h);
+          const double2 bv = *reinterpret_cast<const double2*>(Bs + kk * kGramLd2 + tx * 8 + 2 * h);
+          a[2 * h] = av.x; a[2 * h + 1] = av.y;
+          b[2 * h] = bv.x; b[2 * h + 1] = bv.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      }
+      if (more) stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+
+    double* P = tk.part + (int64_t)split * tk.k * tk.k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gi = i0 + ty * 8 + i;
+      if (gi >= tk.k) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int gj = j0 + tx * 8 + j;
         if (gj < tk.k) P[(int64_t)gi * tk.k + gj] = acc[i][j];
       }
     }
@@ -129,7 +266,8 @@ __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restri
     float v = 0.f;
     if (row < tk.k && col < tk.k) {
       int i = row, j = col;
-      if ((i / kGramT) < (j / kGramT)) { i = col; j = row; }  // stored tiles have ti >= tj
+      const int tsz = gram_tile(gram_class(tk));
+      if ((i / tsz) < (j / tsz)) { i = col; j = row; }  // stored tiles have ti >= tj
       const double* p = tk.part + (int64_t)i * tk.k + j;
       double s = 0.0;
       for (int sidx = 0; sidx < tk.nsplit; ++sidx) s += p[(int64_t)sidx * kk2];
@@ -150,11 +288,16 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
     return TTA_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(gram_partial_big, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kGram2Smem), "gram smem attribute");
+    if (rc) return rc;
+    attr_set = true;
+  }
   for (int first = 0; first < n_tasks; first += kGramMaxTasks) {
     const int cnt = (n_tasks - first) < kGramMaxTasks ? (n_tasks - first) : kGramMaxTasks;
-    GramTable tab;
-    tab.n_tasks = cnt;
-    int64_t total = 0, max_elems = 0;
+    int64_t max_elems = 0;
     for (int t = 0; t < cnt; ++t) {
       const tta_gram_task& tk = tasks_host[first + t];
       if (tk.k <= 0 || tk.nb <= 0 || tk.nc <= 0 || tk.nsplit <= 0 || tk.ld < tk.k || tk.kpad < tk.k ||
@@ -163,21 +306,42 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
                   tk.nc, tk.nsplit, tk.ld, tk.kpad);
         return TTA_E_INVALID;
       }
-      const int T = (tk.k + kGramT - 1) / kGramT;
-      tab.start[t] = (int)total;
-      total += (int64_t)(T * (T + 1) / 2) * tk.nsplit;
       const int64_t el = (int64_t)tk.ld * tk.kpad;
       max_elems = el > max_elems ? el : max_elems;
-      if (total > 0x7fffffff) {
-        set_error("gram: too many tiles");
-        return TTA_E_INVALID;
-      }
     }
-    tab.start[cnt] = (int)total;
-    tab.total = (int)total;
-    const int grid = total < (int64_t)kNumSMs * 8 ? (int)total : kNumSMs * 8;
-    gram_partial<<<grid, kGramThreads, 0, st>>>(tasks_dev + first, tab);
-    TTA_CHECK_LAUNCH("gram_partial launch");
+    // pass 0: k <= 32 on 32 x 32 tiles; pass 1: k <= 64 on 64 x 64 tiles; pass 2: larger k on 128 x 128
+    // tiles.  A task that does not belong to a pass contributes zero tiles to its table.
+    for (int pass = 0; pass < 3; ++pass) {
+      GramTable tab;
+      tab.n_tasks = cnt;
+      int64_t total = 0;
+      const int tsz = pass == 0 ? 32 : pass == 1 ? kGramT : kGramT2;
+      for (int t = 0; t < cnt; ++t) {
+        const tta_gram_task& tk = tasks_host[first + t];
+        tab.start[t] = (int)total;
+        if (gram_class(tk) != pass) continue;
+        const int T = (tk.k + tsz - 1) / tsz;
+        total += (int64_t)(T * (T + 1) / 2) * tk.nsplit;
+        if (total > 0x7fffffff) {
+          set_error("gram: too many tiles");
+          return TTA_E_INVALID;
+        }
+      }
+      tab.start[cnt] = (int)total;
+      tab.total = (int)total;
+      if (total == 0) continue;
+      if (pass < 2) {
+        const int grid = total < (int64_t)kNumSMs * 8 ? (int)total : kNumSMs * 8;
+        if (pass == 0)
+          gram_partial<32, 2><<<grid, kGramThreads, 0, st>>>(tasks_dev + first, tab);
+        else
+          gram_partial<64, 4><<<grid, kGramThreads, 0, st>>>(tasks_dev + first, tab);
+      } else {
+        const int grid = total < (int64_t)kNumSMs ? (int)total : kNumSMs;
+        gram_partial_big<<<grid, kGramThreads, kGram2Smem, st>>>(tasks_dev + first, tab);
+      }
+      TTA_CHECK_LAUNCH("gram_partial launch");
+    }
     int gx = (int)((max_elems + 255) / 256);
     if (gx > kNumSMs * 4) gx = kNumSMs * 4;
     if (gx < 1) gx = 1;

@@ -20,54 +20,59 @@ constexpr double kRefCutRel = 4e-7;     // eigenvalues below cut_rel * lambda_ma
 constexpr double kRefGapRel = 1e-6;     // |lambda_i - lambda_j| below gap_rel * lambda_max: cluster
 constexpr double kRefMaxCorr = 0.05;    // first-order correction must stay small
 
-// qt row p = the unit vector of the p-th largest column of X; lam0[p] = its norm (0 for null columns)
-__global__ void __launch_bounds__(kRefThreads) refine_prepare_kernel(const tta_refine_task* __restrict__ tasks) {
-  extern __shared__ double s_nrm[];   // k squared norms, then k ints (rank position)
+constexpr int kRefSplit = 8;            // CTAs per problem in the prepare / coeff kernels
+
+// c[0..k) (scratch, overwritten later by refine_coeff) = squared column norms of X
+__global__ void __launch_bounds__(kRefThreads) refine_norms_kernel(const tta_refine_task* __restrict__ tasks) {
   const tta_refine_task tk = tasks[blockIdx.x];
   const int k = tk.k;
-  int* s_pos = reinterpret_cast<int*>(s_nrm + k);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarp = kRefThreads / 32;
-  for (int j = warp; j < k; j += nwarp) {
+  for (int j = blockIdx.y * nwarp + warp; j < k; j += nwarp * kRefSplit) {
     const float* x = tk.x + (int64_t)j * tk.ld;
     double a = 0.0;
     for (int e = lane; e < k; e += 32) a = fma((double)x[e], (double)x[e], a);
     a = warp_sum(a);
-    if (lane == 0) s_nrm[j] = a;
+    if (lane == 0) tk.c[j] = a;
   }
+}
+
+// qt row p = the unit vector of the p-th largest column of X; lam0[p] = its norm (0 for null columns)
+__global__ void __launch_bounds__(kRefThreads) refine_prepare_kernel(const tta_refine_task* __restrict__ tasks) {
+  extern __shared__ double s_nrm[];   // k squared norms
+  const tta_refine_task tk = tasks[blockIdx.x];
+  const int k = tk.k;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarp = kRefThreads / 32;
+  for (int j = tid; j < k; j += kRefThreads) s_nrm[j] = tk.c[j];
   __syncthreads();
   double mx = 0.0;
   for (int j = 0; j < k; ++j) mx = fmax(mx, s_nrm[j]);
   const double cut = mx * (kRefCutRel * kRefCutRel);
-  for (int j = tid; j < k; j += kRefThreads) {
+  for (int j = blockIdx.y * nwarp + warp; j < k; j += nwarp * kRefSplit) {
     const double aj = s_nrm[j];
     int pos = 0;
-    for (int i = 0; i < k; ++i) {
+    for (int i = lane; i < k; i += 32) {
       const double ai = s_nrm[i];
       pos += (ai > aj) || (ai == aj && i < j);
     }
-    s_pos[j] = pos;
-  }
-  __syncthreads();
-  for (int j = warp; j < k; j += nwarp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, o);
     const float* x = tk.x + (int64_t)j * tk.ld;
-    const double a = s_nrm[j];
-    const bool live = a > cut && a > 0.0;
-    const double inv = live ? 1.0 / sqrt(a) : 0.0;
-    const int p = s_pos[j];
-    double* q = tk.qt + (int64_t)p * k;
+    const bool live = aj > cut && aj > 0.0;
+    const double inv = live ? 1.0 / sqrt(aj) : 0.0;
+    double* q = tk.qt + (int64_t)pos * k;
     for (int e = lane; e < k; e += 32) q[e] = (double)x[e] * inv;
-    if (lane == 0) tk.lam0[p] = live ? sqrt(a) : 0.0;
+    if (lane == 0) tk.lam0[pos] = live ? sqrt(aj) : 0.0;
   }
 }
 
 // s, t: the first wnd rows of S = Qt G Qt^T and T = Qt Qt^T (wnd x k, row-major)
 __global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_refine_task* __restrict__ tasks) {
-  extern __shared__ double s_lam[];  // k eigenvalues, then k ints (rank inside the window), r ints (selection)
+  extern __shared__ double s_lam[];  // k eigenvalues, then r ints (selection)
   const tta_refine_task tk = tasks[blockIdx.x];
   const int k = tk.k, wnd = tk.wnd;
-  int* s_pos = reinterpret_cast<int*>(s_lam + k);
-  int* s_sel = s_pos + k;            // s_sel[p] = row holding rank p
+  int* s_sel = reinterpret_cast<int*>(s_lam + k);   // s_sel[p] = row holding rank p
   const int tid = threadIdx.x;
   for (int j = tid; j < k; j += kRefThreads) {
     if (j < wnd) {
@@ -88,12 +93,12 @@ __global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_ref
       const double li = s_lam[i];
       pos += (li > lj) || (li == lj && i < j);
     }
-    s_pos[j] = pos;
     if (pos < tk.r) s_sel[pos] = j;
   }
   __syncthreads();
   const double gap_min = kRefGapRel * lmax;
-  for (int idx = tid; idx < tk.r * k; idx += kRefThreads) {
+  const int total = tk.r * k;
+  for (int idx = blockIdx.y * kRefThreads + tid; idx < total; idx += kRefThreads * kRefSplit) {
     const int p = idx / k, i = idx - p * k;
     const int j = s_sel[p];
     const double lj = s_lam[j], li = s_lam[i];
@@ -115,7 +120,8 @@ __global__ void __launch_bounds__(kRefThreads) refine_coeff_kernel(const tta_ref
     }
     tk.c[idx] = c;
   }
-  for (int p = tid; p < tk.r; p += kRefThreads) tk.lam[p] = s_lam[s_sel[p]];
+  if (blockIdx.y == 0)
+    for (int p = tid; p < tk.r; p += kRefThreads) tk.lam[p] = s_lam[s_sel[p]];
 }
 
 // One warp per selected row: renormalise the corrected vector in fp64 (the first-order update leaves
@@ -174,7 +180,7 @@ int tta_refine_prepare_batched(const tta_refine_task* tasks_dev, const tta_refin
   if (rc || n_tasks == 0) return rc;
   size_t smem = 0;
   for (int t = 0; t < n_tasks; ++t) {
-    const size_t need = (size_t)tasks_host[t].k * 12;
+    const size_t need = (size_t)tasks_host[t].k * 8;
     smem = need > smem ? need : smem;
   }
   if (smem > 48 * 1024) {
@@ -182,7 +188,9 @@ int tta_refine_prepare_batched(const tta_refine_task* tasks_dev, const tta_refin
                     "refine_prepare smem attribute");
     if (rc) return rc;
   }
-  refine_prepare_kernel<<<n_tasks, kRefThreads, smem, (cudaStream_t)stream>>>(tasks_dev);
+  refine_norms_kernel<<<dim3(n_tasks, kRefSplit), kRefThreads, 0, (cudaStream_t)stream>>>(tasks_dev);
+  TTA_CHECK_LAUNCH("refine_norms launch");
+  refine_prepare_kernel<<<dim3(n_tasks, kRefSplit), kRefThreads, smem, (cudaStream_t)stream>>>(tasks_dev);
   TTA_CHECK_LAUNCH("refine_prepare launch");
   return TTA_OK;
 }
@@ -194,7 +202,7 @@ int tta_refine_coeff_batched(const tta_refine_task* tasks_dev, const tta_refine_
   if (rc || n_tasks == 0) return rc;
   size_t smem = 0;
   for (int t = 0; t < n_tasks; ++t) {
-    const size_t need = (size_t)tasks_host[t].k * 16;
+    const size_t need = (size_t)tasks_host[t].k * 8 + (size_t)tasks_host[t].r * 4;
     smem = need > smem ? need : smem;
   }
   if (smem > 48 * 1024) {
@@ -202,7 +210,7 @@ int tta_refine_coeff_batched(const tta_refine_task* tasks_dev, const tta_refine_
                     "refine_coeff smem attribute");
     if (rc) return rc;
   }
-  refine_coeff_kernel<<<n_tasks, kRefThreads, smem, (cudaStream_t)stream>>>(tasks_dev);
+  refine_coeff_kernel<<<dim3(n_tasks, kRefSplit), kRefThreads, smem, (cudaStream_t)stream>>>(tasks_dev);
   TTA_CHECK_LAUNCH("refine_coeff launch");
   return TTA_OK;
 }

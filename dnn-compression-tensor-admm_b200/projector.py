@@ -98,9 +98,12 @@ def refine_window(k, r):
 
 
 def gram_splits(k, red_len):
-    tiles = (k + 63) // 64
+    """Slices of the reduction range per Gram problem: enough tiles x slices to fill the SMs twice,
+    at least 512 reduction indices per slice, at most 48 slices (the finish kernel sums them)."""
+    ts = 32 if k <= 32 else 64 if (k <= 64 or red_len < 1536) else 128   # csrc/gram.cu: gram_class
+    tiles = (k + ts - 1) // ts
     pairs = tiles * (tiles + 1) // 2
-    return max(1, min((red_len + 511) // 512, (296 + pairs - 1) // pairs))
+    return max(1, min((red_len + 511) // 512, (296 + pairs - 1) // pairs, 48))
 
 
 def tt_step_flops(shapes, ranks):
