@@ -443,13 +443,22 @@ def forward_bench(dev, peaks):
 
     ms_f, ms_c = _time_cuda(lin_fused, iters=3, warm=1), _time_cuda(lin_chain, iters=3, warm=1)
     macs = 0
+    macs_exec = 0
+    n_dense = 0
     for layer, _ in lin:
         r, sh, o = layer.tt_ranks, layer.tt_shapes, layer.out_tt_order
         # per-token MACs of the 4-step chain (SURVEY 8(d) TTLinearM accounting)
-        macs += sh[2] * sh[3] * r[3] + sh[2] * r[3] * r[2] + r[2] * sh[1] * r[1] + sh[1] * r[1] * sh[0]
+        chain = sh[2] * sh[3] * r[3] + sh[2] * r[3] * r[2] + r[2] * sh[1] * r[1] + sh[1] * r[1] * sh[0]
+        macs += chain
+        dense = bool(getattr(layer, '_dense_first', False))
+        n_dense += dense
+        macs_exec += layer.in_features * layer.out_features if dense else chain
     out['deit_small_ttlinear_layers'] = {'batch': 256, 'tokens': tokens, 'fused_img_s': 256 / (ms_f / 1e3), 'fused_ms': ms_f,
                                          'torch_op_chain_img_s': 256 / (ms_c / 1e3), 'torch_op_chain_ms': ms_c,
-                                         'fused_tflops': 2.0 * macs * tokens / (ms_f / 1e3) / 1e12}
+                                         'contraction_order': '{} of {} layers fold the cores into the dense weight first '
+                                                              '(fewer or comparable MACs than the chain)'.format(n_dense, len(lin)),
+                                         'chain_tflops_equiv': 2.0 * macs * tokens / (ms_f / 1e3) / 1e12,
+                                         'executed_tflops': 2.0 * macs_exec * tokens / (ms_f / 1e3) / 1e12}
     # ---- the tcgen05 GEMM alone: the two big contractions of the block-0 qkv chain ----
     tc = {}
     for (M, N, K) in ((tokens, 1120, 320), (tokens, 320, 368)):

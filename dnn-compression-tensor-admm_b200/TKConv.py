@@ -51,7 +51,12 @@ class _TKConvBase(Module):
         return core.cpu(), last.cpu(), first.t().contiguous().cpu()
 
     def _fused(self, x, first2d, core4d, last2d, bias, params):
-        """1x1 (I -> r_in), k x k (r_in -> r_out), 1x1 (r_out -> O) on pixel-major bf16 rows."""
+        """1x1 (I -> r_in), k x k (r_in -> r_out), 1x1 (r_out -> O): one fused fp32 kernel when the geometry is
+        supported (k in {1, 3}, stride <= 2), else pixel-major bf16 rows through the GEMM kernels."""
+        if fc.fused_conv_supported(self.kernel_size, self.stride, self.padding, self.dilation):
+            if getattr(self, '_folded', None) is None:
+                self._folded = fc.FoldedConv(lambda: (first2d(), core4d(), last2d()), params[:3])
+            return fc.fused_conv(x, self._folded, bias, self.kernel_size, self.stride, self.padding)
         if self._engine is None:
             self._engine = (fc.Workspace(), fc.PackedWeight(first2d, [params[0]]),
                             fc.PackedWeight(lambda: fc.conv_weight_matrix(core4d()), [params[1]]),
@@ -108,7 +113,7 @@ class TKConv2dC(_TKConvBase):
         return [self.first_kernel, self.core_kernel, self.last_kernel, self.bias]
 
     def forward(self, x):
-        if fc.needs_autograd(x, self._params()):
+        if torch.is_grad_enabled() and fc.needs_autograd(x, self._params()):
             return self.forward_features(x)[0]
         rt.require_device(x)
         return self._fused(x, lambda: self.first_kernel.reshape(self.in_rank, -1), lambda: self.core_kernel,
@@ -167,7 +172,7 @@ class TKConv2dM(_TKConvBase):
         return [self.first_factor, self.core_kernel, self.last_factor, self.bias]
 
     def forward(self, x):
-        if fc.needs_autograd(x, self._params()):
+        if torch.is_grad_enabled() and fc.needs_autograd(x, self._params()):
             out = F.linear(x.permute(0, 2, 3, 1), self.first_factor).permute(0, 3, 1, 2)
             out = F.conv2d(out, self.core_kernel, None, self.stride, self.padding, self.dilation, self.groups)
             return F.linear(out.permute(0, 2, 3, 1), self.last_factor, self.bias).permute(0, 3, 1, 2)
@@ -217,7 +222,7 @@ class TKConv2dR(_TKConvBase):
         return [self.first_factor, self.core_tensor, self.last_factor, self.bias]
 
     def forward(self, x):
-        if fc.needs_autograd(x, self._params()):
+        if torch.is_grad_enabled() and fc.needs_autograd(x, self._params()):
             return F.conv2d(x, self._recover_weight(), self.bias, self.stride, self.padding, self.dilation, self.groups)
         rt.require_device(x)
         if self._engine is None:

@@ -55,6 +55,8 @@ class _TTConvBase(Module):
         self.in_tt_ranks = self.tt_ranks[self.out_tt_order + 1:]
         self.filter_dim = self.kernel_size[0] * self.kernel_size[1]
         self._engine = None
+        self._folded = None
+        self._fusable = fc.fused_conv_supported(self.kernel_size, self.stride, self.padding, self.dilation)
 
     def get_ranks(self):
         return ', '.join(str(r) for r in self.tt_ranks)
@@ -124,9 +126,19 @@ class TTConv2dM(_TTConvBase):
         return y
 
     def forward(self, x):
-        if fc.needs_autograd(x, self._params()):
+        if torch.is_grad_enabled() and fc.needs_autograd(x, self._params()):
             return self._forward_torch(x)
         rt.require_device(x)
+        if self._fusable:
+            if self._folded is None:
+                def build():
+                    eye_in = torch.eye(self.in_channels, dtype=torch.float32, device=self.core_kernel.device)
+                    eye_out = torch.eye(self.out_tt_ranks[-1], dtype=torch.float32, device=self.core_kernel.device)
+                    a_in = fc.tt_apply_torch(eye_in, list(self.in_tt_cores), []).t()       # (r_a x C_in)
+                    a_out = fc.tt_apply_torch(eye_out, [], list(self.out_tt_cores)).t()    # (C_out x r_b)
+                    return a_in, self.core_kernel, a_out
+                self._folded = fc.FoldedConv(build, [p for p in self._params() if p is not self.bias])
+            return fc.fused_conv(x, self._folded, self.bias, self.kernel_size, self.stride, self.padding)
         if self._engine is None:
             eng = fc.TTRowsEngine(list(self.in_tt_cores), list(self.out_tt_cores))
             wk = fc.PackedWeight(lambda: fc.conv_weight_matrix(self.core_kernel), [self.core_kernel])
@@ -229,7 +241,7 @@ class TTConv2dR(_TTConvBase):
         return list(self.out_tt_cores) + [self.conv_core] + list(self.in_tt_cores) + [self.bias]
 
     def forward(self, x):
-        if fc.needs_autograd(x, self._params()):
+        if torch.is_grad_enabled() and fc.needs_autograd(x, self._params()):
             return F.conv2d(x, self._recover_weight(), self.bias, self.stride, self.padding, self.dilation, self.groups)
         rt.require_device(x)
         if self._engine is None:

@@ -73,6 +73,49 @@ class PackedWeight:
         return self
 
 
+class FoldedConv:
+    """Cached fp32 operands of the fused factorised-convolution kernel (`tta_ttconv_fused_fwd`):
+    a_in (r_a x C_in), kern (r_b, r_a, k, k), a_out (C_out x r_b); rebuilt when a parameter changes."""
+
+    def __init__(self, builder, params):
+        self.builder = builder
+        self.params = [p for p in params if p is not None]
+        self.key = None
+        self.ops = None
+
+    def get(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.params)
+        if key != self.key:
+            with torch.no_grad():
+                self.ops = tuple(t.detach().to(torch.float32).contiguous() for t in self.builder())
+            self.key = key
+        return self.ops
+
+
+def fused_conv_supported(kernel_size, stride, padding, dilation):
+    return (kernel_size[0] == kernel_size[1] and kernel_size[0] in (1, 3) and stride[0] == stride[1] and
+            stride[0] in (1, 2) and padding[0] == padding[1] and padding[0] <= kernel_size[0] and
+            tuple(dilation) == (1, 1))
+
+
+def fused_conv(x, folded, bias, kernel_size, stride, padding):
+    """y = last(1x1) . core(k x k) . first(1x1) (x) + bias in one kernel; x NCHW (any float dtype) -> NCHW fp32.
+    (Kept lean: at ~10 us of GPU time per layer the Python side of the call is what bounds a network.)"""
+    a_in, kern, a_out = folded.get()
+    B, C, H, W = x.shape
+    if x.dtype is not torch.float32 or not x.is_contiguous() or x.requires_grad:
+        x = x.detach().to(torch.float32).contiguous()
+    ks, s, p = kernel_size[0], stride[0], padding[0]
+    cout = a_out.shape[0]
+    y = torch.empty((B, cout, (H + 2 * p - ks) // s + 1, (W + 2 * p - ks) // s + 1), dtype=torch.float32, device=x.device)
+    if bias is not None and (bias.dtype is not torch.float32 or not bias.is_contiguous()):
+        bias = bias.detach().to(torch.float32).contiguous()
+    rt.ttconv_fused_fwd_raw(x.data_ptr(), a_in.data_ptr(), kern.data_ptr(), a_out.data_ptr(),
+                            bias.data_ptr() if bias is not None else None, y.data_ptr(), B, C, H, W, a_in.shape[0],
+                            kern.shape[0], cout, ks, s, p)
+    return y
+
+
 def contract(a, M, K, w, out, *, a_inner=1, a_outer=None, lda=None, m_inner=1, s_outer=None, s_inner=0, s_col=1,
              bias=None, bias_inner=0, bias_col=1):
     """out = a (M rows of K) . w^T with the skinny or the tensor-core kernel.
@@ -209,6 +252,23 @@ def tt_apply_torch(x2d, in_cores, out_cores):
     for g in reversed(list(out_cores)):
         acc = torch.einsum('tpb,aob->topa', acc, g).reshape(R, -1, g.shape[0])
     return acc.reshape(R, -1)
+
+
+def tt_chain_macs(in_cores, out_cores):
+    """Multiply-accumulates per row of the factorised chain (TTLinear.py:79-88 order)."""
+    macs = 0
+    shapes = [int(c.shape[1]) for c in in_cores]
+    for i in range(len(in_cores) - 1, -1, -1):
+        c = in_cores[i]
+        lead = 1
+        for j in range(i):
+            lead *= shapes[j]
+        macs += lead * int(c.shape[1]) * int(c.shape[2]) * int(c.shape[0])
+    p = 1
+    for g in reversed(list(out_cores)):
+        macs += p * int(g.shape[0]) * int(g.shape[1]) * int(g.shape[2])
+        p *= int(g.shape[1])
+    return macs
 
 
 def split_tt(tt_shapes, out_channels, conv):

@@ -50,7 +50,7 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
-           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16']
+           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd']
 
 
 class TtaError(RuntimeError):
@@ -120,6 +120,7 @@ def _load():
     lib.tta_nchw_to_nhwc_bf16.argtypes = [vp, vp, ci, ci, ci, ci, vp]
     lib.tta_nhwc_to_nchw_f32.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp]
     lib.tta_im2col_bf16.argtypes = [vp, vp] + [ci] * 16 + [vp]
+    lib.tta_ttconv_fused_fwd.argtypes = [vp] * 6 + [ci] * 10 + [vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
@@ -317,6 +318,20 @@ def nhwc_to_nchw_f32(x, y, bias, B, C, HW, ldc):
 def im2col_bf16(x, out, B, H, W, C, ldx, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo, ldo):
     _check(lib().tta_im2col_bf16(_p(x), _p(out), B, H, W, C, ldx, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo, ldo,
                                  stream_handle()), 'tta_im2col_bf16')
+
+
+def ttconv_fused_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
+    _check(lib().tta_ttconv_fused_fwd(_p(x), _p(a_in), _p(kern), _p(a_out), _p(bias), _p(y), int(B), int(Cin), int(H),
+                                      int(W), int(Ra), int(Rb), int(Cout), int(KS), int(stride), int(pad),
+                                      stream_handle()), 'tta_ttconv_fused_fwd')
+
+
+def ttconv_fused_fwd_raw(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
+    """Same call with raw device addresses (ints) -- the per-layer hot path of a network forward."""
+    rc = lib().tta_ttconv_fused_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad,
+                                    torch.cuda.current_stream().cuda_stream if _FAKE is None else None)
+    if rc:
+        _check(rc, 'tta_ttconv_fused_fwd')
 
 
 def launch_count():

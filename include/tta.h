@@ -269,6 +269,19 @@ int tta_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* y, const float* bia
 int tta_im2col_bf16(const void* x, void* out, int B, int H, int W, int C, int ldx, int KH, int KW, int sh, int sw,
                     int ph, int pw, int dh, int dw, int Ho, int Wo, int ldo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused forward of a factorised convolution:  1x1 (C_in -> r_a)  ->  k x k (r_a -> r_b, stride, zero
+ * padding)  ->  1x1 (r_b -> C_out) + bias in ONE kernel, intermediates in shared memory, fp32.
+ * Replaces the op chains of TTConv2dM.forward (TTConv.py:130-153; the host folds the in-core chain into
+ * a_in and the out-core chain into a_out) and TKConv2dC/M.forward (TKConv.py:93-98, 205-222: first
+ * factor, core, last factor).
+ *   x (B, C_in, H, W) NCHW fp32;  a_in (r_a x C_in);  kern (r_b, r_a, k, k);  a_out (C_out x r_b);
+ *   bias (C_out) nullable;  y (B, C_out, Ho, Wo) NCHW fp32.   k in {1, 3}, stride in {1, 2}, dilation 1.
+ * ------------------------------------------------------------------------------------------- */
+int tta_ttconv_fused_fwd(const float* x, const float* a_in, const float* kern, const float* a_out,
+                         const float* bias, float* y, int B, int Cin, int H, int W, int Ra, int Rb,
+                         int Cout, int KS, int stride, int pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,3 +198,33 @@ def test_tklinear_forward_matches_dense(variant):
     ref = torch.nn.functional.linear(x, z, b.to(DEV))
     assert _rel(y, ref) <= FWD_TOL, _rel(y, ref)
     assert tuple(layer.first_factor.shape) == (72, 384) and tuple(layer.last_factor.shape) == (192, 40)
+
+
+@pytest.mark.parametrize('B,Cin,H,W,Ra,Rb,Cout,KS,stride,pad', [
+    (3, 16, 32, 32, 16, 16, 16, 3, 1, 1),      # ttm_resnet32 layer1
+    (2, 16, 32, 32, 16, 32, 32, 3, 2, 1),      # stride-2 transition
+    (4, 64, 8, 8, 27, 29, 64, 3, 1, 1),        # layer3 ranks, ranks not multiples of 4
+    (2, 7, 13, 9, 5, 6, 11, 3, 1, 1),          # ragged everything
+    (2, 12, 10, 10, 8, 8, 20, 1, 1, 0),        # 1x1 core
+    (1, 32, 19, 17, 10, 12, 24, 3, 2, 0),      # stride 2, no padding
+    (1, 64, 56, 56, 40, 40, 64, 3, 1, 1),      # bigger image: several tiles per image, tile shrink
+])
+def test_ttconv_fused_kernel_matches_conv_chain(B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
+    """tta_ttconv_fused_fwd == conv1x1 -> conv kxk -> conv1x1 (+bias) of torch in fp32 (tolerance: fp32 rounding)."""
+    import torch.nn.functional as F
+    g = torch.Generator(device='cpu').manual_seed(B * 131 + Cin * 17 + H)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+    a_in = (torch.randn(Ra, Cin, generator=g) / Cin ** 0.5).to(DEV)
+    kern = (torch.randn(Rb, Ra, KS, KS, generator=g) / (Ra * KS * KS) ** 0.5).to(DEV)
+    a_out = (torch.randn(Cout, Rb, generator=g) / Rb ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    Ho, Wo = (H + 2 * pad - KS) // stride + 1, (W + 2 * pad - KS) // stride + 1
+    for b in (bias, None):
+        y = torch.full((B, Cout, Ho, Wo), float('nan'), device=DEV)
+        rt.ttconv_fused_fwd(x, a_in, kern, a_out, b, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad)
+        torch.cuda.synchronize()
+        with torch.backends.cudnn.flags(allow_tf32=False):
+            ref = F.conv2d(F.conv2d(F.conv2d(x.double(), a_in.double()[:, :, None, None]), kern.double(), None, stride, pad),
+                           a_out.double()[:, :, None, None], b.double() if b is not None else None)
+        assert torch.isfinite(y).all()
+        assert _rel(y, ref) <= 2e-6, _rel(y, ref)
