@@ -133,6 +133,11 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const tta_sqnorm_task* __re
 }  // namespace tta
 
 namespace tta {
+// tensor-core path for fp32 tasks (gemm_tf32.cu)
+bool gemm_tf32x3_eligible(const tta_gemm_task& tk);
+int gemm_tf32x3_run(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int cnt, cudaStream_t st);
+static bool g_gemm_tc = false;   // see DESIGN.md: 3xTF32 accumulation error is amplified by the small-gap projections
+
 template <typename T>
 static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks, void* stream) {
   if (n_tasks < 0 || (n_tasks > 0 && (!tasks_dev || !tasks_host))) {
@@ -152,6 +157,7 @@ static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* task
         return TTA_E_INVALID;
       }
       tab.start[t] = (int)total;
+      if (sizeof(T) == 4 && g_gemm_tc && gemm_tf32x3_eligible(tk)) continue;   // served by the tcgen05 kernel below
       total += (int64_t)((tk.M + kGemmBM - 1) / kGemmBM) * ((tk.N + kGemmBN - 1) / kGemmBN);
       if (total > 0x7fffffff) {
         set_error("gemm: too many tiles");
@@ -160,6 +166,10 @@ static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* task
     }
     tab.start[cnt] = (int)total;
     tab.total = (int)total;
+    if (sizeof(T) == 4 && g_gemm_tc) {
+      const int rc = gemm_tf32x3_run(tasks_dev + first, tasks_host + first, cnt, st);
+      if (rc) return rc;
+    }
     if (total == 0) continue;
     const int grid = total < (int64_t)kNumSMs * 16 ? (int)total : kNumSMs * 16;
     gemm_kernel<T><<<grid, kGemmThreads, 0, st>>>(tasks_dev + first, tab);
@@ -170,6 +180,8 @@ static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* task
 }  // namespace tta
 
 extern "C" {
+
+void tta_gemm_enable_tc(int on) { tta::g_gemm_tc = on != 0; }
 
 int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
                      void* stream) {

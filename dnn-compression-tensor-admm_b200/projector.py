@@ -91,6 +91,39 @@ def eig_ctas(k):
     return 1 if k <= 32 else min((k + 31) // 32, 16) if k <= 512 else 148
 
 
+_GPC_SMS = (18, 18, 18, 18, 18, 18, 20, 20)      # B200: 148 SMs in 8 GPCs (a cluster lives inside one GPC)
+
+
+def wave_makespan_ms(ks):
+    """Simulated duration of one eigensolver wave: problems are started largest cluster first (the internal
+    streams carry descending priorities) on the first GPC with enough free SMs; one CTA per SM."""
+    if not ks:
+        return 0.0
+    pending = sorted(ks, reverse=True)
+    free = list(_GPC_SMS)
+    running = []                 # (end time, gpc, ctas)
+    now, end = 0.0, 0.0
+    while pending:
+        placed = False
+        for idx, k in enumerate(pending):
+            need = eig_ctas(k)
+            g = next((g for g in range(len(free)) if free[g] >= need), None)
+            if g is not None:
+                free[g] -= need
+                t_end = now + eig_time_ms(k)
+                running.append((t_end, g, need))
+                end = max(end, t_end)
+                pending.pop(idx)
+                placed = True
+                break
+        if not placed:
+            running.sort()
+            t_end, g, need = running.pop(0)
+            now = t_end
+            free[g] += need
+    return end
+
+
 def refine_window(k, r):
     """Rows of S / T the refinement forms: the r selectable vectors plus a margin that is far wider
     than the ordering error of the fp32 eigenvalue estimates (include/tta.h, tta_refine_task)."""
@@ -264,28 +297,19 @@ class TTProjectionPlan:
 
     def _schedule(self):
         """Wave index of every real (non-identity) step.  Steps of one layer keep their order; a layer
-        with fewer real steps than the longest one may start at any offset.  A wave lasts as long as
-        its slowest eigenproblem, or as long as its total eigensolver work keeps the SMs busy, whichever
-        is longer (`eig_time_ms`, `eig_ctas`: measured on B200); flexible layers are placed, costliest
-        first, where they lengthen the sum of the wave durations least -- e.g. the k = 512 problems of
-        the 1x1 convolutions are split between the two waves that hold the big middle steps of the
-        k x k convolutions instead of adding a wave-long critical path of their own."""
+        with fewer real steps than the longest one may start at any offset.  Flexible layers are placed,
+        costliest first, at the offset that minimises the sum of the simulated wave durations
+        (`wave_makespan_ms`: one cluster of P CTAs per eigenproblem, a cluster lives inside one GPC) --
+        e.g. the k = 512 problems of the 1x1 convolutions are split between the two waves that hold the big
+        middle steps of the k x k convolutions instead of adding a wave-long critical path of their own."""
         real = [[i for i, st in enumerate(w['steps']) if not st['identity']] for w in self.ws]
         nwaves = max((len(r) for r in real), default=0)
-        tmax = [0.0] * max(nwaves, 1)
-        work = [0.0] * max(nwaves, 1)
-        cap = 148 * 0.7      # SMs, derated for cluster packing
-
-        def dur(t, w):
-            return max(t, w / cap)
-
-        def cost(li, i):
-            k = self.ws[li]['steps'][i]['k']
-            return eig_time_ms(k), eig_time_ms(k) * eig_ctas(k)
-
+        jobs = [[] for _ in range(max(nwaves, 1))]          # k of every eigenproblem of a wave
+        ks = lambda li: [self.ws[li]['steps'][i]['k'] for i in real[li]]
         sched = [None] * len(self.ws)
         order = sorted(range(len(self.ws)),
-                       key=lambda li: (-len(real[li]), -sum(cost(li, i)[1] for i in real[li]), li))
+                       key=lambda li: (-len(real[li]), -sum(eig_time_ms(k) * eig_ctas(k) for k in ks(li)), li))
+        base = [0.0] * max(nwaves, 1)
         for li in order:
             n = len(real[li])
             if n == 0:
@@ -295,20 +319,18 @@ class TTProjectionPlan:
             for off in range(nwaves - n + 1):
                 total = 0.0
                 for wv in range(nwaves):
-                    t, w = tmax[wv], work[wv]
                     if off <= wv < off + n:
-                        ct, cw = cost(li, real[li][wv - off])
-                        t, w = max(t, ct), w + cw
-                    total += dur(t, w)
+                        total += wave_makespan_ms(jobs[wv] + [ks(li)[wv - off]])
+                    else:
+                        total += base[wv]
                 # ties: prefer the centre of the sequence (the long middle waves)
-                key = (round(total, 6), abs(2 * off + n - nwaves))
+                key = (round(total, 4), abs(2 * off + n - nwaves))
                 if best_key is None or key < best_key:
                     best, best_key = off, key
             sched[li] = {i: best + q for q, i in enumerate(real[li])}
-            for q, i in enumerate(real[li]):
-                ct, cw = cost(li, i)
-                tmax[best + q] = max(tmax[best + q], ct)
-                work[best + q] += cw
+            for q, k in enumerate(ks(li)):
+                jobs[best + q].append(k)
+                base[best + q] = wave_makespan_ms(jobs[best + q])
         return nwaves, sched
 
     def max_order(self):

@@ -44,7 +44,7 @@ STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.item
 
 EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_device', 'tta_jacobi_profile_enable',
            'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch', 'tta_jacobi_enable_gra',
-           'tta_jacobi_set_stop_rel', 'tta_dual_update_multi',
+           'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_dual_update_multi',
            'tta_penalty_fwd_multi', 'tta_penalty_bwd_multi', 'tta_unfold_add_batched',
            'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
            'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
@@ -94,6 +94,8 @@ def _load():
     lib.tta_jacobi_enable_gra.restype = None
     lib.tta_jacobi_set_stop_rel.argtypes = [cf]
     lib.tta_jacobi_set_stop_rel.restype = None
+    lib.tta_gemm_enable_tc.argtypes = [ci]
+    lib.tta_gemm_enable_tc.restype = None
     lib.tta_jacobi_profile_read.argtypes = [vp, vp]
     lib.tta_jacobi_profile_read.restype = None
     lib.tta_check_device.argtypes = [ci]
@@ -124,7 +126,7 @@ def _load():
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
-                        'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel'):
+                        'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc'):
             getattr(lib, name).restype = ci
     _LIB = lib
     return lib
@@ -341,6 +343,14 @@ def launch_count():
 def jacobi_force_multilaunch(on):
     if _FAKE is None:
         lib().tta_jacobi_force_multilaunch(int(bool(on)))
+
+
+def gemm_enable_tc(on):
+    """True routes fp32 GEMM tasks with M >= 48, N >= 24 to the tcgen05 3xTF32 kernel; the library default is
+    the CUDA-core kernel (the tensor core's truncating fp32 accumulation costs ~3e-6 relative error at
+    K = 480, which the small-gap TT projections amplify past the 1e-4 parity bar on DeiT-small)."""
+    if _FAKE is None:
+        lib().tta_gemm_enable_tc(int(bool(on)))
 
 
 def jacobi_enable_gra(on):

@@ -188,6 +188,12 @@ typedef struct {
 
 int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
                      void* stream);
+/* on != 0: tasks with M >= 48, N >= 24, K >= 8 run on the tensor cores (tcgen05, 3xTF32 split: A_hi B_hi +
+ * A_lo B_hi + A_hi B_lo, fp32 TMEM accumulation); the rest, and by default all tasks, on CUDA cores.  Measured
+ * on B200: the tensor core's truncating accumulation gives 3.3e-6 relative error at K = 480 (CUDA cores:
+ * 3e-7); fed into the next small-gap SVD of a TT chain this is amplified past the 1e-4 parity bar
+ * (DeiT-small, 1.3e-4), so the projection path keeps the CUDA-core kernel. */
+void tta_gemm_enable_tc(int on);
 /* Same operator in fp64: a, b, c, colscale address doubles (used by the refinement step below). */
 int tta_gemm_f64_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
                          void* stream);
