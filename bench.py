@@ -441,7 +441,15 @@ def forward_bench(dev, peaks):
                 import fwd_common as fc
                 fc.tt_apply_torch(x, list(layer.tt_cores)[layer.out_tt_order:], list(layer.tt_cores)[:layer.out_tt_order])
 
+    xs_bf = {k: v.to(torch.bfloat16) for k, v in xs.items()}
+
+    def lin_fused_bf16():
+        with torch.no_grad():
+            for layer, x in lin:
+                layer(xs_bf[x.shape[1]])
+
     ms_f, ms_c = _time_cuda(lin_fused, iters=3, warm=1), _time_cuda(lin_chain, iters=3, warm=1)
+    ms_fb = _time_cuda(lin_fused_bf16, iters=3, warm=1)
     macs = 0
     macs_exec = 0
     n_dense = 0
@@ -455,6 +463,9 @@ def forward_bench(dev, peaks):
         macs_exec += layer.in_features * layer.out_features if dense else chain
     out['deit_small_ttlinear_layers'] = {'batch': 256, 'tokens': tokens, 'fused_img_s': 256 / (ms_f / 1e3), 'fused_ms': ms_f,
                                          'torch_op_chain_img_s': 256 / (ms_c / 1e3), 'torch_op_chain_ms': ms_c,
+                                         'fused_bf16_activations_ms': ms_fb,
+                                         'fused_bf16_activations_img_s': 256 / (ms_fb / 1e3),
+                                         'two_factor_fused_layers': sum(bool(getattr(l, '_fused2', False)) for l, _ in lin),
                                          'contraction_order': '{} of {} layers fold the cores into the dense weight first '
                                                               '(fewer or comparable MACs than the chain)'.format(n_dense, len(lin)),
                                          'chain_tflops_equiv': 2.0 * macs * tokens / (ms_f / 1e3) / 1e12,
@@ -469,6 +480,22 @@ def forward_bench(dev, peaks):
         tf = 2.0 * M * N * K / (ms / 1e3) / 1e12
         tc['{}x{}x{}'.format(M, N, K)] = {'ms': ms, 'tflops': tf, 'frac_of_bf16_peak': tf / peaks['bf16_tflops']}
     out['gemm_bf16_tc_kernel'] = {'bound': 'tensor', 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'shapes': tc}
+    # ---- the fused two-factor kernel (TMA + tcgen05, intermediate on chip) on the DeiT-small layer shapes ----
+    lr = {}
+    for nm, K1, N1, N2 in (('qkv_block0', 384, 320, 1152), ('qkv', 384, 256, 1152), ('proj', 384, 256, 384),
+                           ('fc1', 384, 256, 1536), ('fc2', 1536, 256, 384)):
+        x = torch.randn(tokens, K1, device=dev).to(torch.bfloat16)
+        w1 = torch.randn(N1, K1, device=dev).to(torch.bfloat16)
+        w2 = torch.randn(N2, N1, device=dev).to(torch.bfloat16)
+        y = torch.empty(tokens, N2, device=dev, dtype=torch.bfloat16)
+        ms = _time_cuda(lambda: rt.lowrank2_fwd(x, w1, w2, None, y, tokens, K1, N1, N2), iters=10, warm=3)
+        tf = 2.0 * tokens * N1 * (K1 + N2) / (ms / 1e3) / 1e12
+        gbs = tokens * 2.0 * (K1 + N2) / (ms / 1e3) / 1e9
+        lr['{}_{}x{}x{}x{}'.format(nm, tokens, K1, N1, N2)] = {
+            'ms': ms, 'tflops': tf, 'frac_of_bf16_peak': tf / peaks['bf16_tflops'],
+            'algorithmic_hbm_gbs': gbs, 'frac_of_hbm_peak': gbs / peaks['hbm_gbs']}
+    out['lowrank2_fwd_kernel'] = {'bound': 'tensor', 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                                  'io': 'bf16 in, bf16 out; algorithmic bytes = x + y (weights stay in L2)', 'shapes': lr}
     return out
 
 

@@ -50,6 +50,7 @@ class _TTLinearBase(Module):
         self._engine = None
         self._dense_engine = None
         self._dense_first = None
+        self._fused2 = None
 
     def get_ranks(self):
         return ', '.join(str(r) for r in self.tt_ranks)
@@ -83,6 +84,27 @@ class TTLinearM(_TTLinearBase):
                 y = y + self.bias
             return y.reshape(out_shape)
         rt.require_device(x)
+        if self._fused2 is None:
+            # Two-factor form: the input-side cores fold into W1 (r x in) and the output-side cores into
+            # W2 (out x r), r = the rank between the two sides (weights only, cached).  One fused tcgen05
+            # kernel then runs in -> r -> out with the rank-r intermediate kept on the SM
+            # (`tta_lowrank2_fwd`).  Taken when r fits its TMEM budget and the two dense factors cost no
+            # more than 1.5x the MACs of the four-step chain (DeiT-small tables: 0.94x ... 1.25x).
+            r_mid = int(self.tt_ranks[self.out_tt_order])
+            macs2 = r_mid * (self.in_features + self.out_features)
+            self._fused2 = bool(r_mid <= fc.LOWRANK2_MAX_INNER and self.in_features % 8 == 0 and
+                                self.in_tt_order >= 1 and self.out_tt_order >= 1 and
+                                macs2 <= 1.5 * fc.tt_chain_macs(in_cores, out_cores))
+            if self._fused2:
+                self._w1 = fc.PackedWeight(lambda: fc.fold_in_cores(list(self.tt_cores)[self.out_tt_order:]),
+                                           list(self.tt_cores)[self.out_tt_order:])
+                self._w2 = fc.PackedWeight(lambda: fc.fold_out_cores(list(self.tt_cores)[:self.out_tt_order]),
+                                           list(self.tt_cores)[:self.out_tt_order])
+                self._ws = fc.Workspace()
+        if self._fused2:
+            with torch.no_grad():
+                y = fc.lowrank2_apply(self._ws, x2d, self._w1.get(), self._w2.get(), self.bias)
+            return y.reshape(out_shape)
         if self._dense_first is None:
             # Contraction order: folding the cores into the (out x in) matrix first is a weights-only
             # computation; it is taken when the dense product is less work per token than the chain AND

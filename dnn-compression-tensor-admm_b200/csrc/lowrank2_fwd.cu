@@ -1,0 +1,533 @@
+// Fused forward of a two-factor (TT-matrix / Tucker / SVD) linear layer on the 5th-generation tensor
+// cores:   y[M, N2] = bf16( x[M, K1] * W1[N1, K1]^T ) * W2[N2, N1]^T + bias
+// One persistent kernel; the rank-N1 intermediate never leaves the SM.
+//
+// This is the contraction of TTLinearM.forward (TTLinear.py:75-93): for the 4-core TT-matrices of the
+// reference's tables (tt_deit_small_patch16_224_hp.py) the two input-side cores fold into W1 (r2 x in)
+// and the two output-side cores into W2 (out x r2) with no more MACs than the four-step chain
+// (weights-only, cached by the host), so the layer is  in -> r2 -> out  with r2 = 256 / 320.
+// Also TKLinearM (TKLinear.py:60-75: first factor, core, last factor with the core folded into one side).
+//
+// CTA = 128 rows of x, persistent over row tiles (grid = min(tiles, 148)).  Warp roles (192 threads):
+//   warp 0     TMA producer (one lane): x k-blocks into a 2-stage ring, W1 / W2 blocks (<= 128 rows x
+//              64 k, SWIZZLE_128B) into a ring of 16 KB stages; mbarrier expect_tx / complete_tx.
+//   warp 1     TMEM allocator (512 columns) + single-lane tcgen05.mma issuer.
+//              GEMM 1: acc1[128 x N1] (TMEM columns 0..)  += x-block * W1-block^T
+//              GEMM 2: acc2[buf][128 x BN2]               = V * W2-chunk^T, V = bf16(acc1) in shared memory
+//   warps 2-5  epilogue (one TMEM lane quadrant each): acc1 -> bf16 -> V (UMMA K-major SWIZZLE_128B layout,
+//              written by hand) ; acc2 chunks -> +bias -> staged transpose -> coalesced global y (fp32 or bf16).  acc2 is double buffered, so
+//              the chunk epilogue overlaps the next chunk's MMAs, and GEMM 1 of the next row tile overlaps the
+//              last chunk epilogues of this one.
+// TMEM budget: acc1 = round_up(N1, 32) columns, acc2 = 2 x BN2 with BN2 = min(128, (512 - acc1) / 2 rounded
+// down to 32)  =>  N1 <= 384.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "tta_common.cuh"
+
+namespace tta {
+
+namespace lr2 {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;                    // 64 bf16 = one 128-byte swizzle row
+constexpr int kStageBytes = kBM * 128;     // 16 KB: 128 rows x 128 B
+constexpr int kXStages = 2;
+constexpr int kMaxWStages = 8;
+constexpr int kThreads = 192;
+constexpr int kMaxN1 = 384;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A mis-sequenced pipeline must not hang the device: a wait that lasts longer than ~2 s traps.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t n = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++n & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// explicit shared-space accesses (a generic pointer into dynamic shared memory compiles to LD.E / ST.E and
+// is assumed to alias the global stores of the epilogue)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
+struct Params {
+  int M, K1, N1, N2;
+  int nk1;        // k-blocks of GEMM 1
+  int nb1;        // 128-row blocks of W1
+  int n1p16;      // N1 rounded up to 16 (MMA N granularity)
+  int nkv;        // k-blocks of GEMM 2 = ceil(N1 / 64)
+  int bn2;        // GEMM-2 chunk width
+  int nchunks;    // ceil(N2 / bn2)
+  int acc2_col;   // first TMEM column of acc2
+  int wstages;
+  int ntiles;
+  int out_f32;
+  int64_t ldy;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+    lowrank2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+                        const __grid_constant__ CUtensorMap tm_w2, const float* __restrict__ bias,
+                        void* __restrict__ yout, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Vs = smem;                                   // nkv x 16 KB
+  uint8_t* Xs = Vs + (size_t)p.nkv * kStageBytes;       // kXStages x 16 KB
+  uint8_t* Ws = Xs + (size_t)kXStages * kStageBytes;    // wstages x 16 KB
+  __shared__ uint64_t x_full[kXStages], x_empty[kXStages];
+  __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
+  __shared__ uint64_t acc1_full;
+  __shared__ uint64_t v_ready[kMaxN1 / 64];   // one per 64-column block of V: GEMM 2 starts on block 0 while the rest converts
+  __shared__ uint64_t acc2_full[2], acc2_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kXStages; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+    }
+    for (int s = 0; s < kMaxWStages; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(&acc1_full, 1);
+    for (int b = 0; b < kMaxN1 / 64; ++b) mbar_init(&v_ready[b], 128);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc2_full[b], 1);
+      mbar_init(&acc2_empty[b], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w2)) : "memory");
+      int xs = 0, ws = 0;
+      uint32_t xph = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int m0 = tile * kBM;
+        for (int kb = 0; kb < p.nk1; ++kb) {
+          mbar_wait(&x_empty[xs], xph ^ 1);
+          mbar_expect_tx(&x_full[xs], kStageBytes);
+          tma_load_2d(smem_u32(Xs + (size_t)xs * kStageBytes), &tm_x, &x_full[xs], kb * kBK, m0);
+          if (++xs == kXStages) { xs = 0; xph ^= 1; }
+          for (int j = 0; j < p.nb1; ++j) {
+            mbar_wait(&w_empty[ws], wph ^ 1);
+            mbar_expect_tx(&w_full[ws], kStageBytes);
+            tma_load_2d(smem_u32(Ws + (size_t)ws * kStageBytes), &tm_w1, &w_full[ws], kb * kBK, j * 128);
+            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+          }
+        }
+        for (int c = 0; c < p.nchunks; ++c)
+          for (int kb = 0; kb < p.nkv; ++kb) {
+            mbar_wait(&w_empty[ws], wph ^ 1);
+            mbar_expect_tx(&w_full[ws], (uint32_t)p.bn2 * 128u);
+            tma_load_2d(smem_u32(Ws + (size_t)ws * kStageBytes), &tm_w2, &w_full[ws], kb * kBK, c * p.bn2);
+            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int xs = 0, ws = 0;
+      uint32_t xph = 0, wph = 0;
+      uint32_t it = 0, g = 0;   // row tiles / GEMM-2 chunks processed by this CTA
+      const uint32_t idesc2 = umma_idesc_bf16(p.bn2);
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        // ---- GEMM 1 ----
+        for (int kb = 0; kb < p.nk1; ++kb) {
+          mbar_wait(&x_full[xs], xph);
+          const uint64_t da = umma_desc_sw128(smem_u32(Xs + (size_t)xs * kStageBytes));
+          for (int j = 0; j < p.nb1; ++j) {
+            mbar_wait(&w_full[ws], wph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t db = umma_desc_sw128(smem_u32(Ws + (size_t)ws * kStageBytes));
+            const int nj = (p.n1p16 - j * 128) < 128 ? (p.n1p16 - j * 128) : 128;
+            const uint32_t idesc1 = umma_idesc_bf16(nj);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(tmem_base + (uint32_t)(j * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&w_empty[ws]);
+            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(&x_empty[xs]);
+          if (++xs == kXStages) { xs = 0; xph ^= 1; }
+        }
+        umma_commit(&acc1_full);
+        // ---- GEMM 2 ----
+        for (int c = 0; c < p.nchunks; ++c, ++g) {
+          const uint32_t buf = g & 1;
+          mbar_wait(&acc2_empty[buf], ((g >> 1) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_tmem = tmem_base + (uint32_t)(p.acc2_col + (int)buf * p.bn2);
+          for (int kb = 0; kb < p.nkv; ++kb) {
+            if (c == 0) mbar_wait(&v_ready[kb], it & 1);
+            mbar_wait(&w_full[ws], wph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = umma_desc_sw128(smem_u32(Vs + (size_t)kb * kStageBytes));
+            const uint64_t db = umma_desc_sw128(smem_u32(Ws + (size_t)ws * kStageBytes));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&w_empty[ws]);
+            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(&acc2_full[buf]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue warps ------------------------------
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;           // row inside the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stage = smem_u32(Ws) + (uint32_t)p.wstages * kStageBytes + (uint32_t)q * 4096;   // 32 rows x 128 B per warp
+    uint32_t it = 0, g = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int64_t tile0 = (int64_t)tile * kBM;
+      // ---- acc1 -> bf16 -> V ----
+      mbar_wait(&acc1_full, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.nkv * 64; c0 += 32) {
+        uint32_t v[32];
+        if (c0 < p.n1p16) {
+          tmem_ld32(lane_addr + (uint32_t)c0, v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        const uint32_t vrow = smem_u32(Vs) + (uint32_t)(c0 >> 6) * kStageBytes + row * 128;
+        const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = c0 + 8 * i + 2 * j;
+            const float lo = col < p.N1 ? __uint_as_float(v[8 * i + 2 * j]) : 0.f;
+            const float hi = col + 1 < p.N1 ? __uint_as_float(v[8 * i + 2 * j + 1]) : 0.f;
+            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          sts128(vrow + (((ch0 + i) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+        if ((c0 & 63) == 32) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of V -> async proxy (UMMA)
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&v_ready[c0 >> 6]);
+        }
+      }
+      // ---- acc2 chunks -> y ----
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t buf = g & 1;
+        mbar_wait(&acc2_full[buf], (g >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.bn2; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + (uint32_t)(p.acc2_col + (int)buf * p.bn2 + c0), v);
+          if (c0 + 32 >= p.bn2) {
+            // the last block of this accumulator is in registers: hand the buffer back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc2_empty[buf]);
+          }
+          const int gn0 = c * p.bn2 + c0;
+          if (gn0 >= p.N2) continue;                                   // warp-uniform
+          // The accumulator arrives one row per lane; a row-per-lane store would touch 32 lines per
+          // instruction.  Transpose the 32 x 32 fp32 block through this warp's staging buffer (XOR-swizzled
+          // 16-byte chunks, conflict-free both ways) so that every store instruction writes whole lines.
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            sts128(stage + lane * 128 + ((ch ^ (lane & 7)) << 4), v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+          __syncwarp();
+          if (p.out_f32) {
+            const int cc = lane & 7, col = gn0 + 4 * cc;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) {
+              if (col + 0 < p.N2) bv.x = __ldg(bias + col);
+              if (col + 1 < p.N2) bv.y = __ldg(bias + col + 1);
+              if (col + 2 < p.N2) bv.z = __ldg(bias + col + 2);
+              if (col + 3 < p.N2) bv.w = __ldg(bias + col + 3);
+            }
+            float4 o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              o[i] = lds128(stage + rr * 128 + ((cc ^ (rr & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              o[i].x += bv.x; o[i].y += bv.y; o[i].z += bv.z; o[i].w += bv.w;
+              const int64_t grow = tile0 + q * 32 + rr;
+              if (grow < p.M) {
+                float* yr = reinterpret_cast<float*>(yout) + grow * p.ldy + col;
+                if (col + 4 <= p.N2) {
+                  *reinterpret_cast<float4*>(yr) = o[i];
+                } else {
+                  if (col + 0 < p.N2) yr[0] = o[i].x;
+                  if (col + 1 < p.N2) yr[1] = o[i].y;
+                  if (col + 2 < p.N2) yr[2] = o[i].z;
+                }
+              }
+            }
+          } else {
+            const int cc = lane & 3, col = gn0 + 8 * cc;
+            float bv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bv[e] = (bias && col + e < p.N2) ? __ldg(bias + col + e) : 0.f;
+            float4 o[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2);
+              o[2 * i] = lds128(stage + rr * 128 + (((2 * cc) ^ (rr & 7)) << 4));
+              o[2 * i + 1] = lds128(stage + rr * 128 + (((2 * cc + 1) ^ (rr & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2);
+              const float f[8] = {o[2 * i].x + bv[0], o[2 * i].y + bv[1], o[2 * i].z + bv[2], o[2 * i].w + bv[3],
+                                  o[2 * i + 1].x + bv[4], o[2 * i + 1].y + bv[5], o[2 * i + 1].z + bv[6], o[2 * i + 1].w + bv[7]};
+              const int64_t grow = tile0 + q * 32 + rr;
+              if (grow < p.M) {
+                __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(yout) + grow * p.ldy + col;
+                if (col + 8 <= p.N2) {
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                    pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  *reinterpret_cast<uint4*>(yr) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (col + e < p.N2) yr[e] = __float2bfloat16(f[e]);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor (rows x cols, row stride ld elements), box = box_rows x 64 columns, SWIZZLE_128B,
+// out-of-bounds elements read as zero.
+static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("lowrank2_fwd: cuTensorMapEncodeTiled is not available from the driver");
+    return TTA_E_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("lowrank2_fwd: cuTensorMapEncodeTiled failed (%d) for a %lld x %lld tensor, ld %lld", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+    return TTA_E_CUDA;
+  }
+  return TTA_OK;
+}
+
+}  // namespace lr2
+}  // namespace tta
+
+extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int64_t ld1, const void* w2, int64_t ld2,
+                                const float* bias, void* y, int64_t ldy, int out_fp32, int64_t M, int K1, int N1,
+                                int N2, void* stream) {
+  using namespace tta;
+  using namespace tta::lr2;
+  if (M <= 0 || N2 <= 0) return TTA_OK;
+  if (!x || !w1 || !w2 || !y || K1 <= 0 || N1 <= 0) {
+    set_error("lowrank2_fwd: bad argument");
+    return TTA_E_INVALID;
+  }
+  if (N1 > kMaxN1) {
+    set_error("lowrank2_fwd: inner width %d exceeds %d (TMEM budget)", N1, kMaxN1);
+    return TTA_E_INVALID;
+  }
+  if ((ldx & 7) || (ld1 & 7) || (ld2 & 7) || ((uintptr_t)x & 15) || ((uintptr_t)w1 & 15) || ((uintptr_t)w2 & 15) ||
+      ((uintptr_t)y & 15) || (ldy & (out_fp32 ? 3 : 7)) || M > (int64_t)kBM * 0x7fffff) {
+    set_error("lowrank2_fwd: operands must be 16-byte aligned with leading dimensions multiples of 8 (ldx %lld ld1 %lld ld2 %lld ldy %lld)",
+              (long long)ldx, (long long)ld1, (long long)ld2, (long long)ldy);
+    return TTA_E_INVALID;
+  }
+  Params p;
+  p.M = (int)M; p.K1 = K1; p.N1 = N1; p.N2 = N2;
+  p.nk1 = (K1 + kBK - 1) / kBK;
+  p.nb1 = (N1 + 127) / 128;
+  p.n1p16 = (N1 + 15) & ~15;
+  p.nkv = (N1 + 63) / 64;
+  p.acc2_col = (p.n1p16 + 31) & ~31;
+  int bn2 = ((512 - p.acc2_col) / 2) & ~31;
+  if (bn2 > 128) bn2 = 128;
+  // no wider than the output needs
+  while (bn2 > 32 && bn2 - 32 >= N2) bn2 -= 32;
+  p.bn2 = bn2;
+  p.nchunks = (N2 + bn2 - 1) / bn2;
+  p.ntiles = (int)((M + kBM - 1) / kBM);
+  p.out_f32 = out_fp32 ? 1 : 0;
+  p.ldy = ldy;
+  const size_t budget = 227 * 1024 - 1024 - 512;   // dynamic shared memory minus alignment slack and the barriers
+  const size_t fixed = (size_t)(p.nkv + kXStages + 1) * kStageBytes;   // V, x ring, output staging
+  int wst = (int)((budget - fixed) / kStageBytes);
+  if (wst > kMaxWStages) wst = kMaxWStages;
+  if (wst < 2) {
+    set_error("lowrank2_fwd: shared memory exhausted (N1 = %d)", N1);
+    return TTA_E_INVALID;
+  }
+  p.wstages = wst;
+  const size_t smem = fixed + (size_t)wst * kStageBytes + 1024;
+
+  CUtensorMap tm_x, tm_w1, tm_w2;
+  int rc = make_map(&tm_x, x, M, K1, ldx, kBM);
+  if (rc) return rc;
+  rc = make_map(&tm_w1, w1, N1, K1, ld1, 128);
+  if (rc) return rc;
+  rc = make_map(&tm_w2, w2, N2, N1, ld2, bn2);
+  if (rc) return rc;
+
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    rc = check_cuda(cudaFuncSetAttribute(lowrank2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "lowrank2_fwd smem attribute");
+    if (rc) return rc;
+    smem_set = smem;
+  }
+  const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+  lowrank2_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_w1, tm_w2, bias, y, p);
+  TTA_CHECK_LAUNCH("lowrank2_fwd launch");
+  return TTA_OK;
+}

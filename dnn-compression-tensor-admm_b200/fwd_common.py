@@ -254,6 +254,46 @@ def tt_apply_torch(x2d, in_cores, out_cores):
     return acc.reshape(R, -1)
 
 
+LOWRANK2_MAX_INNER = 384      # TMEM budget of tta_lowrank2_fwd: inner width + two output chunks <= 512 columns
+
+
+def fold_in_cores(in_cores):
+    """(r x in) matrix of the input-side cores: W1[a, (i_0..i_q)] = sum G_0[a,i_0,.] G_1[.,i_1,.] ... (TTLinear.py:79-83)."""
+    w = in_cores[0]
+    r = w.shape[0]
+    for c in in_cores[1:]:
+        w = w.reshape(-1, c.shape[0]) @ c.reshape(c.shape[0], -1)
+    return w.reshape(r, -1)
+
+
+def fold_out_cores(out_cores):
+    """(out x r) matrix of the output-side cores, rows in natural (o_0, ..., o_{p-1}) order (TTLinear.py:84-88)."""
+    w = out_cores[0]
+    for c in out_cores[1:]:
+        w = w.reshape(-1, c.shape[0]) @ c.reshape(c.shape[0], -1)
+    return w.reshape(-1, out_cores[-1].shape[2])
+
+
+def lowrank2_apply(ws, x2d, w1, w2, bias):
+    """y = (x W1^T) W2^T + bias through the fused tcgen05 kernel.  x fp32 (cast to bf16 once) or bf16 (used
+    as is); y has the dtype of x.  w1, w2: PackedWeight (bf16, row stride padded to 8)."""
+    R, K1 = x2d.shape
+    dev = x2d.device
+    if x2d.dtype == torch.bfloat16:
+        xb = x2d.contiguous()
+        out_dtype = torch.bfloat16
+    else:
+        x32 = x2d.contiguous().to(torch.float32)
+        xb = ws.get('xbf16', R * K1, torch.bfloat16, dev)
+        rt.cast_bf16(x32.reshape(-1), xb)
+        out_dtype = torch.float32
+    N1, N2 = w1.N, w2.N
+    ldy = N2 if out_dtype == torch.float32 or N2 % 8 == 0 else pad8(N2)
+    y = torch.empty(R, ldy, dtype=out_dtype, device=dev)
+    rt.lowrank2_fwd(xb, w1.mat, w2.mat, bias, y, R, K1, N1, N2, ldx=K1, ld1=w1.ld, ld2=w2.ld, ldy=ldy)
+    return y if ldy == N2 else y[:, :N2]
+
+
 def tt_chain_macs(in_cores, out_cores):
     """Multiply-accumulates per row of the factorised chain (TTLinear.py:79-88 order)."""
     macs = 0

@@ -50,7 +50,8 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
-           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd']
+           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd',
+           'tta_lowrank2_fwd']
 
 
 class TtaError(RuntimeError):
@@ -123,6 +124,7 @@ def _load():
     lib.tta_nhwc_to_nchw_f32.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp]
     lib.tta_im2col_bf16.argtypes = [vp, vp] + [ci] * 16 + [vp]
     lib.tta_ttconv_fused_fwd.argtypes = [vp] * 6 + [ci] * 10 + [vp]
+    lib.tta_lowrank2_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, ci, i64, ci, ci, ci, vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
@@ -320,6 +322,14 @@ def nhwc_to_nchw_f32(x, y, bias, B, C, HW, ldc):
 def im2col_bf16(x, out, B, H, W, C, ldx, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo, ldo):
     _check(lib().tta_im2col_bf16(_p(x), _p(out), B, H, W, C, ldx, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo, ldo,
                                  stream_handle()), 'tta_im2col_bf16')
+
+
+def lowrank2_fwd(x, w1, w2, bias, y, M, K1, N1, N2, ldx=None, ld1=None, ld2=None, ldy=None):
+    """y[M,N2] = bf16(x[M,K1] @ w1[N1,K1]^T) @ w2[N2,N1]^T + bias: one fused tcgen05 kernel (x, w1, w2 bf16)."""
+    _check(lib().tta_lowrank2_fwd(_p(x), ldx if ldx is not None else K1, _p(w1), ld1 if ld1 is not None else K1,
+                                  _p(w2), ld2 if ld2 is not None else N1, _p(bias), _p(y),
+                                  ldy if ldy is not None else N2, int(y.dtype == torch.float32), int(M), int(K1),
+                                  int(N1), int(N2), stream_handle()), 'tta_lowrank2_fwd')
 
 
 def ttconv_fused_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):

@@ -288,6 +288,20 @@ int tta_ttconv_fused_fwd(const float* x, const float* a_in, const float* kern, c
                          const float* bias, float* y, int B, int Cin, int H, int W, int Ra, int Rb,
                          int Cout, int KS, int stride, int pad, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused two-factor linear forward on the tcgen05 tensor cores (TMA-fed, persistent, the rank-N1
+ * intermediate stays in TMEM / shared memory):
+ *     y[M, N2] = bf16( x[M, K1] * w1[N1, K1]^T ) * w2[N2, N1]^T + bias[N2]
+ * Replaces the op chain of TTLinearM.forward (TTLinear.py:75-93; the host folds the input-side cores
+ * into w1 and the output-side cores into w2) and of TKLinearM.forward (TKLinear.py:60-75).
+ *   x, w1, w2 bf16 row-major with leading dimensions ldx, ld1, ld2 (multiples of 8, 16-byte aligned
+ *   bases);  bias fp32 nullable;  y fp32 (out_fp32 != 0, ldy % 4 == 0) or bf16 (ldy % 8 == 0);
+ *   N1 <= 384 (TMEM budget: N1 + 2 output chunks <= 512 columns).
+ * ------------------------------------------------------------------------------------------- */
+int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int64_t ld1, const void* w2, int64_t ld2,
+                     const float* bias, void* y, int64_t ldy, int out_fp32, int64_t M, int K1, int N1, int N2,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

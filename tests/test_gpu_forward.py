@@ -90,6 +90,15 @@ def test_ttlinear_m_forward_matches_dense(name, fin, fout):
     ref = torch.nn.functional.linear(x, z, b.to(DEV))
     assert y.shape == ref.shape
     assert _rel(y, ref) <= FWD_TOL, _rel(y, ref)
+    assert layer._fused2 is True                    # the DeiT-small tables take the fused two-factor tcgen05 kernel
+    with torch.no_grad():
+        yb = layer(x.to(torch.bfloat16))            # bf16 activations in -> bf16 out, no cast pass
+    assert yb.dtype == torch.bfloat16 and _rel(yb.float(), ref) <= FWD_TOL
+    layer._fused2 = False                           # the four-step chain (skinny contractions + tcgen05 GEMMs)
+    with torch.no_grad():
+        yc = layer(x)
+    assert _rel(yc, ref) <= FWD_TOL, _rel(yc, ref)
+    layer._fused2 = True
     # training path (autograd) agrees with the fused path and produces gradients for every core
     xg = x.clone().requires_grad_(True)
     yt = layer(xg)
@@ -228,3 +237,39 @@ def test_ttconv_fused_kernel_matches_conv_chain(B, Cin, H, W, Ra, Rb, Cout, KS, 
                            a_out.double()[:, :, None, None], b.double() if b is not None else None)
         assert torch.isfinite(y).all()
         assert _rel(y, ref) <= 2e-6, _rel(y, ref)
+
+
+@pytest.mark.parametrize('M,K1,N1,N2', [(128, 64, 64, 64), (256, 384, 320, 1152), (1000, 384, 256, 384),
+                                        (300, 1536, 320, 384), (77, 72, 40, 50), (4096, 384, 320, 1536),
+                                        (513, 200, 23, 1000), (129, 384, 384, 96), (20000, 384, 256, 1152)])
+@pytest.mark.parametrize('out_f32', [False, True])
+def test_lowrank2_fused_forward_matches_torch(M, K1, N1, N2, out_f32):
+    """y = bf16(x W1^T) W2^T + bias in one TMA-fed tcgen05 kernel (persistent over row tiles; ragged M, K1, N1, N2)."""
+    g = torch.Generator(device='cpu').manual_seed(M + 3 * K1 + 5 * N1 + 7 * N2)
+    x = torch.randn(M, K1, generator=g).to(DEV).to(torch.bfloat16)
+    w1 = (torch.randn(N1, K1, generator=g) / K1 ** 0.5).to(DEV).to(torch.bfloat16)
+    ld2 = (N1 + 7) // 8 * 8                       # leading dimensions must be multiples of 8 (16-byte rows for TMA)
+    w2_full = torch.full((N2, ld2), float('nan'), dtype=torch.bfloat16, device=DEV)
+    w2_full[:, :N1] = (torch.randn(N2, N1, generator=g) / N1 ** 0.5).to(DEV).to(torch.bfloat16)
+    w2 = w2_full[:, :N1]
+    bias = torch.randn(N2, generator=g).to(DEV)
+    ldy = (N2 + 7) // 8 * 8 + 8
+    y = torch.full((M, ldy), 7.0, device=DEV, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    rt.lowrank2_fwd(x, w1, w2_full, bias, y, M, K1, N1, N2, ld2=ld2, ldy=ldy)
+    torch.cuda.synchronize()
+    v = (x.float() @ w1.float().t()).to(torch.bfloat16).float()
+    ref = v @ w2.float().t() + bias
+    tol = 2e-3 if out_f32 else 6e-3      # bf16 rounding of the intermediate can differ by one ulp at ties
+    assert _rel(y[:, :N2].float(), ref) <= tol, _rel(y[:, :N2].float(), ref)
+    assert float((y[:, N2:].float() - 7.0).abs().max()) == 0.0       # nothing written past N2
+
+
+def test_lowrank2_rejects_bad_arguments():
+    x = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
+    w1 = torch.zeros(400, 64, device=DEV, dtype=torch.bfloat16)
+    w2 = torch.zeros(64, 400, device=DEV, dtype=torch.bfloat16)
+    y = torch.zeros(128, 64, device=DEV)
+    with pytest.raises(rt.TtaError):
+        rt.lowrank2_fwd(x, w1, w2, None, y, 128, 64, 400, 64)          # inner width beyond the TMEM budget
+    with pytest.raises(rt.TtaError):
+        rt.lowrank2_fwd(x, w1, w2, None, y, 128, 64, 64, 64, ldx=60)    # leading dimension not a multiple of 8
