@@ -98,6 +98,8 @@ class ADMM:
         self._ew_cache = None
         self.sweeps = {}
         self._shard = None
+        self._streams = None
+        self.concurrent_groups = True    # additive: False runs all TT layers as one lock-step plan
 
     # ------------------------------------------------------------------------------------------
     def _state_device(self):
@@ -149,7 +151,9 @@ class ADMM:
                 tk_names.append(name)
         plans = []
         if tt_layers:
-            plans.append((projector.TTProjectionPlan(tt_layers, dev), tt_names))
+            # independent layer groups, most critical chain first; each runs on its own stream in update()
+            for g in (projector.tt_layer_groups(tt_layers) if self.concurrent_groups else [list(range(len(tt_layers)))]):
+                plans.append((projector.TTProjectionPlan([tt_layers[i] for i in g], dev), [tt_names[i] for i in g]))
         if tk_layers:
             plans.append((projector.TKProjectionPlan(tk_layers, dev), tk_names))
         return plans
@@ -181,12 +185,7 @@ class ADMM:
             self._shard = sharding.LayerSharding(self, self._names)
             self._plans = self._build_plans(self._shard.local_names)
         with torch.no_grad():
-            for plan, names in self._plans:
-                ws = [self._params[n].data for n in names]
-                us = [self.u[n] for n in names]
-                zs = [self.z[n] for n in names]
-                plan.run(ws, us, zs)
-                self.sweeps.update(plan.sweeps)
+            self._run_plans()
             self._shard.exchange(self.z)
             if update_u:
                 want_norm = self.log or self.verbose
@@ -199,6 +198,40 @@ class ADMM:
                             self.logger[n].append(float(v))
                         if self.verbose:
                             print('*INFO: {} in ADMM, norm(w-z)={}'.format(n, v))
+
+    def _run_plans(self):
+        """Z-update of the local layers.  Several TT plans (layer groups) are enqueued on side streams -- the
+        first two on high-priority streams -- forked from and joined back into the current stream, so that
+        the Gram / refinement kernels of one group overlap the eigensolves of another and short chains do not
+        wait for long ones; sweep counts are read back (the only host sync) after everything is enqueued."""
+        args = lambda names: ([self._params[n].data for n in names], [self.u[n] for n in names],
+                              [self.z[n] for n in names])
+        async_plans = [(pl, nm) for pl, nm in self._plans if hasattr(pl, 'enqueue')]
+        if len(async_plans) > 1 and not rt.backend_is_emulated() and all(pl.profile is None for pl, _ in async_plans):
+            dev = self._state_device()
+            if self._streams is None or len(self._streams) != len(async_plans):
+                self._streams = [torch.cuda.Stream(device=dev, priority=-1 if i < 2 else 0)
+                                 for i in range(len(async_plans))]
+            main = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for (plan, names), st in zip(async_plans, self._streams):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    plan.enqueue(*args(names))
+                    done = torch.cuda.Event()
+                    done.record(st)
+                main.wait_event(done)
+            for plan, names in self._plans:
+                if hasattr(plan, 'enqueue'):
+                    plan.collect()
+                else:
+                    plan.run(*args(names))
+                self.sweeps.update(plan.sweeps)
+            return
+        for plan, names in self._plans:
+            plan.run(*args(names))
+            self.sweeps.update(plan.sweeps)
 
     def append_admm_loss(self, loss):
         if not self._names:

@@ -15,8 +15,11 @@
 //     go to concurrent internal streams).
 #include <cooperative_groups.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <map>
+#include <utility>
 #include <vector>
 
 #include "eig_device.cuh"
@@ -165,26 +168,41 @@ struct StreamPool {
   cudaStream_t s[kPoolStreams] = {};
   cudaEvent_t fork = nullptr;
   cudaEvent_t join[kPoolStreams] = {};
+  int base_prio = 0, prio_lo = 0;
+  cudaStream_t get(int i) {
+    if (!s[i]) {
+      int prio = base_prio + i;
+      if (prio > prio_lo) prio = prio_lo;
+      if (cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return s[i];
+  }
 };
 
-static StreamPool* pool_for_device(int dev) {
-  static std::map<int, StreamPool*> pools;
-  auto it = pools.find(dev);
+// One pool per (device, calling stream): independent callers (the layer groups of admm.ADMM.update run on
+// their own streams) must not share internal streams, or the launches of one caller would queue behind
+// the other's in stream order although the problems are independent.
+static StreamPool* pool_for(int dev, cudaStream_t caller) {
+  static std::map<std::pair<int, cudaStream_t>, StreamPool*> pools;
+  const auto key = std::make_pair(dev, caller);
+  auto it = pools.find(key);
   if (it != pools.end()) return it->second;
   StreamPool* p = new StreamPool();
   // Stream i serves the i-th largest cluster size of a call: descending priority, so that when SMs
   // free up the block scheduler places the big clusters (the critical path of a wave) first and the
-  // small problems fill the SMs that are left.
+  // small problems fill the SMs that are left.  A caller on a default-priority stream starts one level
+  // lower than a caller on a high-priority stream (the critical layer group).  Streams are created on
+  // first use: every stream occupies one of the device's hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS),
+  // and streams that share a queue serialise.
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // hi is numerically the smallest
-  for (int i = 0; i < kPoolStreams; ++i) {
-    int prio = prio_hi + i;
-    if (prio > prio_lo) prio = prio_lo;
-    if (cudaStreamCreateWithPriority(&p->s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-  }
+  int caller_prio = 0;
+  if (caller == nullptr || cudaStreamGetPriority(caller, &caller_prio) != cudaSuccess) caller_prio = 0;
+  p->base_prio = prio_hi + (caller_prio < 0 ? 0 : 1);
+  p->prio_lo = prio_lo;
   if (cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-  pools[dev] = p;
+  pools[key] = p;
   return p;
 }
 
@@ -263,7 +281,7 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
-  StreamPool* pool = pool_for_device(dev);
+  StreamPool* pool = pool_for(dev, st);
   if (!pool) {
     set_error("jacobi cluster: cannot create internal streams");
     return TTA_E_CUDA;
@@ -285,7 +303,12 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
     offs[key] = (int)flat.size();
     flat.insert(flat.end(), groups[key].begin(), groups[key].end());
   }
-  rc = check_cuda(cudaMemcpyAsync(ids_dev, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+  const void* ids_src = flat.data();
+  if (void* slot = pinned_stage(flat.size() * sizeof(int32_t))) {   // pinned source: the copy only enqueues
+    memcpy(slot, flat.data(), flat.size() * sizeof(int32_t));
+    ids_src = slot;
+  }
+  rc = check_cuda(cudaMemcpyAsync(ids_dev, ids_src, flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st),
                   "jacobi cluster ids upload");
   if (rc) return rc;
   rc = check_cuda(cudaEventRecord(pool->fork, st), "jacobi cluster fork");
@@ -294,7 +317,11 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
   int gi = 0;
   for (int key : order) {
     const int si = gi++ % kPoolStreams;
-    cudaStream_t gs = pool->s[si];
+    cudaStream_t gs = pool->get(si);
+    if (!gs) {
+      set_error("jacobi cluster: cannot create an internal stream");
+      return TTA_E_CUDA;
+    }
     if (!used[si]) {
       rc = check_cuda(cudaStreamWaitEvent(gs, pool->fork, 0), "jacobi cluster stream wait");
       if (rc) return rc;

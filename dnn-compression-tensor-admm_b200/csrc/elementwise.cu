@@ -23,6 +23,27 @@ void set_error(const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Pinned staging ring for small host -> device uploads inside enqueue-only calls.  cudaMemcpyAsync from
+// pageable memory first synchronises the stream ("a stream sync is performed before the copy is
+// initiated"), which would stall the host once per eigensolver wave; from pinned memory it only enqueues.
+// A slot is reused after kRingBytes of later uploads -- far more than a launch queue can hold in flight.
+void* pinned_stage(size_t bytes) {
+  constexpr size_t kRingBytes = 4u << 20;
+  static char* ring = nullptr;
+  static size_t head = 0;
+  if (!ring) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, kRingBytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    ring = static_cast<char*>(p);
+  }
+  bytes = (bytes + 63) & ~(size_t)63;
+  if (bytes > kRingBytes) return nullptr;
+  if (head + bytes > kRingBytes) head = 0;
+  void* out = ring + head;
+  head += bytes;
+  return out;
+}
+
 constexpr int kEwThreads = 256;
 constexpr int kEwVecPerThread = 4;                                  // float4 per thread per chunk
 constexpr int kEwChunk = kEwThreads * kEwVecPerThread * 4;          // 4096 elements

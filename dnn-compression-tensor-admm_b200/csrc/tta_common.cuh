@@ -16,6 +16,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 
 void set_error(const char* fmt, ...);
 void count_launch();   // every kernel launch of the library is counted (bench.py reports `gpu_launches`)
+void* pinned_stage(size_t bytes);   // slot of a pinned ring for small async H2D uploads (NULL if unavailable)
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {

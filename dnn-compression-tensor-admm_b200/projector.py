@@ -220,6 +220,63 @@ class TTLayer:
         self.d = len(self.shapes)
 
 
+def tt_layer_groups(layers, skip_full_rank=True, max_groups=6):
+    """Partition TT layers into groups that run as independent plans on their own CUDA streams.
+
+    One plan executes its waves in lock step (every eigenproblem of a wave must finish before the next
+    Gram starts), so layers whose chains have very different lengths hold each other up, and the Gram /
+    refinement / projection kernels between two eigensolver phases leave most SMs idle.  Groups are formed by
+    (number of real steps, size class of the largest eigenproblem); a class whose big wave needs more than
+    one GPU-full of SMs is chunked, and the classes of small problems (k <= 128) are merged.  Returned most
+    critical first (longest modelled chain): the caller gives the first groups the high-priority streams.
+    """
+    def real_ks(L):
+        ks = []
+        for i in range(L.d - 1):
+            m, n = L.ranks[i] * L.shapes[i], _prod(L.shapes[i + 1:])
+            k = min(m, n)
+            if not (skip_full_rank and L.ranks[i + 1] == k):
+                ks.append(k)
+        return ks
+
+    mode = os.environ.get('TTA_GROUP_MODE', '')
+    if mode.startswith('rr'):
+        # experiment: G balanced groups, every class dealt round-robin (same wave structure in every group)
+        G = int(mode[2:] or 2)
+        order = sorted(range(len(layers)), key=lambda li: (-sum(eig_time_ms(k) * eig_ctas(k) for k in real_ks(layers[li])), li))
+        out = [[] for _ in range(G)]
+        for q, li in enumerate(order):
+            out[q % G].append(li)
+        return [sorted(g) for g in out if g]
+    classes = {}
+    for li, L in enumerate(layers):
+        ks = real_ks(L)
+        kmax = max(ks, default=0)
+        key = (0, 0) if kmax <= 128 else (len(ks), int(math.ceil(math.log2(kmax))))
+        classes.setdefault(key, []).append((li, ks))
+    groups = []
+    for key, members in classes.items():
+        chunks = [[]]
+        load = 0
+        for li, ks in members:
+            need = eig_ctas(max(ks, default=1))
+            if chunks[-1] and key != (0, 0) and load + need > kNumSMsB200:
+                chunks.append([])
+                load = 0
+            chunks[-1].append((li, ks))
+            load += need
+        groups.extend(chunks)
+    chain = lambda g: max(sum(eig_time_ms(k) for k in ks) for _, ks in g) if g else 0.0
+    groups.sort(key=lambda g: -chain(g))
+    while len(groups) > max_groups:                       # merge the two least critical groups
+        b = groups.pop()
+        groups[-1] = groups[-1] + b
+    return [[li for li, _ in g] for g in groups if g]
+
+
+kNumSMsB200 = 148
+
+
 class TTProjectionPlan:
     """Batched TT-SVD projection of a list of layers: Z_l = Proj_TT(W_l + U_l)."""
 
@@ -236,6 +293,7 @@ class TTProjectionPlan:
         self.skip_full_rank = bool(skip_full_rank)
         self.sweeps = {}
         self.profile = None
+        self.trace = None
         self._bound = None
         self._alloc()
 
@@ -432,16 +490,30 @@ class TTProjectionPlan:
 
     # -- execution ---------------------------------------------------------------------------------
     def run(self, w_list, u_list, z_list):
+        self.enqueue(w_list, u_list, z_list)
+        self.collect()
+
+    def enqueue(self, w_list, u_list, z_list):
+        """Enqueue the whole projection on the current stream; no host synchronisation."""
         self.bind(w_list, u_list, z_list)
-        self.sweeps = {}
         ph = _Phases(self.profile)
+        tr = self.trace            # None, or a list that receives (label, CUDA event) marks of this stream (diagnostics)
+
+        def mark(label):
+            if tr is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                tr.append((label, ev))
+        mark('start')
         ph.mark('unfold')
         rt.unfold_add(self.t_unfold)
-        for wave in self.waves:
+        for wi, wave in enumerate(self.waves):
             ph.mark('gram')
             rt.gram(wave['gram'])
+            mark('w{} eig begin'.format(wi))
             ph.mark('eig')
             rt.jacobi_eigh_async(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
+            mark('w{} eig end'.format(wi))
             ph.mark('select')
             if self.refine:
                 rt.refine_prepare(wave['refine'])
@@ -460,10 +532,21 @@ class TTProjectionPlan:
         ph.mark('fold')
         if self.t_fold.n:
             rt.fold_store(self.t_fold)
+        mark('end')
         ph.finish()
-        # one host synchronisation per update: sweep counts / convergence status of every wave
-        for wave in self.waves:
-            sw = rt.jacobi_results(wave['eig'], wave['scratch'], self.max_sweeps)
+
+    def collect(self):
+        """The one host synchronisation of an update: sweep counts / convergence status of every wave."""
+        self.sweeps = {}
+        live = [w for w in self.waves if w['eig'].n]
+        if not live:
+            return
+        flat = torch.cat([w['scratch'][:6 * w['eig'].n] for w in live]).cpu().numpy()     # one D2H copy per plan
+        off = 0
+        for wave in live:
+            n6 = 6 * wave['eig'].n
+            sw = rt.jacobi_results_from_host(flat[off:off + n6], wave['eig'], self.max_sweeps)
+            off += n6
             for q, li in enumerate(wave['idx']):
                 self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
 

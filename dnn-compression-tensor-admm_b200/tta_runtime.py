@@ -14,6 +14,10 @@ import os
 import numpy as np
 import torch
 
+# The layer groups of ADMM.update() and the eigensolver's internal streams need more hardware work queues
+# than the default 8 (streams that share a queue serialise); read by the driver when the context is created.
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libtta.so')
 
@@ -240,6 +244,12 @@ def jacobi_results(tab, scratch, max_sweeps=40):
     if tab.n == 0:
         return sweeps[:0]
     host = scratch[:6 * tab.n].cpu().numpy() if _FAKE is None else scratch[:6 * tab.n].numpy()
+    return jacobi_results_from_host(host, tab, max_sweeps)
+
+
+def jacobi_results_from_host(host, tab, max_sweeps=40):
+    """Same, from a host copy of the first 6 * n int32 of the scratch buffer (one D2H copy can serve many waves)."""
+    sweeps = np.zeros(max(tab.n, 1), dtype=np.int32)
     host = np.ascontiguousarray(host, dtype=np.int32)
     _check(lib().tta_jacobi_read_results(ctypes.c_void_p(host.ctypes.data), tab.host_ptr, tab.n, int(max_sweeps),
                                          ctypes.c_void_p(sweeps.ctypes.data)), 'tta_jacobi_read_results')
