@@ -226,11 +226,9 @@ def run_ours(args):
     params = dict(model.named_parameters())
 
     def e2e_step():
-        for n in admm._names:
-            params[n].data.copy_(host_w[n], non_blocking=True)
-        admm.update()
-        for n in admm._names:
-            host_z[n].copy_(admm.z[n], non_blocking=True)
+        # public API for host-resident weights: pinned W in, Z out (admm.ADMM.update_from_host); the copies of
+        # one layer group run on that group's stream and overlap the projection of the others
+        admm.update_from_host(host_w, host_z)
         torch.cuda.current_stream().synchronize()
 
     e2e_step()

@@ -177,7 +177,15 @@ class ADMM:
         return tab
 
     # ------------------------------------------------------------------------------------------
-    def update(self, update_u=True):
+    def update_from_host(self, host_w, host_z=None, update_u=True):
+        """Additive: `update()` for weights that live in (pinned) host memory.  `host_w[name]` is copied into the
+        parameter and, when `host_z` is given, Z is copied back into `host_z[name]` -- group by group on the
+        groups' own streams, so the transfers overlap the projection of the other groups (the critical group is
+        uploaded first, and only its download is exposed at the end).  Synchronise the current stream before reading
+        `host_z`."""
+        self.update(update_u, _host_in=host_w, _host_out=host_z)
+
+    def update(self, update_u=True, _host_in=None, _host_out=None):
         if not self._names:
             return
         import sharding
@@ -185,8 +193,18 @@ class ADMM:
             self._shard = sharding.LayerSharding(self, self._names)
             self._plans = self._build_plans(self._shard.local_names)
         with torch.no_grad():
-            self._run_plans()
+            if _host_in is not None:      # parameters this rank does not project are only read by the dual update
+                local = set(self._shard.local_names)
+                for n in self._names:
+                    if n not in local:
+                        self._params[n].data.copy_(_host_in[n], non_blocking=True)
+            self._run_plans(_host_in, _host_out)
             self._shard.exchange(self.z)
+            if _host_out is not None:
+                local = set(self._shard.local_names)
+                for n in self._names:
+                    if n not in local:
+                        _host_out[n].copy_(self.z[n], non_blocking=True)
             if update_u:
                 want_norm = self.log or self.verbose
                 sq = torch.zeros(len(self._names), dtype=torch.float64, device=self._state_device()) if want_norm else None
@@ -199,7 +217,7 @@ class ADMM:
                         if self.verbose:
                             print('*INFO: {} in ADMM, norm(w-z)={}'.format(n, v))
 
-    def _run_plans(self):
+    def _run_plans(self, host_in=None, host_out=None):
         """Z-update of the local layers.  Several TT plans (layer groups) are enqueued on side streams -- the
         first two on high-priority streams -- forked from and joined back into the current stream, so that
         the Gram / refinement kernels of one group overlap the eigensolves of another and short chains do not
@@ -218,7 +236,13 @@ class ADMM:
             for (plan, names), st in zip(async_plans, self._streams):
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
+                    if host_in is not None:
+                        for n in names:
+                            self._params[n].data.copy_(host_in[n], non_blocking=True)
                     plan.enqueue(*args(names))
+                    if host_out is not None:
+                        for n in names:
+                            host_out[n].copy_(self.z[n], non_blocking=True)
                     done = torch.cuda.Event()
                     done.record(st)
                 main.wait_event(done)
@@ -226,12 +250,25 @@ class ADMM:
                 if hasattr(plan, 'enqueue'):
                     plan.collect()
                 else:
+                    self._copy(host_in, names, True)
                     plan.run(*args(names))
+                    self._copy(host_out, names, False)
                 self.sweeps.update(plan.sweeps)
             return
         for plan, names in self._plans:
+            self._copy(host_in, names, True)
             plan.run(*args(names))
+            self._copy(host_out, names, False)
             self.sweeps.update(plan.sweeps)
+
+    def _copy(self, host, names, to_device):
+        if host is None:
+            return
+        for n in names:
+            if to_device:
+                self._params[n].data.copy_(host[n], non_blocking=True)
+            else:
+                host[n].copy_(self.z[n], non_blocking=True)
 
     def append_admm_loss(self, loss):
         if not self._names:

@@ -168,3 +168,29 @@ def test_tucker_sweep_config(C, frac):
     z_ref, sweeps = port.project_tk(weights['weight'].numpy(), hp.ranks['weight'], return_sweeps=True)
     assert rel_fro(a.z['weight'].cpu().numpy(), z_ref) <= Z_TOL
     assert a._plans[0][0].hooi_sweeps['weight'] == sweeps
+
+
+def test_update_from_host_matches_update_on_gpu():
+    """Host-resident weights: ADMM.update_from_host (copies overlapped on the layer groups' streams) gives the same
+    Z, U as update() on device-resident weights, and the single-plan mode gives the same Z as the grouped one."""
+    from admm import ADMM
+    wb, hb, fmt = workloads.CONFIGS['resnet50_tt']
+    names = ['layer1.1.conv2.weight', 'layer2.0.conv2.weight', 'layer3.0.conv1.weight', 'layer3.1.conv2.weight',
+             'layer4.0.conv1.weight']
+    weights = {n: w for n, w in wb().items() if n in names}
+    pinned = {n: w.contiguous().pin_memory() for n, w in weights.items()}
+    host_z = {n: torch.empty_like(w).pin_memory() for n, w in weights.items()}
+    a = ADMM(workloads.ParamBag({n: torch.zeros_like(w) for n, w in weights.items()}, device=DEV), 1e-3, hb(), fmt, DEV)
+    b = ADMM(workloads.ParamBag(weights, device=DEV), 1e-3, hb(), fmt, DEV)
+    c = ADMM(workloads.ParamBag(weights, device=DEV), 1e-3, hb(), fmt, DEV)
+    c.concurrent_groups = False
+    for _ in range(2):
+        a.update_from_host(pinned, host_z)
+        b.update()
+        c.update()
+    torch.cuda.synchronize()
+    assert len(a._plans) > 1 and len(c._plans) == 1
+    for n in weights:
+        assert torch.equal(a.z[n], b.z[n]) and torch.equal(a.u[n], b.u[n]), n
+        assert torch.equal(host_z[n], b.z[n].cpu()), n
+        assert rel_fro(c.z[n].cpu().numpy(), b.z[n].cpu().numpy()) <= 1e-6, n

@@ -204,3 +204,39 @@ def test_layer_modules_autograd_path_on_cpu(emulated_backend):
     with pytest.raises(rt.TtaError):
         with torch.no_grad():
             lin(x.detach())
+
+
+def test_update_from_host_equals_update(emulated_backend):
+    """ADMM.update_from_host(host_w, host_z): same Z / U as copying the weights in, update(), copying Z out."""
+    from admm import ADMM
+    wb, hb, fmt = workloads.CONFIGS['resnet32_tt']
+    weights = _subset(wb(), ['layer1.0.conv1.weight', 'layer2.0.conv1.weight', 'layer3.1.conv2.weight'])
+    a = ADMM(workloads.ParamBag({n: torch.zeros_like(w) for n, w in weights.items()}), 1e-3, hb(), fmt, 'cpu')
+    b = ADMM(workloads.ParamBag(weights), 1e-3, hb(), fmt, 'cpu')
+    host_z = {n: torch.empty_like(w) for n, w in weights.items()}
+    for _ in range(2):
+        a.update_from_host(weights, host_z)
+        b.update()
+    for n in weights:
+        assert torch.equal(a.z[n], b.z[n]) and torch.equal(a.u[n], b.u[n]) and torch.equal(host_z[n], b.z[n])
+
+
+def test_tt_layer_groups_partition():
+    """Layer groups of ADMM.update(): a partition of the layers, classes by chain shape, most critical first."""
+    import projector
+    wb, hb, _ = workloads.CONFIGS['resnet50_tt']
+    hp, weights = hb(), wb()
+    layers = [projector.TTLayer(n, weights[n].shape, hp.tt_shapes[n], hp.ranks[n]) for n in hp.ranks]
+    groups = projector.tt_layer_groups(layers)
+    assert sorted(i for g in groups for i in g) == list(range(len(layers)))
+    assert 2 <= len(groups) <= 6
+    names = [[layers[i].name for i in g] for g in groups]
+    assert all('layer4' in n and 'conv2' in n for n in names[0]) and len(names[0]) == 3     # the 480 -> 512 chain
+    small = [g for g in names if any(n.startswith('layer1') for n in g)]
+    assert len(small) == 1 and all(n.startswith(('layer1', 'layer2')) for n in small[0])
+    # DeiT-small: 48 equal-shaped chains, chunked into GPU-fulls
+    wb, hb, _ = workloads.CONFIGS['deit_small_tt']
+    hp, weights = hb(), wb()
+    layers = [projector.TTLayer(n, weights[n].shape, hp.tt_shapes[n], list(hp.ranks[n])) for n in hp.ranks]
+    groups = projector.tt_layer_groups(layers)
+    assert sorted(i for g in groups for i in g) == list(range(48)) and len(groups) <= 6
