@@ -35,7 +35,7 @@ namespace cg = cooperative_groups;
 namespace tta {
 
 template <int RL>
-__global__ void __launch_bounds__(kGraThreads, 1)
+__global__ void __launch_bounds__(kGraThreads, RL == 4 ? 2 : 1)
     jacobi_gra_kernel(const tta_eig_task* __restrict__ tasks, const int32_t* __restrict__ prob_ids,
                       int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
                       const float* __restrict__ floor2, float tol2, float stop2, int max_sweeps,

@@ -15,7 +15,7 @@
 //              GEMM 1: acc1[128 x N1] (TMEM columns 0..)  += x-block * W1-block^T
 //              GEMM 2: acc2[buf][128 x BN2]               = V * W2-chunk^T, V = bf16(acc1) in shared memory
 //   warps 2-5  epilogue (one TMEM lane quadrant each): acc1 -> bf16 -> V (UMMA K-major SWIZZLE_128B layout,
-//              written by hand) ; acc2 chunks -> +bias -> staged transpose -> coalesced global y (fp32 or bf16).  acc2 is double buffered, so
+//              written by hand) ; acc2 chunks -> +bias -> swizzled staging -> TMA store of y (fp32 or bf16).  acc2 is double buffered, so
 //              the chunk epilogue overlaps the next chunk's MMAs, and GEMM 1 of the next row tile overlaps the
 //              last chunk epilogues of this one.
 // TMEM budget: acc1 = round_up(N1, 32) columns, acc2 = 2 x BN2 with BN2 = min(128, (512 - acc1) / 2 rounded
@@ -146,8 +146,8 @@ struct Params {
 
 __global__ void __launch_bounds__(kThreads, 1)
     lowrank2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
-                        const __grid_constant__ CUtensorMap tm_w2, const float* __restrict__ bias,
-                        void* __restrict__ yout, const Params p) {
+                        const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_y,
+                        const float* __restrict__ bias, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Vs = smem;                                   // nkv x 16 KB
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;           // row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stage = smem_u32(Ws) + (uint32_t)p.wstages * kStageBytes + (uint32_t)q * 4096;   // 32 rows x 128 B per warp
-    uint32_t it = 0, g = 0;
+    const uint32_t stage = smem_u32(Ws) + (uint32_t)p.wstages * kStageBytes + (uint32_t)q * 8192;   // 2 x (32 rows x 128 B) per warp
+    uint32_t it = 0, g = 0, nst = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int64_t tile0 = (int64_t)tile * kBM;
       // ---- acc1 -> bf16 -> V ----
@@ -333,83 +333,56 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int gn0 = c * p.bn2 + c0;
           if (gn0 >= p.N2) continue;                                   // warp-uniform
           // The accumulator arrives one row per lane; a row-per-lane store would touch 32 lines per
-          // instruction.  Transpose the 32 x 32 fp32 block through this warp's staging buffer (XOR-swizzled
-          // 16-byte chunks, conflict-free both ways) so that every store instruction writes whole lines.
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            sts128(stage + lane * 128 + ((ch ^ (lane & 7)) << 4), v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+          // instruction.  The 32 x 32 block goes (bias added, converted) into this warp's staging buffer in
+          // the SWIZZLE_128B (fp32) / SWIZZLE_64B (bf16) pattern of the output tensor map, and one lane hands
+          // it to the TMA store engine, which writes whole lines and clips rows >= M / columns >= N2 (16-byte granules).
+          // Two staging buffers per warp: the store of block i drains while block i + 1 is staged.
+          const uint32_t sbuf = stage + (nst & 1) * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer of block i - 2 is free
           __syncwarp();
           if (p.out_f32) {
-            const int cc = lane & 7, col = gn0 + 4 * cc;
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias) {
-              if (col + 0 < p.N2) bv.x = __ldg(bias + col);
-              if (col + 1 < p.N2) bv.y = __ldg(bias + col + 1);
-              if (col + 2 < p.N2) bv.z = __ldg(bias + col + 2);
-              if (col + 3 < p.N2) bv.w = __ldg(bias + col + 3);
-            }
-            float4 o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + (lane >> 3);
-              o[i] = lds128(stage + rr * 128 + ((cc ^ (rr & 7)) << 4));
-            }
+            for (int ch = 0; ch < 8; ++ch) {
+              float o[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + (lane >> 3);
-              o[i].x += bv.x; o[i].y += bv.y; o[i].z += bv.z; o[i].w += bv.w;
-              const int64_t grow = tile0 + q * 32 + rr;
-              if (grow < p.M) {
-                float* yr = reinterpret_cast<float*>(yout) + grow * p.ldy + col;
-                if (col + 4 <= p.N2) {
-                  *reinterpret_cast<float4*>(yr) = o[i];
-                } else {
-                  if (col + 0 < p.N2) yr[0] = o[i].x;
-                  if (col + 1 < p.N2) yr[1] = o[i].y;
-                  if (col + 2 < p.N2) yr[2] = o[i].z;
-                }
+              for (int e = 0; e < 4; ++e) {
+                const int cix = gn0 + 4 * ch + e;
+                o[e] = __uint_as_float(v[4 * ch + e]) + ((bias && cix < p.N2) ? __ldg(bias + cix) : 0.f);
               }
+              sts128(sbuf + lane * 128 + ((ch ^ (lane & 7)) << 4), __float_as_uint(o[0]), __float_as_uint(o[1]),
+                     __float_as_uint(o[2]), __float_as_uint(o[3]));
             }
           } else {
-            const int cc = lane & 3, col = gn0 + 8 * cc;
-            float bv[8];
+            const int sw = (lane >> 1) & 3;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) bv[e] = (bias && col + e < p.N2) ? __ldg(bias + col + e) : 0.f;
-            float4 o[8];
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t pk[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = 8 * i + (lane >> 2);
-              o[2 * i] = lds128(stage + rr * 128 + (((2 * cc) ^ (rr & 7)) << 4));
-              o[2 * i + 1] = lds128(stage + rr * 128 + (((2 * cc + 1) ^ (rr & 7)) << 4));
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = 8 * i + (lane >> 2);
-              const float f[8] = {o[2 * i].x + bv[0], o[2 * i].y + bv[1], o[2 * i].z + bv[2], o[2 * i].w + bv[3],
-                                  o[2 * i + 1].x + bv[4], o[2 * i + 1].y + bv[5], o[2 * i + 1].z + bv[6], o[2 * i + 1].w + bv[7]};
-              const int64_t grow = tile0 + q * 32 + rr;
-              if (grow < p.M) {
-                __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(yout) + grow * p.ldy + col;
-                if (col + 8 <= p.N2) {
-                  uint32_t pk[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                    pk[e] = *reinterpret_cast<uint32_t*>(&h);
-                  }
-                  *reinterpret_cast<uint4*>(yr) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (col + e < p.N2) yr[e] = __float2bfloat16(f[e]);
-                }
+              for (int e = 0; e < 4; ++e) {
+                const int cix = gn0 + 8 * ch + 2 * e;
+                const float lo = __uint_as_float(v[8 * ch + 2 * e]) + ((bias && cix < p.N2) ? __ldg(bias + cix) : 0.f);
+                const float hi = __uint_as_float(v[8 * ch + 2 * e + 1]) + ((bias && cix + 1 < p.N2) ? __ldg(bias + cix + 1) : 0.f);
+                __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h);
               }
+              sts128(sbuf + lane * 64 + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
             }
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged block -> async proxy (TMA)
           __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tm_y)),
+                         "r"(sbuf), "r"(gn0), "r"((int)(tile0 + q * 32))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++nst;
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores done before the CTA retires
+    __syncwarp();
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -438,21 +411,22 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor (rows x cols, row stride ld elements), box = box_rows x 64 columns, SWIZZLE_128B,
-// out-of-bounds elements read as zero.
-static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D tensor (rows x cols, row stride ld elements), box = box_rows x box_cols, out-of-bounds elements read as
+// zero / are not written.
+static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    int box_cols = kBK, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, int esize = 2,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("lowrank2_fwd: cuTensorMapEncodeTiled is not available from the driver");
     return TTA_E_CUDA;
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * esize};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("lowrank2_fwd: cuTensorMapEncodeTiled failed (%d) for a %lld x %lld tensor, ld %lld", (int)r,
               (long long)rows, (long long)cols, (long long)ld);
@@ -501,7 +475,7 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
   p.out_f32 = out_fp32 ? 1 : 0;
   p.ldy = ldy;
   const size_t budget = 227 * 1024 - 1024 - 512;   // dynamic shared memory minus alignment slack and the barriers
-  const size_t fixed = (size_t)(p.nkv + kXStages + 1) * kStageBytes;   // V, x ring, output staging
+  const size_t fixed = (size_t)(p.nkv + kXStages + 2) * kStageBytes;   // V, x ring, output staging (8 x 4 KB)
   int wst = (int)((budget - fixed) / kStageBytes);
   if (wst > kMaxWStages) wst = kMaxWStages;
   if (wst < 2) {
@@ -511,12 +485,19 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
   p.wstages = wst;
   const size_t smem = fixed + (size_t)wst * kStageBytes + 1024;
 
-  CUtensorMap tm_x, tm_w1, tm_w2;
+  CUtensorMap tm_x, tm_w1, tm_w2, tm_y;
   int rc = make_map(&tm_x, x, M, K1, ldx, kBM);
   if (rc) return rc;
   rc = make_map(&tm_w1, w1, N1, K1, ld1, 128);
   if (rc) return rc;
   rc = make_map(&tm_w2, w2, N2, N1, ld2, bn2);
+  if (rc) return rc;
+  // output: 32 x 32 blocks, 128-byte (fp32) or 64-byte (bf16) rows in the staging buffers
+  // The TMA store works in 16-byte granules: the map covers N2 rounded up to 4 fp32 / 8 bf16 columns (<= ldy by the
+  // alignment rule above); the pad columns of a ragged N2 receive zeros.
+  const int n2m = out_fp32 ? ((N2 + 3) & ~3) : ((N2 + 7) & ~7);
+  rc = out_fp32 ? make_map(&tm_y, y, M, n2m, ldy, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map(&tm_y, y, M, n2m, ldy, 32, 32, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
 
   static size_t smem_set = 0;
@@ -527,7 +508,7 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
     smem_set = smem;
   }
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-  lowrank2_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_w1, tm_w2, bias, y, p);
+  lowrank2_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_w1, tm_w2, tm_y, bias, p);
   TTA_CHECK_LAUNCH("lowrank2_fwd launch");
   return TTA_OK;
 }

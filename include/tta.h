@@ -296,7 +296,9 @@ int tta_ttconv_fused_fwd(const float* x, const float* a_in, const float* kern, c
  * into w1 and the output-side cores into w2) and of TKLinearM.forward (TKLinear.py:60-75).
  *   x, w1, w2 bf16 row-major with leading dimensions ldx, ld1, ld2 (multiples of 8, 16-byte aligned
  *   bases);  bias fp32 nullable;  y fp32 (out_fp32 != 0, ldy % 4 == 0) or bf16 (ldy % 8 == 0);
- *   N1 <= 384 (TMEM budget: N1 + 2 output chunks <= 512 columns).
+ *   N1 <= 384 (TMEM budget: N1 + 2 output chunks <= 512 columns).  y is written by TMA stores in 16-byte
+ *   granules: when N2 is not a multiple of 4 (fp32) / 8 (bf16) the pad columns up to that multiple (they lie
+ *   inside ldy) receive zeros.
  * ------------------------------------------------------------------------------------------- */
 int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int64_t ld1, const void* w2, int64_t ld2,
                      const float* bias, void* y, int64_t ldy, int out_fp32, int64_t M, int K1, int N1, int N2,
