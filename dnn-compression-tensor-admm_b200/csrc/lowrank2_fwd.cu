@@ -21,6 +21,7 @@
 // TMEM budget: acc1 = round_up(N1, 32) columns, acc2 = 2 x BN2 with BN2 = min(128, (512 - acc1) / 2 rounded
 // down to 32)  =>  N1 <= 384.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "tta_common.cuh"
@@ -144,10 +145,12 @@ struct Params {
   int64_t ldy;
 };
 
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
     lowrank2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                         const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_y,
-                        const float* __restrict__ bias, const Params p) {
+                        const float* __restrict__ bias, const Params p,
+                        unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Vs = smem;                                   // nkv x 16 KB
@@ -189,6 +192,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  // TTA_LR2_PROF=1: cycles spent by CTA 0's roles in each wait / work phase (diagnostics)
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tp = 0;
+  const bool profiling = PROF && prof != nullptr && blockIdx.x == 0;
+#define LR2_T0() if constexpr (PROF) { if (profiling) tp = clock64(); }
+#define LR2_ACC(i) if constexpr (PROF) { if (profiling) { const long long t1_ = clock64(); pc[i] += t1_ - tp; tp = t1_; } }
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -206,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_2d(smem_u32(Xs + (size_t)xs * kStageBytes), &tm_x, &x_full[xs], kb * kBK, m0);
           if (++xs == kXStages) { xs = 0; xph ^= 1; }
           for (int j = 0; j < p.nb1; ++j) {
-            mbar_wait(&w_empty[ws], wph ^ 1);
+            LR2_T0() mbar_wait(&w_empty[ws], wph ^ 1); LR2_ACC(0)
             mbar_expect_tx(&w_full[ws], kStageBytes);
             tma_load_2d(smem_u32(Ws + (size_t)ws * kStageBytes), &tm_w1, &w_full[ws], kb * kBK, j * 128);
             if (++ws == p.wstages) { ws = 0; wph ^= 1; }
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         for (int c = 0; c < p.nchunks; ++c)
           for (int kb = 0; kb < p.nkv; ++kb) {
-            mbar_wait(&w_empty[ws], wph ^ 1);
+            LR2_T0() mbar_wait(&w_empty[ws], wph ^ 1); LR2_ACC(1)
             mbar_expect_tx(&w_full[ws], (uint32_t)p.bn2 * 128u);
             tma_load_2d(smem_u32(Ws + (size_t)ws * kStageBytes), &tm_w2, &w_full[ws], kb * kBK, c * p.bn2);
             if (++ws == p.wstages) { ws = 0; wph ^= 1; }
@@ -232,10 +241,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         // ---- GEMM 1 ----
         for (int kb = 0; kb < p.nk1; ++kb) {
-          mbar_wait(&x_full[xs], xph);
+          LR2_T0() mbar_wait(&x_full[xs], xph); LR2_ACC(2)
           const uint64_t da = umma_desc_sw128(smem_u32(Xs + (size_t)xs * kStageBytes));
           for (int j = 0; j < p.nb1; ++j) {
-            mbar_wait(&w_full[ws], wph);
+            LR2_T0() mbar_wait(&w_full[ws], wph); LR2_ACC(3)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t db = umma_desc_sw128(smem_u32(Ws + (size_t)ws * kStageBytes));
             const int nj = (p.n1p16 - j * 128) < 128 ? (p.n1p16 - j * 128) : 128;
@@ -254,12 +263,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ---- GEMM 2 ----
         for (int c = 0; c < p.nchunks; ++c, ++g) {
           const uint32_t buf = g & 1;
-          mbar_wait(&acc2_empty[buf], ((g >> 1) & 1) ^ 1);
+          LR2_T0() mbar_wait(&acc2_empty[buf], ((g >> 1) & 1) ^ 1); LR2_ACC(4)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d_tmem = tmem_base + (uint32_t)(p.acc2_col + (int)buf * p.bn2);
           for (int kb = 0; kb < p.nkv; ++kb) {
-            if (c == 0) mbar_wait(&v_ready[kb], it & 1);
-            mbar_wait(&w_full[ws], wph);
+            LR2_T0() if (c == 0) mbar_wait(&v_ready[kb], it & 1); LR2_ACC(5)
+            mbar_wait(&w_full[ws], wph); LR2_ACC(6)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t da = umma_desc_sw128(smem_u32(Vs + (size_t)kb * kStageBytes));
             const uint64_t db = umma_desc_sw128(smem_u32(Ws + (size_t)ws * kStageBytes));
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int64_t tile0 = (int64_t)tile * kBM;
       // ---- acc1 -> bf16 -> V ----
-      mbar_wait(&acc1_full, it & 1);
+      LR2_T0() mbar_wait(&acc1_full, it & 1); LR2_ACC(0)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int c0 = 0; c0 < p.nkv * 64; c0 += 32) {
@@ -316,10 +325,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_arrive(&v_ready[c0 >> 6]);
         }
       }
+      LR2_ACC(1)
       // ---- acc2 chunks -> y ----
       for (int c = 0; c < p.nchunks; ++c, ++g) {
         const uint32_t buf = g & 1;
-        mbar_wait(&acc2_full[buf], (g >> 1) & 1);
+        LR2_T0() mbar_wait(&acc2_full[buf], (g >> 1) & 1); LR2_ACC(2)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int c0 = 0; c0 < p.bn2; c0 += 32) {
@@ -379,12 +389,19 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           ++nst;
         }
+        LR2_ACC(3)
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores done before the CTA retires
     __syncwarp();
   }
 
+  if constexpr (PROF) {
+    if (profiling && lane == 0 && warp <= 2)
+      for (int i = 0; i < 8; ++i) prof[warp * 8 + i] = (unsigned long long)pc[i];
+  }
+#undef LR2_T0
+#undef LR2_ACC
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -502,13 +519,37 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
 
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    rc = check_cuda(cudaFuncSetAttribute(lowrank2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    rc = check_cuda(cudaFuncSetAttribute(lowrank2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "lowrank2_fwd smem attribute");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(lowrank2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                     "lowrank2_fwd smem attribute");
     if (rc) return rc;
     smem_set = smem;
   }
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-  lowrank2_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_w1, tm_w2, tm_y, bias, p);
+  static unsigned long long* prof = nullptr;
+  static bool prof_init = false;
+  if (!prof_init) {
+    prof_init = true;
+    const char* e = getenv("TTA_LR2_PROF");
+    if (e && e[0] == '1' && cudaMalloc(&prof, 24 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(prof, 0, 24 * sizeof(unsigned long long));
+  }
+  if (prof) {
+    unsigned long long h[24];
+    cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+    if (h[8] | h[16])
+      fprintf(stderr,
+              "[lr2 prof, CTA 0, cycles] producer: wait w_empty g1 %llu g2 %llu | mma: wait x_full %llu w_full(g1) %llu acc2_empty %llu "
+              "v_ready %llu w_full(g2) %llu | epilogue warp: wait acc1 %llu convert V %llu wait acc2 %llu store y %llu\n",
+              h[0], h[1], h[10], h[11], h[12], h[13], h[14], h[16], h[17], h[18], h[19]);
+    cudaMemset(prof, 0, sizeof(h));
+  }
+  if (prof)
+    lowrank2_fwd_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_w1, tm_w2, tm_y, bias, p, prof);
+  else
+    lowrank2_fwd_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_w1, tm_w2, tm_y, bias, p, nullptr);
   TTA_CHECK_LAUNCH("lowrank2_fwd launch");
   return TTA_OK;
 }
