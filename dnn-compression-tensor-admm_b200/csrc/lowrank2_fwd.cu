@@ -9,9 +9,9 @@
 // Also TKLinearM (TKLinear.py:60-75: first factor, core, last factor with the core folded into one side).
 //
 // CTA = 128 rows of x, persistent over row tiles (grid = min(tiles, 148)).  Warp roles (192 threads):
-//   warp 0     TMA producer (one lane): x k-blocks into a 2-stage ring, W1 / W2 blocks (<= 128 rows x
+//   warp 0     TMA producer (one elected lane): x k-blocks into a 2-stage ring, W1 / W2 blocks (<= 128 rows x
 //              64 k, SWIZZLE_128B) into a ring of 16 KB stages; mbarrier expect_tx / complete_tx.
-//   warp 1     TMEM allocator (512 columns) + single-lane tcgen05.mma issuer.
+//   warp 1     TMEM allocator (512 columns) + tcgen05.mma issuer (one elected lane).
 //              GEMM 1: acc1[128 x N1] (TMEM columns 0..)  += x-block * W1-block^T
 //              GEMM 2: acc2[buf][128 x BN2]               = V * W2-chunk^T, V = bf16(acc1) in shared memory
 //   warps 2-5  epilogue (one TMEM lane quadrant each): acc1 -> bf16 -> V (UMMA K-major SWIZZLE_128B layout,
@@ -40,16 +40,17 @@ constexpr int kMaxN1 = 384;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// barriers are addressed by their 32-bit shared-window address
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -58,12 +59,12 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // A mis-sequenced pipeline must not hang the device: a wait that lasts longer than ~2 s traps.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t n = 0;
@@ -72,10 +73,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -102,9 +103,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
   asm volatile(
@@ -142,8 +142,34 @@ struct Params {
   int wstages;
   int ntiles;
   int out_f32;
+  int bias_vec;   // bias is 16-byte aligned: 128-bit loads
   int64_t ldy;
 };
+
+// Barrier slots (8 bytes each) inside one shared array; all barrier / buffer addresses are formed once as 32-bit
+// shared-window addresses (taking the address of a __shared__ variable inside the loops costs an S2UR + shifts
+// every time).
+constexpr int kBarXFull = 0;
+constexpr int kBarXEmpty = kBarXFull + kXStages;
+constexpr int kBarWFull = kBarXEmpty + kXStages;
+constexpr int kBarWEmpty = kBarWFull + kMaxWStages;
+constexpr int kBarAcc1Full = kBarWEmpty + kMaxWStages;
+constexpr int kBarVReady = kBarAcc1Full + 1;
+constexpr int kBarAcc2Full = kBarVReady + kMaxN1 / 64;
+constexpr int kBarAcc2Empty = kBarAcc2Full + 2;
+constexpr int kNumBars = kBarAcc2Empty + 2;
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -152,33 +178,32 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const float* __restrict__ bias, const Params p,
                         unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Vs = smem;                                   // nkv x 16 KB
-  uint8_t* Xs = Vs + (size_t)p.nkv * kStageBytes;       // kXStages x 16 KB
-  uint8_t* Ws = Xs + (size_t)kXStages * kStageBytes;    // wstages x 16 KB
-  __shared__ uint64_t x_full[kXStages], x_empty[kXStages];
-  __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
-  __shared__ uint64_t acc1_full;
-  __shared__ uint64_t v_ready[kMaxN1 / 64];   // one per 64-column block of V: GEMM 2 starts on block 0 while the rest converts
-  __shared__ uint64_t acc2_full[2], acc2_empty[2];
+  __shared__ __align__(8) uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_smem;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t Vs = smem0;                                         // nkv x 16 KB
+  const uint32_t Xs = Vs + (uint32_t)p.nkv * kStageBytes;            // kXStages x 16 KB
+  const uint32_t Ws = Xs + (uint32_t)kXStages * kStageBytes;         // wstages x 16 KB
+  const uint32_t St = Ws + (uint32_t)p.wstages * kStageBytes;        // 4 warps x 2 x 4 KB output staging
+  const uint32_t bar0 = smem_u32(bars);
+#define BAR(i) (bar0 + 8u * (uint32_t)(i))
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < kXStages; ++s) {
-      mbar_init(&x_full[s], 1);
-      mbar_init(&x_empty[s], 1);
+      mbar_init(BAR(kBarXFull + s), 1);
+      mbar_init(BAR(kBarXEmpty + s), 1);
     }
     for (int s = 0; s < kMaxWStages; ++s) {
-      mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
+      mbar_init(BAR(kBarWFull + s), 1);
+      mbar_init(BAR(kBarWEmpty + s), 1);
     }
-    mbar_init(&acc1_full, 1);
-    for (int b = 0; b < kMaxN1 / 64; ++b) mbar_init(&v_ready[b], 128);
+    mbar_init(BAR(kBarAcc1Full), 1);
+    for (int b = 0; b < kMaxN1 / 64; ++b) mbar_init(BAR(kBarVReady + b), 128);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc2_full[b], 1);
-      mbar_init(&acc2_empty[b], 128);
+      mbar_init(BAR(kBarAcc2Full + b), 1);
+      mbar_init(BAR(kBarAcc2Empty + b), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -199,101 +224,141 @@ __global__ void __launch_bounds__(kThreads, 1)
 #define LR2_T0() if constexpr (PROF) { if (profiling) tp = clock64(); }
 #define LR2_ACC(i) if constexpr (PROF) { if (profiling) { const long long t1_ = clock64(); pc[i] += t1_ - tp; tp = t1_; } }
 
+  // The producer and the MMA issuer run their loops with the whole warp (barrier waits are warp-wide polls) and
+  // issue through ONE elected lane: code under `elect.sync` stays on the uniform datapath, whereas a role
+  // wrapped in `if (lane == 0)` makes the compiler serialise every TMA / UMMA instruction in an election loop.
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    const bool leader = elect_one();
+    if (leader) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w1)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w2)) : "memory");
-      int xs = 0, ws = 0;
-      uint32_t xph = 0, wph = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int m0 = tile * kBM;
-        for (int kb = 0; kb < p.nk1; ++kb) {
-          mbar_wait(&x_empty[xs], xph ^ 1);
-          mbar_expect_tx(&x_full[xs], kStageBytes);
-          tma_load_2d(smem_u32(Xs + (size_t)xs * kStageBytes), &tm_x, &x_full[xs], kb * kBK, m0);
-          if (++xs == kXStages) { xs = 0; xph ^= 1; }
-          for (int j = 0; j < p.nb1; ++j) {
-            LR2_T0() mbar_wait(&w_empty[ws], wph ^ 1); LR2_ACC(0)
-            mbar_expect_tx(&w_full[ws], kStageBytes);
-            tma_load_2d(smem_u32(Ws + (size_t)ws * kStageBytes), &tm_w1, &w_full[ws], kb * kBK, j * 128);
-            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
-          }
+    }
+    int xs = 0, ws = 0;
+    uint32_t xph = 0, wph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int m0 = tile * kBM;
+      for (int kb = 0; kb < p.nk1; ++kb) {
+        mbar_wait(BAR(kBarXEmpty + xs), xph ^ 1);
+        if (leader) {
+          mbar_expect_tx(BAR(kBarXFull + xs), kStageBytes);
+          tma_load_2d(Xs + (uint32_t)xs * kStageBytes, &tm_x, BAR(kBarXFull + xs), kb * kBK, m0);
         }
-        for (int c = 0; c < p.nchunks; ++c)
-          for (int kb = 0; kb < p.nkv; ++kb) {
-            LR2_T0() mbar_wait(&w_empty[ws], wph ^ 1); LR2_ACC(1)
-            mbar_expect_tx(&w_full[ws], (uint32_t)p.bn2 * 128u);
-            tma_load_2d(smem_u32(Ws + (size_t)ws * kStageBytes), &tm_w2, &w_full[ws], kb * kBK, c * p.bn2);
-            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+        if (++xs == kXStages) { xs = 0; xph ^= 1; }
+        for (int j = 0; j < p.nb1; ++j) {
+          LR2_T0() mbar_wait(BAR(kBarWEmpty + ws), wph ^ 1); LR2_ACC(0)
+          if (leader) {
+            mbar_expect_tx(BAR(kBarWFull + ws), kStageBytes);
+            tma_load_2d(Ws + (uint32_t)ws * kStageBytes, &tm_w1, BAR(kBarWFull + ws), kb * kBK, j * 128);
           }
+          if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+        }
       }
+      for (int c = 0; c < p.nchunks; ++c)
+        for (int kb = 0; kb < p.nkv; ++kb) {
+          LR2_T0() mbar_wait(BAR(kBarWEmpty + ws), wph ^ 1); LR2_ACC(1)
+          if (leader) {
+            mbar_expect_tx(BAR(kBarWFull + ws), (uint32_t)p.bn2 * 128u);
+            tma_load_2d(Ws + (uint32_t)ws * kStageBytes, &tm_w2, BAR(kBarWFull + ws), kb * kBK, c * p.bn2);
+          }
+          if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+        }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      int xs = 0, ws = 0;
-      uint32_t xph = 0, wph = 0;
-      uint32_t it = 0, g = 0;   // row tiles / GEMM-2 chunks processed by this CTA
-      const uint32_t idesc2 = umma_idesc_bf16(p.bn2);
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        // ---- GEMM 1 ----
-        for (int kb = 0; kb < p.nk1; ++kb) {
-          LR2_T0() mbar_wait(&x_full[xs], xph); LR2_ACC(2)
-          const uint64_t da = umma_desc_sw128(smem_u32(Xs + (size_t)xs * kStageBytes));
-          for (int j = 0; j < p.nb1; ++j) {
-            LR2_T0() mbar_wait(&w_full[ws], wph); LR2_ACC(3)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t db = umma_desc_sw128(smem_u32(Ws + (size_t)ws * kStageBytes));
+    const bool leader = elect_one();
+    int xs = 0, ws = 0;
+    uint32_t xph = 0, wph = 0;
+    uint32_t it = 0, g = 0;   // row tiles / GEMM-2 chunks processed by this CTA
+    const uint32_t idesc2 = umma_idesc_bf16(p.bn2);
+    const uint64_t descX = umma_desc_sw128(Xs), descW = umma_desc_sw128(Ws), descV = umma_desc_sw128(Vs);
+    constexpr uint64_t kStageDesc = kStageBytes >> 4;    // descriptor address units are 16 bytes
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      // ---- GEMM 1 ----
+      for (int kb = 0; kb < p.nk1; ++kb) {
+        LR2_T0() mbar_wait(BAR(kBarXFull + xs), xph); LR2_ACC(2)
+        const uint64_t da = descX + (uint64_t)xs * kStageDesc;
+        for (int j = 0; j < p.nb1; ++j) {
+          LR2_T0() mbar_wait(BAR(kBarWFull + ws), wph); LR2_ACC(3)
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (leader) {
+            const uint64_t db = descW + (uint64_t)ws * kStageDesc;
             const int nj = (p.n1p16 - j * 128) < 128 ? (p.n1p16 - j * 128) : 128;
             const uint32_t idesc1 = umma_idesc_bf16(nj);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
               umma_bf16(tmem_base + (uint32_t)(j * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1,
                         (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&w_empty[ws]);
-            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+            umma_commit(BAR(kBarWEmpty + ws));
           }
-          umma_commit(&x_empty[xs]);
-          if (++xs == kXStages) { xs = 0; xph ^= 1; }
+          __syncwarp();
+          if (++ws == p.wstages) { ws = 0; wph ^= 1; }
         }
-        umma_commit(&acc1_full);
-        // ---- GEMM 2 ----
-        for (int c = 0; c < p.nchunks; ++c, ++g) {
-          const uint32_t buf = g & 1;
-          LR2_T0() mbar_wait(&acc2_empty[buf], ((g >> 1) & 1) ^ 1); LR2_ACC(4)
+        if (leader) umma_commit(BAR(kBarXEmpty + xs));
+        __syncwarp();
+        if (++xs == kXStages) { xs = 0; xph ^= 1; }
+      }
+      if (leader) umma_commit(BAR(kBarAcc1Full));
+      __syncwarp();
+      // ---- GEMM 2 ----
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t buf = g & 1;
+        LR2_T0() mbar_wait(BAR(kBarAcc2Empty + buf), ((g >> 1) & 1) ^ 1); LR2_ACC(4)
+        const uint32_t d_tmem = tmem_base + (uint32_t)(p.acc2_col + (int)buf * p.bn2);
+        for (int kb = 0; kb < p.nkv; ++kb) {
+          LR2_T0() if (c == 0) mbar_wait(BAR(kBarVReady + kb), it & 1); LR2_ACC(5)
+          mbar_wait(BAR(kBarWFull + ws), wph); LR2_ACC(6)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d_tmem = tmem_base + (uint32_t)(p.acc2_col + (int)buf * p.bn2);
-          for (int kb = 0; kb < p.nkv; ++kb) {
-            LR2_T0() if (c == 0) mbar_wait(&v_ready[kb], it & 1); LR2_ACC(5)
-            mbar_wait(&w_full[ws], wph); LR2_ACC(6)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t da = umma_desc_sw128(smem_u32(Vs + (size_t)kb * kStageBytes));
-            const uint64_t db = umma_desc_sw128(smem_u32(Ws + (size_t)ws * kStageBytes));
+          if (leader) {
+            const uint64_t da = descV + (uint64_t)kb * kStageDesc;
+            const uint64_t db = descW + (uint64_t)ws * kStageDesc;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
               umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&w_empty[ws]);
-            if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+            umma_commit(BAR(kBarWEmpty + ws));
           }
-          umma_commit(&acc2_full[buf]);
+          __syncwarp();
+          if (++ws == p.wstages) { ws = 0; wph ^= 1; }
         }
+        if (leader) umma_commit(BAR(kBarAcc2Full + buf));
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------ epilogue warps ------------------------------
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;           // row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stage = smem_u32(Ws) + (uint32_t)p.wstages * kStageBytes + (uint32_t)q * 8192;   // 2 x (32 rows x 128 B) per warp
+    const uint32_t stage = St + (uint32_t)q * 8192;   // 2 x (32 rows x 128 B) per warp
     uint32_t it = 0, g = 0, nst = 0;
+    // Bias of a block's 32 columns: eight 128-bit loads (every lane reads the same addresses: one broadcast
+    // transaction each) on the aligned interior, predicated scalars on a ragged edge.  With 224 KB of the SM's
+    // memory carved out as shared memory the loads are served by L2 (~600 cycles), so the bias of block i + 1
+    // is requested while block i is processed.
+    auto load_bias = [&](int gn0, float (&dst)[32]) {
+      if (bias == nullptr || gn0 >= p.N2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = 0.f;
+      } else if (gn0 + 32 <= p.N2 && p.bias_vec) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + gn0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(b4 + j);
+          dst[4 * j] = t.x; dst[4 * j + 1] = t.y; dst[4 * j + 2] = t.z; dst[4 * j + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = (gn0 + j < p.N2) ? __ldg(bias + gn0 + j) : 0.f;
+      }
+    };
+    float bnext[32];
+    load_bias(0, bnext);
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int64_t tile0 = (int64_t)tile * kBM;
+      const int tile0 = tile * kBM;
       // ---- acc1 -> bf16 -> V ----
-      LR2_T0() mbar_wait(&acc1_full, it & 1); LR2_ACC(0)
+      LR2_T0() mbar_wait(BAR(kBarAcc1Full), it & 1); LR2_ACC(0)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int c0 = 0; c0 < p.nkv * 64; c0 += 32) {
@@ -304,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        const uint32_t vrow = smem_u32(Vs) + (uint32_t)(c0 >> 6) * kStageBytes + row * 128;
+        const uint32_t vrow = Vs + (uint32_t)(c0 >> 6) * kStageBytes + row * 128;
         const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -322,46 +387,48 @@ __global__ void __launch_bounds__(kThreads, 1)
         if ((c0 & 63) == 32) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of V -> async proxy (UMMA)
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&v_ready[c0 >> 6]);
+          mbar_arrive(BAR(kBarVReady + (c0 >> 6)));
         }
       }
       LR2_ACC(1)
       // ---- acc2 chunks -> y ----
       for (int c = 0; c < p.nchunks; ++c, ++g) {
         const uint32_t buf = g & 1;
-        LR2_T0() mbar_wait(&acc2_full[buf], (g >> 1) & 1); LR2_ACC(2)
+        LR2_T0() mbar_wait(BAR(kBarAcc2Full + buf), (g >> 1) & 1); LR2_ACC(2)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int c0 = 0; c0 < p.bn2; c0 += 32) {
           uint32_t v[32];
+          LR2_T0()
           tmem_ld32(lane_addr + (uint32_t)(p.acc2_col + (int)buf * p.bn2 + c0), v);
+          LR2_ACC(4)
           if (c0 + 32 >= p.bn2) {
             // the last block of this accumulator is in registers: hand the buffer back to the MMA issuer
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc2_empty[buf]);
+            mbar_arrive(BAR(kBarAcc2Empty + buf));
           }
           const int gn0 = c * p.bn2 + c0;
+          float bv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bv[j] = bnext[j];
+          load_bias(c0 + 32 < p.bn2 ? gn0 + 32 : (c + 1 < p.nchunks ? (c + 1) * p.bn2 : 0), bnext);
           if (gn0 >= p.N2) continue;                                   // warp-uniform
           // The accumulator arrives one row per lane; a row-per-lane store would touch 32 lines per
           // instruction.  The 32 x 32 block goes (bias added, converted) into this warp's staging buffer in
           // the SWIZZLE_128B (fp32) / SWIZZLE_64B (bf16) pattern of the output tensor map, and one lane hands
-          // it to the TMA store engine, which writes whole lines and clips rows >= M / columns >= N2 (16-byte granules).
-          // Two staging buffers per warp: the store of block i drains while block i + 1 is staged.
+          // it to the TMA store engine, which writes whole lines and clips rows >= M / columns >= N2 (16-byte
+          // granules).  Two staging buffers per warp: the store of block i drains while block i + 1 is staged.
           const uint32_t sbuf = stage + (nst & 1) * 4096;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer of block i - 2 is free
           __syncwarp();
+          LR2_ACC(5)
           if (p.out_f32) {
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int cix = gn0 + 4 * ch + e;
-                o[e] = __uint_as_float(v[4 * ch + e]) + ((bias && cix < p.N2) ? __ldg(bias + cix) : 0.f);
-              }
-              sts128(sbuf + lane * 128 + ((ch ^ (lane & 7)) << 4), __float_as_uint(o[0]), __float_as_uint(o[1]),
-                     __float_as_uint(o[2]), __float_as_uint(o[3]));
-            }
+            for (int ch = 0; ch < 8; ++ch)
+              sts128(sbuf + lane * 128 + ((ch ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(v[4 * ch]) + bv[4 * ch]),
+                     __float_as_uint(__uint_as_float(v[4 * ch + 1]) + bv[4 * ch + 1]),
+                     __float_as_uint(__uint_as_float(v[4 * ch + 2]) + bv[4 * ch + 2]),
+                     __float_as_uint(__uint_as_float(v[4 * ch + 3]) + bv[4 * ch + 3]));
           } else {
             const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -369,25 +436,25 @@ __global__ void __launch_bounds__(kThreads, 1)
               uint32_t pk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int cix = gn0 + 8 * ch + 2 * e;
-                const float lo = __uint_as_float(v[8 * ch + 2 * e]) + ((bias && cix < p.N2) ? __ldg(bias + cix) : 0.f);
-                const float hi = __uint_as_float(v[8 * ch + 2 * e + 1]) + ((bias && cix + 1 < p.N2) ? __ldg(bias + cix + 1) : 0.f);
-                __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[8 * ch + 2 * e]) + bv[8 * ch + 2 * e],
+                                                         __uint_as_float(v[8 * ch + 2 * e + 1]) + bv[8 * ch + 2 * e + 1]);
                 pk[e] = *reinterpret_cast<uint32_t*>(&h);
               }
               sts128(sbuf + lane * 64 + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
             }
           }
+          LR2_ACC(6)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged block -> async proxy (TMA)
           __syncwarp();
           if (lane == 0) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(&tm_y)),
-                         "r"(sbuf), "r"(gn0), "r"((int)(tile0 + q * 32))
+                         "r"(sbuf), "r"(gn0), "r"(tile0 + q * 32)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++nst;
+          LR2_ACC(7)
         }
         LR2_ACC(3)
       }
@@ -402,6 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 #undef LR2_T0
 #undef LR2_ACC
+#undef BAR
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -490,6 +558,7 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
   p.nchunks = (N2 + bn2 - 1) / bn2;
   p.ntiles = (int)((M + kBM - 1) / kBM);
   p.out_f32 = out_fp32 ? 1 : 0;
+  p.bias_vec = (bias && ((uintptr_t)bias & 15) == 0) ? 1 : 0;
   p.ldy = ldy;
   const size_t budget = 227 * 1024 - 1024 - 512;   // dynamic shared memory minus alignment slack and the barriers
   const size_t fixed = (size_t)(p.nkv + kXStages + 2) * kStageBytes;   // V, x ring, output staging (8 x 4 KB)
@@ -542,8 +611,9 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
     if (h[8] | h[16])
       fprintf(stderr,
               "[lr2 prof, CTA 0, cycles] producer: wait w_empty g1 %llu g2 %llu | mma: wait x_full %llu w_full(g1) %llu acc2_empty %llu "
-              "v_ready %llu w_full(g2) %llu | epilogue warp: wait acc1 %llu convert V %llu wait acc2 %llu store y %llu\n",
-              h[0], h[1], h[10], h[11], h[12], h[13], h[14], h[16], h[17], h[18], h[19]);
+              "v_ready %llu w_full(g2) %llu | epilogue warp: wait acc1 %llu convert V %llu wait acc2 %llu store y (rest) %llu "
+              "[tmem ld %llu, wait staging %llu, bias+convert+sts %llu, fence+tma %llu]\n",
+              h[0], h[1], h[10], h[11], h[12], h[13], h[14], h[16], h[17], h[18], h[19], h[20], h[21], h[22], h[23]);
     cudaMemset(prof, 0, sizeof(h));
   }
   if (prof)
