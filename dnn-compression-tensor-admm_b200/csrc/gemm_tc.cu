@@ -196,13 +196,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kTcStages;
-        mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes);
+    // The whole warp runs the loop (barrier waits are warp-wide polls) and ONE elected lane issues: code under
+    // `elect.sync` stays on the uniform datapath, whereas `if (lane == 0)` makes the compiler wrap every
+    // UMMA / commit in an election loop.
+    uint32_t leader;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(leader));
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), accum_addr = smem_u32(&accum_bar);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kTcStages;
+      mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (leader) {
+        const uint32_t sa = smem_base + (uint32_t)s * kStageBytes;
         const uint32_t sb = sa + kABytes;
         const uint64_t da = umma_desc_sw128(sa);
         const uint64_t db = umma_desc_sw128(sb);
@@ -220,15 +233,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               : "memory");
         }
         // frees the ring slot once the MMAs above have consumed it (implies fence::before_thread_sync)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(&empty_bar[s]))
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8u * s)
                      : "memory");
+        if (kb == nkb - 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accum_addr)
+                       : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(&accum_bar))
-                   : "memory");
+      __syncwarp();
     }
-    __syncwarp();
+    (void)full0;
   }
 
   __syncthreads();
