@@ -1,7 +1,8 @@
 """Drop-in replacement for the reference's `TKLinear.py` (`TKLinearM`, `TKLinearR`; TKLinear.py:23-122):
 same constructor, parameters `first_factor (r_in, in)`, `core_tensor (r_out, r_in)`,
-`last_factor (out, r_out)`, `bias`.  Inference forward = three tcgen05 GEMMs in bf16 (M) or one GEMM with
-the rebuilt weight (R); autograd forward = the torch op chain."""
+`last_factor (out, r_out)`, `bias`.  Inference forward (M) = one fused two-factor tcgen05 kernel (the core is
+folded into the smaller side; three separate GEMMs when the inner rank exceeds its TMEM budget), (R) = one GEMM
+with the rebuilt weight; autograd forward = the torch op chain."""
 from __future__ import annotations
 
 import math
@@ -41,6 +42,7 @@ class _TKLinearBase(Module):
         else:
             self.reset_parameters()
         self._engine = None
+        self._fused = None
 
     def reset_parameters(self):
         init.kaiming_uniform_(self.first_factor, a=math.sqrt(5))
@@ -64,6 +66,24 @@ class TKLinearM(_TKLinearBase):
             out = F.linear(out, self.core_tensor)
             return F.linear(out, self.last_factor, self.bias)
         rt.require_device(x)
+        # Two-factor form: the core folds into the smaller side (weights only, cached), then ONE fused tcgen05
+        # kernel runs in -> r -> out with the rank-r intermediate on the SM (`tta_lowrank2_fwd`).
+        r_mid = min(self.in_rank, self.out_rank)
+        if r_mid <= fc.LOWRANK2_MAX_INNER:
+            if self._fused is None:
+                if self.in_rank <= self.out_rank:      # (last core) (first): inner width r_in
+                    w1 = fc.PackedWeight(lambda: self.first_factor, [self.first_factor])
+                    w2 = fc.PackedWeight(lambda: self.last_factor @ self.core_tensor, [self.last_factor, self.core_tensor])
+                else:                                  # (last) (core first): inner width r_out
+                    w1 = fc.PackedWeight(lambda: self.core_tensor @ self.first_factor, [self.core_tensor, self.first_factor])
+                    w2 = fc.PackedWeight(lambda: self.last_factor, [self.last_factor])
+                self._fused = (fc.Workspace(), w1, w2)
+            ws, w1, w2 = self._fused
+            with torch.no_grad():
+                out_shape = list(x.shape)
+                out_shape[-1] = self.out_features
+                y = fc.lowrank2_apply(ws, x.reshape(-1, self.in_features), w1.get(), w2.get(), self.bias)
+            return y.reshape(out_shape)
         if self._engine is None:
             self._engine = (fc.Workspace(), fc.PackedWeight(lambda: self.first_factor, [self.first_factor]),
                             fc.PackedWeight(lambda: self.core_tensor, [self.core_tensor]),

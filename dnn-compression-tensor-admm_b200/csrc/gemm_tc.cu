@@ -12,10 +12,17 @@
 //              slots / publishes the accumulator through mbarriers.
 // Accumulator: 128 lanes x BN fp32 columns of TMEM.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "tta_common.cuh"
 
 namespace tta {
+
+// gemm_tma.cu
+bool gemm_tma_eligible(const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc, int M, int N,
+                       int K, int out_fp32);
+int gemm_tma_launch(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int M, int N, int K,
+                    const float* bias, int out_fp32, cudaStream_t st);
 
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 64;        // 64 bf16 = one 128-byte swizzle row
@@ -277,6 +284,15 @@ extern "C" int tta_gemm_bf16_tc(const void* a, int64_t lda, const void* b, int64
     return TTA_E_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // TMA-fed persistent kernel (gemm_tma.cu) whenever the operands meet TMA's alignment rules; TTA_GEMM_TMA=0
+  // keeps the cp.async kernel below (comparison / debugging)
+  static int use_tma = -1;
+  if (use_tma < 0) {
+    const char* e = getenv("TTA_GEMM_TMA");
+    use_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_tma && gemm_tma_eligible(a, lda, b, ldb, c, ldc, M, N, K, out_fp32))
+    return gemm_tma_launch(a, lda, b, ldb, c, ldc, M, N, K, bias, out_fp32, st);
   // tile width: 64 when it wastes fewer padded columns than 128
   const int waste128 = ((N + 127) / 128) * 128 - N;
   const int waste64 = ((N + 63) / 64) * 64 - N;

@@ -18,7 +18,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 64, 64), (256, 128, 128), (300, 320, 368), (1000, 1120, 320),
-                                   (128, 800, 256), (77, 23, 24), (4096, 352, 1344), (130, 129, 72)])
+                                   (128, 800, 256), (77, 23, 24), (4096, 352, 1344), (130, 129, 72),
+                                   (20000, 1120, 320), (5000, 384, 1536), (300, 264, 40)])
 @pytest.mark.parametrize('out_f32', [False, True])
 def test_tcgen05_gemm_matches_torch(M, N, K, out_f32):
     g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + K)
