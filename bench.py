@@ -448,6 +448,26 @@ def forward_bench(dev, peaks):
 
     ms_f, ms_c = _time_cuda(lin_fused, iters=3, warm=1), _time_cuda(lin_chain, iters=3, warm=1)
     ms_fb = _time_cuda(lin_fused_bf16, iters=3, warm=1)
+    # training step of the same layers (forward + backward with a random upstream gradient): fused path
+    # (fwd_common.LowRank2Fn: forward and dX on the two-factor kernel) vs the torch op chain
+    gys = {}
+
+    def lin_train(fused):
+        for layer, x in lin:
+            layer.fused_training = fused
+            xg = x.detach().requires_grad_(True)
+            y = layer(xg)
+            gy = gys.get(y.shape[1])
+            if gy is None:
+                gy = gys[y.shape[1]] = torch.randn_like(y)
+            y.backward(gy)
+        for layer, _ in lin:
+            layer.zero_grad(set_to_none=True)
+            layer.fused_training = False
+
+    ms_tf = _time_cuda(lambda: lin_train(True), iters=2, warm=1)
+    ms_tc = _time_cuda(lambda: lin_train(False), iters=2, warm=1)
+    gys.clear()
     macs = 0
     macs_exec = 0
     n_dense = 0
@@ -463,6 +483,7 @@ def forward_bench(dev, peaks):
                                          'torch_op_chain_img_s': 256 / (ms_c / 1e3), 'torch_op_chain_ms': ms_c,
                                          'fused_bf16_activations_ms': ms_fb,
                                          'fused_bf16_activations_img_s': 256 / (ms_fb / 1e3),
+                                         'train_step_fused_ms': ms_tf, 'train_step_torch_op_chain_ms': ms_tc,
                                          'two_factor_fused_layers': sum(bool(getattr(l, '_fused2', False)) for l, _ in lin),
                                          'contraction_order': '{} of {} layers fold the cores into the dense weight first '
                                                               '(fewer or comparable MACs than the chain)'.format(n_dense, len(lin)),

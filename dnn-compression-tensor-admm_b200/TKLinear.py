@@ -60,7 +60,22 @@ class _TKLinearBase(Module):
 
 
 class TKLinearM(_TKLinearBase):
+    fused_training = False     # additive: route the autograd path through the fused kernels (bf16 operands)
+
     def forward(self, x):
+        if (fc.needs_autograd(x, self._params()) and (self.fused_training or torch.is_autocast_enabled()) and x.is_cuda and
+                fc.lowrank2_trainable(self.in_features, self.out_features, min(self.in_rank, self.out_rank))):
+            # fused training path: forward and dX on the two-factor tcgen05 kernel, factor
+            # gradients by the chain rule through the folded core (TKLinear.py:60-75)
+            with torch.autocast('cuda', enabled=False):
+                if self.in_rank <= self.out_rank:
+                    w1, w2 = self.first_factor.float(), self.last_factor.float() @ self.core_tensor.float()
+                else:
+                    w1, w2 = self.core_tensor.float() @ self.first_factor.float(), self.last_factor.float()
+                out_shape = list(x.shape)
+                out_shape[-1] = self.out_features
+                y = fc.LowRank2Fn.apply(x.reshape(-1, self.in_features), w1, w2, self.bias)
+            return y.reshape(out_shape)
         if fc.needs_autograd(x, self._params()) or self.in_features % 8:
             out = F.linear(x, self.first_factor)
             out = F.linear(out, self.core_tensor)

@@ -51,6 +51,7 @@ class _TTLinearBase(Module):
         self._dense_engine = None
         self._dense_first = None
         self._fused2 = None
+        self.fused_training = False     # additive: route the autograd path through the fused kernels (bf16 operands)
 
     def get_ranks(self):
         return ', '.join(str(r) for r in self.tt_ranks)
@@ -79,6 +80,16 @@ class TTLinearM(_TTLinearBase):
         out_cores = list(self.tt_cores)[:self.out_tt_order]
         x2d = x.reshape(-1, self.in_features)
         if fc.needs_autograd(x, params):
+            # Fused training path (forward and dX on the two-factor tcgen05 kernel, bf16 operands): taken under
+            # autocast -- the reference trains under torch.cuda.amp.autocast (engines.py:285) -- or when
+            # `fused_training` is set; otherwise the fp32 torch op chain below.
+            if ((self.fused_training or torch.is_autocast_enabled()) and x.is_cuda and
+                    fc.lowrank2_trainable(self.in_features, self.out_features, int(self.tt_ranks[self.out_tt_order]))):
+                with torch.autocast('cuda', enabled=False):
+                    w1 = fc.fold_in_cores([c.float() for c in in_cores])
+                    w2 = fc.fold_out_cores([c.float() for c in out_cores])
+                    y = fc.LowRank2Fn.apply(x2d, w1, w2, self.bias)
+                return y.reshape(out_shape)
             y = fc.tt_apply_torch(x2d, in_cores, out_cores)
             if self.bias is not None:
                 y = y + self.bias

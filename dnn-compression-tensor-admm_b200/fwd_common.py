@@ -294,6 +294,78 @@ def lowrank2_apply(ws, x2d, w1, w2, bias):
     return y if ldy == N2 else y[:, :N2]
 
 
+def _pack_bf16(w):
+    """(N x K) matrix -> bf16 with row stride pad8(K), zero padded (TMA wants 16-byte row pitches)."""
+    n, k = w.shape
+    ld = pad8(k)
+    if ld == k:
+        return w.detach().to(torch.bfloat16).contiguous(), ld
+    m = torch.zeros(n, ld, dtype=torch.bfloat16, device=w.device)
+    m[:, :k] = w.detach().to(torch.bfloat16)
+    return m, ld
+
+
+class LowRank2Fn(torch.autograd.Function):
+    """Training path of the two-factor layers (backward of the fused forwards):
+    y = (x W1^T) W2^T + bias with the forward AND the input gradient on the fused TMA + tcgen05 kernel.
+
+        dX  = (dY W2) W1         -- `tta_lowrank2_fwd` again, factors W2^T (N1 x N2) and W1^T (K1 x N1)
+        dW2 = dY^T V,  V = x W1^T (recomputed by `tta_gemm_bf16_tc`, not stored)
+        dW1 = dV^T x,  dV = dY W2 (`tta_gemm_bf16_tc`)
+    The two weight gradients reduce over the token dimension (transposed-A products): they are plain library
+    GEMMs (`torch.matmul`, bf16 operands, fp32 result).  Operands are rounded to bf16 as in the inference path;
+    W1 / W2 are functions of the layer's cores built with autograd-tracked torch ops, so the core gradients
+    follow by the chain rule.  Requires K1 % 8 == 0, N2 % 8 == 0, N1 <= LOWRANK2_MAX_INNER.
+    """
+
+    @staticmethod
+    def forward(ctx, x2d, w1, w2, bias):
+        rt.require_device(x2d)
+        R, K1 = x2d.shape
+        N1, N2 = w1.shape[0], w2.shape[0]
+        xb = x2d.detach().contiguous().to(torch.bfloat16)
+        w1b, ld1 = _pack_bf16(w1)
+        w2b, ld2 = _pack_bf16(w2)
+        out_dtype = torch.bfloat16 if x2d.dtype == torch.bfloat16 else torch.float32
+        y = torch.empty(R, N2, dtype=out_dtype, device=x2d.device)
+        b32 = bias.detach().to(torch.float32).contiguous() if bias is not None else None
+        rt.lowrank2_fwd(xb, w1b, w2b, b32, y, R, K1, N1, N2, ldx=K1, ld1=ld1, ld2=ld2, ldy=N2)
+        ctx.save_for_backward(xb, w1b, w2b)
+        ctx.dims = (R, K1, N1, N2, ld1, ld2, x2d.dtype, w1.dtype, w2.dtype, bias is not None,
+                    bias.dtype if bias is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, w1b, w2b = ctx.saved_tensors
+        R, K1, N1, N2, ld1, ld2, xdt, w1dt, w2dt, has_bias, bdt = ctx.dims
+        dev = dy.device
+        dyb = dy.detach().contiguous().to(torch.bfloat16)
+        n1p = pad8(N1)
+        w2t = w2b[:, :N1].t().contiguous()                       # (N1 x N2), row pitch N2 (a multiple of 8)
+        w1t = torch.zeros(K1, n1p, dtype=torch.bfloat16, device=dev)
+        w1t[:, :N1] = w1b[:, :K1].t()                            # (K1 x N1), row pitch pad8(N1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(R, K1, dtype=torch.bfloat16 if xdt == torch.bfloat16 else torch.float32, device=dev)
+            rt.lowrank2_fwd(dyb, w2t, w1t, None, dx, R, N2, N1, K1, ldx=N2, ld1=N2, ld2=n1p, ldy=K1)
+            dx = dx.to(xdt)
+        dw1 = dw2 = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            v = torch.zeros(R, n1p, dtype=torch.bfloat16, device=dev)
+            rt.gemm_bf16_tc(xb, w1b, v, R, N1, K1, lda=K1, ldb=ld1, ldc=n1p)          # V = x W1^T
+            dw2 = (dyb.t() @ v[:, :N1]).to(w2dt)
+            dv = torch.zeros(R, n1p, dtype=torch.bfloat16, device=dev)
+            rt.gemm_bf16_tc(dyb, w2t, dv, R, N1, N2, lda=N2, ldb=N2, ldc=n1p)         # dV = dY W2
+            dw1 = (dv[:, :N1].t() @ xb).to(w1dt)
+        db = dy.sum(0).to(bdt) if has_bias and ctx.needs_input_grad[3] else None
+        return dx, dw1, dw2, db
+
+
+def lowrank2_trainable(in_features, out_features, r_mid):
+    return in_features % 8 == 0 and out_features % 8 == 0 and r_mid <= LOWRANK2_MAX_INNER
+
+
 def tt_chain_macs(in_cores, out_cores):
     """Multiply-accumulates per row of the factorised chain (TTLinear.py:79-88 order)."""
     macs = 0

@@ -208,6 +208,17 @@ def test_tklinear_forward_matches_dense(variant):
     ref = torch.nn.functional.linear(x, z, b.to(DEV))
     assert _rel(y, ref) <= FWD_TOL, _rel(y, ref)
     assert tuple(layer.first_factor.shape) == (72, 384) and tuple(layer.last_factor.shape) == (192, 40)
+    if variant == 'M':                     # fused training path: same gradients as the torch op chain (bf16 rounding)
+        grads = []
+        for fused in (False, True):
+            layer.fused_training = fused
+            layer.zero_grad()
+            xg = x.clone().requires_grad_(True)
+            layer(xg).square().sum().backward()
+            grads.append([xg.grad.clone(), layer.first_factor.grad.clone(), layer.core_tensor.grad.clone(),
+                          layer.last_factor.grad.clone(), layer.bias.grad.clone()])
+        for a, b_ in zip(grads[1], grads[0]):
+            assert _rel(a, b_) <= 3e-2, _rel(a, b_)
 
 
 @pytest.mark.parametrize('B,Cin,H,W,Ra,Rb,Cout,KS,stride,pad', [
@@ -277,3 +288,39 @@ def test_lowrank2_rejects_bad_arguments():
         rt.lowrank2_fwd(x, w1, w2, None, y, 128, 64, 400, 64)          # inner width beyond the TMEM budget
     with pytest.raises(rt.TtaError):
         rt.lowrank2_fwd(x, w1, w2, None, y, 128, 64, 64, 64, ldx=60)    # leading dimension not a multiple of 8
+
+
+@pytest.mark.parametrize('name,fin,fout', [('blocks.0.attn.qkv.weight', 384, 1152), ('blocks.1.mlp.fc2.weight', 1536, 384)])
+def test_ttlinear_fused_training_path(name, fin, fout):
+    """forward + dX on the fused two-factor kernel, core gradients by the chain rule through the
+    folded factors; compared with the fp32 torch op chain (bf16 operand rounding: 2e-2 on gradients)."""
+    import TTLinear
+    hp = _deit_hp()
+    torch.manual_seed(11)
+    layer = TTLinear.TTLinearM(fin, fout, bias=True, hp_dict=hp.fresh(), name=name).to(DEV)
+    with torch.no_grad():
+        layer.bias.normal_(0, 0.1)
+    x = torch.randn(2, 197, fin, device=DEV)
+    gy = torch.randn(2, 197, fout, device=DEV)
+
+    def run(fused):
+        layer.fused_training = fused
+        layer.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        y = layer(xg)
+        (y * gy).sum().backward()
+        return y.detach(), xg.grad.clone(), [c.grad.clone() for c in layer.tt_cores], layer.bias.grad.clone()
+
+    y0, dx0, dc0, db0 = run(False)
+    y1, dx1, dc1, db1 = run(True)
+    assert _rel(y1, y0) <= FWD_TOL and _rel(dx1, dx0) <= 2e-2
+    for a, b in zip(dc1, dc0):
+        assert _rel(a, b) <= 2e-2, _rel(a, b)
+    assert _rel(db1, db0) <= 1e-5
+    with torch.autocast('cuda', dtype=torch.bfloat16):           # autocast selects the fused path by itself
+        layer.fused_training = False
+        layer.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        y2 = layer(xg)
+    (y2.float() * gy).sum().backward()
+    assert _rel(y2.detach().float(), y0) <= FWD_TOL and _rel(xg.grad, dx0) <= 2e-2
