@@ -13,7 +13,9 @@
 //              64 k, SWIZZLE_128B) into a ring of 16 KB stages; mbarrier expect_tx / complete_tx.
 //   warp 1     TMEM allocator (512 columns) + tcgen05.mma issuer (one elected lane).
 //              GEMM 1: acc1[128 x N1] (TMEM columns 0..)  += x-block * W1-block^T
-//              GEMM 2: acc2[buf][128 x BN2]               = V * W2-chunk^T, V = bf16(acc1) in shared memory
+//              GEMM 2: acc2[buf][128 x BN2]               = V * W2-chunk^T, V = bf16(acc1): packed in place over
+//                      acc1 in TMEM and used as the TMEM A operand (default), or staged in shared memory in the
+//                      UMMA K-major layout (TTA_LR2_TS=0)
 //   warps 2-5  epilogue (one TMEM lane quadrant each): acc1 -> bf16 -> V (UMMA K-major SWIZZLE_128B layout,
 //              written by hand) ; acc2 chunks -> +bias -> swizzled staging -> TMA store of y (fp32 or bf16).  acc2 is double buffered, so
 //              the chunk epilogue overlaps the next chunk's MMAs, and GEMM 1 of the next row tile overlaps the
@@ -31,7 +33,7 @@ namespace lr2 {
 using namespace tta::tc;
 
 constexpr int kXStages = 2;
-constexpr int kMaxWStages = 8;
+constexpr int kMaxWStages = 12;
 constexpr int kThreads = 192;
 constexpr int kMaxN1 = 384;
 
@@ -48,6 +50,7 @@ struct Params {
   int wstages;
   int ntiles;
   int out_f32;
+  int ts;         // GEMM 2 takes its A operand (V, bf16) from TMEM instead of shared memory
   int bias_vec;   // bias is 16-byte aligned: 128-bit loads
   int64_t ldy;
 };
@@ -72,12 +75,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_y,
                         const float* __restrict__ bias, const Params p,
                         unsigned long long* __restrict__ prof) {
+  const long long t_kernel0 = PROF ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_smem;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t Vs = smem0;                                         // nkv x 16 KB
-  const uint32_t Xs = Vs + (uint32_t)p.nkv * kStageBytes;            // kXStages x 16 KB
+  const uint32_t Xs = Vs + (uint32_t)(p.ts ? 0 : p.nkv) * kStageBytes;   // kXStages x 16 KB (V lives in TMEM in TS mode)
   const uint32_t Ws = Xs + (uint32_t)kXStages * kStageBytes;         // wstages x 16 KB
   const uint32_t St = Ws + (uint32_t)p.wstages * kStageBytes;        // 4 warps x 2 x 4 KB output staging
   const uint32_t bar0 = smem_u32(bars);
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
+    const long long t_role0 = PROF ? clock64() : 0;
     const bool leader = elect_one();
     int xs = 0, ws = 0;
     uint32_t xph = 0, wph = 0;
@@ -189,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             umma_commit(BAR(kBarWEmpty + ws));
           }
           __syncwarp();
+          LR2_ACC(0)
           if (++ws == p.wstages) { ws = 0; wph ^= 1; }
         }
         if (leader) umma_commit(BAR(kBarXEmpty + xs));
@@ -207,18 +213,33 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_wait(BAR(kBarWFull + ws), wph); LR2_ACC(6)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (leader) {
-            const uint64_t da = descV + (uint64_t)kb * kStageDesc;
             const uint64_t db = descW + (uint64_t)ws * kStageDesc;
+            if (p.ts) {
+              // A = V from TMEM: bf16 pairs packed in 32-bit cells, 16 k-elements = 8 columns per MMA
+              const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            } else {
+              const uint64_t da = descV + (uint64_t)kb * kStageDesc;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            }
             umma_commit(BAR(kBarWEmpty + ws));
           }
           __syncwarp();
+          LR2_ACC(7)
           if (++ws == p.wstages) { ws = 0; wph ^= 1; }
         }
         if (leader) umma_commit(BAR(kBarAcc2Full + buf));
         __syncwarp();
+      }
+    }
+    if constexpr (PROF) {
+      if (profiling && lane == 0) {
+        prof[24] = (unsigned long long)(t_role0 - t_kernel0);
+        prof[25] = (unsigned long long)(clock64() - t_role0);
       }
     }
   } else {
@@ -264,25 +285,35 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        const uint32_t vrow = Vs + (uint32_t)(c0 >> 6) * kStageBytes + row * 128;
-        const int ch0 = (c0 & 63) >> 3;
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = c0 + 8 * i + 2 * j;
-            const float lo = col < p.N1 ? __uint_as_float(v[8 * i + 2 * j]) : 0.f;
-            const float hi = col + 1 < p.N1 ? __uint_as_float(v[8 * i + 2 * j + 1]) : 0.f;
-            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          sts128(vrow + (((ch0 + i) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + 2 * j;
+          const float lo = col < p.N1 ? __uint_as_float(v[2 * j]) : 0.f;
+          const float hi = col + 1 < p.N1 ? __uint_as_float(v[2 * j + 1]) : 0.f;
+          __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
         }
-        if ((c0 & 63) == 32) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of V -> async proxy (UMMA)
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(BAR(kBarVReady + (c0 >> 6)));
+        if (p.ts) {
+          // V overwrites acc1 in place: the pairs of columns c0 .. c0+31 (already in registers) go to the 16
+          // cells c0/2 .. c0/2+15 of this lane, all of which lie in the part of acc1 that has been read
+          tmem_st16(lane_addr + (uint32_t)(c0 >> 1), pk);
+          if ((c0 & 63) == 32) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(BAR(kBarVReady + (c0 >> 6)));
+          }
+        } else {
+          const uint32_t vrow = Vs + (uint32_t)(c0 >> 6) * kStageBytes + row * 128;
+          const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(vrow + (((ch0 + i) ^ (row & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          if ((c0 & 63) == 32) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of V -> async proxy (UMMA)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(BAR(kBarVReady + (c0 >> 6)));
+          }
         }
       }
       LR2_ACC(1)
@@ -367,6 +398,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 #undef BAR
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (PROF) {
+    if (profiling && tid == 0) prof[26] = (unsigned long long)(clock64() - t_kernel0);
+  }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -415,7 +449,13 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
   p.bias_vec = (bias && ((uintptr_t)bias & 15) == 0) ? 1 : 0;
   p.ldy = ldy;
   const size_t budget = 227 * 1024 - 1024 - 512;   // dynamic shared memory minus alignment slack and the barriers
-  const size_t fixed = (size_t)(p.nkv + kXStages + 2) * kStageBytes;   // V, x ring, output staging (8 x 4 KB)
+  static int ts_mode = -1;
+  if (ts_mode < 0) {
+    const char* e = getenv("TTA_LR2_TS");
+    ts_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  p.ts = ts_mode;
+  const size_t fixed = (size_t)((p.ts ? 0 : p.nkv) + kXStages + 2) * kStageBytes;   // (V,) x ring, output staging (8 x 4 KB)
   int wst = (int)((budget - fixed) / kStageBytes);
   if (wst > kMaxWStages) wst = kMaxWStages;
   if (wst < 2) {
@@ -456,18 +496,18 @@ extern "C" int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int6
   if (!prof_init) {
     prof_init = true;
     const char* e = getenv("TTA_LR2_PROF");
-    if (e && e[0] == '1' && cudaMalloc(&prof, 24 * sizeof(unsigned long long)) == cudaSuccess)
-      cudaMemset(prof, 0, 24 * sizeof(unsigned long long));
+    if (e && e[0] == '1' && cudaMalloc(&prof, 32 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(prof, 0, 32 * sizeof(unsigned long long));
   }
   if (prof) {
-    unsigned long long h[24];
+    unsigned long long h[32];
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
     if (h[8] | h[16])
       fprintf(stderr,
               "[lr2 prof, CTA 0, cycles] producer: wait w_empty g1 %llu g2 %llu | mma: wait x_full %llu w_full(g1) %llu acc2_empty %llu "
-              "v_ready %llu w_full(g2) %llu | epilogue warp: wait acc1 %llu convert V %llu wait acc2 %llu store y (rest) %llu "
-              "[tmem ld %llu, wait staging %llu, bias+convert+sts %llu, fence+tma %llu]\n",
-              h[0], h[1], h[10], h[11], h[12], h[13], h[14], h[16], h[17], h[18], h[19], h[20], h[21], h[22], h[23]);
+              "v_ready %llu w_full(g2) %llu issue(g2) %llu issue(g1) %llu | epilogue warp: wait acc1 %llu convert V %llu wait acc2 %llu store y (rest) %llu "
+              "[tmem ld %llu, wait staging %llu, bias+convert+sts %llu, fence+tma %llu] | setup %llu mma role %llu whole CTA %llu\n",
+              h[0], h[1], h[10], h[11], h[12], h[13], h[14], h[15], h[8], h[16], h[17], h[18], h[19], h[20], h[21], h[22], h[23], h[24], h[25], h[26]);
     cudaMemset(prof, 0, sizeof(h));
   }
   if (prof)
