@@ -628,6 +628,20 @@ class EigBatch:
         self.tables[sig] = tabs
         return tabs
 
+    def enqueue(self, tabs):
+        """Same as `run` without the host synchronisation; sweep counts via `results(tabs)` after a sync."""
+        rt.gram(tabs['gram'])
+        rt.jacobi_eigh_async(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
+        rt.refine_prepare(tabs['refine'])
+        rt.gemm_f64(tabs['d_yt'])
+        rt.gemm_f64(tabs['d_s'])
+        rt.refine_coeff(tabs['refine'])
+        rt.gemm_f64(tabs['d_e'])
+        rt.refine_finalize(tabs['refine'])
+
+    def results(self, tabs):
+        return rt.jacobi_results(tabs['eig'], tabs['scratch'], self.max_sweeps)
+
     def run(self, tabs):
         rt.gram(tabs['gram'])
         sweeps = rt.jacobi_eigh(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
@@ -769,15 +783,19 @@ class TKProjectionPlan:
         it = 0
         ph.mark('hooi')
         while active and it < self.n_iter_max:
+            # one host synchronisation per HOOI sweep (the stopping rule needs the core norm on the host):
+            # both eigensolves are only enqueued, their sweep counts are read after the norm has arrived
+            t0, t1 = self._eig_tabs('sweep0', active), self._eig_tabs('sweep1', active)
             rt.gemm(self._tab('p0', active))
-            s0 = self.eig.run(self._eig_tabs('sweep0', active))
+            self.eig.enqueue(t0)
             rt.gemm(self._tab('p1', active))
-            s1 = self.eig.run(self._eig_tabs('sweep1', active))
+            self.eig.enqueue(t1)
             rt.gemm(self._tab('core', active))
             out = self.norms[n:n + len(active)]
             out.zero_()
             rt.sqnorm(self._tab('nc', active), out)
             norm_c2 = out.cpu().numpy()
+            s0, s1 = self.eig.results(t0), self.eig.results(t1)
             stop = []
             for q, li in enumerate(active):
                 jac[self.layers[li].name] += [int(s0[q]), int(s1[q])]

@@ -30,3 +30,4 @@ for _ in range(n):
     b.synchronize()
     ts.append(a.elapsed_time(b))
 print('chain-only update ms:', ' '.join('{:.2f}'.format(t) for t in ts))
+print('jacobi sweeps per TT step:', {n: v for n, v in admm.sweeps.items()})
