@@ -320,6 +320,8 @@ def run_ours(args):
                         '74 TFLOP/s FFMA2 rate measured with scripts/ubench/fp64_rate.cu'}
     ew_bytes = 16.0 * numel
     kernels = {
+        'note': 'per-phase device times of a separate profiling pass in which the layer groups run one after another '
+                '(CUDA events on one stream); in the timed update the groups overlap on their own streams',
         'dual_update': {'bound': 'hbm', 'ms': ew_ms, 'achieved': ew_bytes / (ew_ms / 1e3) / 1e9 if ew_ms else None,
                         'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                         'frac': (ew_bytes / (ew_ms / 1e3) / 1e9) / peaks['hbm_gbs'] if ew_ms else None},

@@ -62,24 +62,41 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task*
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
 
-    for (int k0 = 0; k0 < tk.K; k0 += kGemmBK) {
+    // The global loads of k-tile t + 1 are issued into registers before the FMAs of tile t, so their latency
+    // overlaps the arithmetic (with few tiles per launch -- the refinement / projection GEMMs of a three-layer
+    // group -- the kernel is otherwise a chain of load -> barrier -> compute -> barrier round trips).
+    T ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int e = q * kGemmThreads + tid;  // 0..1023
         int ar, ak;
         if (a_kfast) { ar = e >> 4; ak = e & 15; } else { ak = e >> 6; ar = e & 63; }
         const int gi = m0 + ar, gk = k0 + ak;
-        T v = T(0);
-        if (gi < tk.M && gk < tk.K) v = __ldg(pa + (int64_t)gi * tk.sai + (int64_t)gk * tk.sak);
-        As[ak][ar] = v;
+        ra[q] = (gi < tk.M && gk < tk.K) ? __ldg(pa + (int64_t)gi * tk.sai + (int64_t)gk * tk.sak) : T(0);
         int bk, bj;
         if (b_jfast) { bk = e >> 6; bj = e & 63; } else { bj = e >> 4; bk = e & 15; }
         const int gj = n0 + bj, gkb = k0 + bk;
-        T vb = T(0);
-        if (gj < tk.N && gkb < tk.K) vb = __ldg(pb + (int64_t)gkb * tk.sbk + (int64_t)gj * tk.sbj);
-        Bs[bk][bj] = vb;
+        rb[q] = (gj < tk.N && gkb < tk.K) ? __ldg(pb + (int64_t)gkb * tk.sbk + (int64_t)gj * tk.sbj) : T(0);
       }
+    };
+    auto stash = [&]() {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = q * kGemmThreads + tid;
+        int ar, ak;
+        if (a_kfast) { ar = e >> 4; ak = e & 15; } else { ak = e >> 6; ar = e & 63; }
+        As[ak][ar] = ra[q];
+        int bk, bj;
+        if (b_jfast) { bk = e >> 6; bj = e & 63; } else { bj = e >> 4; bk = e & 15; }
+        Bs[bk][bj] = rb[q];
+      }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < tk.K; k0 += kGemmBK) {
+      stash();
       __syncthreads();
+      if (k0 + kGemmBK < tk.K) fetch(k0 + kGemmBK);
 #pragma unroll
       for (int kk = 0; kk < kGemmBK; ++kk) {
         using V4 = typename Vec4<T>::type;
