@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task*
     const T* __restrict__ pa = reinterpret_cast<const T*>(tk.a);
     const T* __restrict__ pb = reinterpret_cast<const T*>(tk.b);
     T* __restrict__ pc = reinterpret_cast<T*>(tk.c);
-    const T* __restrict__ pcs = reinterpret_cast<const T*>(tk.colscale);
+    const bool guarded = sizeof(T) == 8 && (tk.flags & TTA_GEMM_GUARD);
+    if (guarded && *reinterpret_cast<const double*>(tk.colscale) == 0.0) continue;   // CTA-uniform
+    const T* __restrict__ pcs = guarded ? nullptr : reinterpret_cast<const T*>(tk.colscale);
     T acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -122,7 +124,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const tta_gemm_task*
         if (gj >= tk.N) continue;
         T v = acc[i][j];
         if (pcs) v *= __ldg(pcs + gj);
-        pc[(int64_t)gi * tk.ldc + gj] = v;
+        if (sizeof(T) == 8 && (tk.flags & TTA_GEMM_STORE_F32))
+          reinterpret_cast<float*>(tk.c)[(int64_t)gi * tk.ldc + gj] = (float)v;
+        else
+          pc[(int64_t)gi * tk.ldc + gj] = v;
       }
     }
   }

@@ -295,6 +295,14 @@ class TTProjectionPlan:
         self.profile = None
         self.trace = None
         self._bound = None
+        # Warm start: from the second update on, the Jacobi state of a step starts from X = G Q_prev (Q_prev = the
+        # eigenvector estimate of the previous update, still in the refinement buffer `qt`) instead of X = G.  Any
+        # orthogonal Q is a valid start of the one-sided iteration (it converges to G Q J = V Lambda all the same);
+        # when consecutive updates see similar Gram matrices -- ADMM iterates, fine-tuning epochs -- G Q_prev is
+        # nearly orthogonal already and the solver needs fewer sweeps.  Results are converged to the same
+        # criterion either way.  TTA_WARM_START=0 disables it.
+        self.warm_start = bool(refine) and os.environ.get('TTA_WARM_START', '1') != '0'
+        self._warm_valid = False
         self._alloc()
 
     # -- workspace ---------------------------------------------------------------------------------
@@ -425,6 +433,7 @@ class TTProjectionPlan:
             mm = np.zeros(len(idx), dtype=rt.GEMM_TASK)
             rf = np.zeros(len(idx), dtype=rt.REFINE_TASK)
             dg = [np.zeros(len(idx), dtype=rt.GEMM_TASK) for _ in range(4)]
+            wg = np.zeros(len(idx), dtype=rt.GEMM_TASK)
             for q, (li, si) in enumerate(members):
                 st = self.ws[li]['steps'][si]
                 m, n, k, r = st['m'], st['n'], st['k'], st['r']
@@ -453,6 +462,12 @@ class TTProjectionPlan:
                     dg[1][q] = (st['y'].ptr, qt, st['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)      # s = y * qt^T
                     dg[2][q] = (qt, qt, st['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)               # t = qt[:wnd] * qt^T
                     dg[3][q] = (st['c'].ptr, qt, st['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)      # e64 = c * qt
+                    # warm start: X (column j at x + j*ld, fp32) = G q_j, i.e. rows of qt * g64 (G symmetric)
+                    # guarded by the smallest eigenvalue estimate of the previous solve (lam0 is sorted, descending):
+                    # a null column is stored as a zero row of qt, and a rank-deficient start could not recover
+                    # directions that become non-null later -- such a problem starts cold (X = G stays in place)
+                    wg[q] = (qt, st['g64'].ptr, st['X'].ptr, st['lam0'].ptr + 8 * (k - 1), k, 1, k, 1, st['ld'], k, k, k,
+                             rt.GEMM_STORE_F32 | rt.GEMM_GUARD)
             wave = dict(idx=idx, gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev),
                         select=rt.TaskTable(s, dev), gemm=rt.TaskTable(mm, dev))
             if self.refine:
@@ -460,6 +475,7 @@ class TTProjectionPlan:
                 wave['dgemm_ys_t'] = rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev)   # independent: one launch
                 wave['dgemm_s'] = rt.TaskTable(dg[1], dev)
                 wave['dgemm_e'] = rt.TaskTable(dg[3], dev)
+                wave['warm'] = rt.TaskTable(wg, dev)
             nbytes = rt.jacobi_scratch_bytes(wave['eig'])
             wave['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
             self.waves.append(wave)
@@ -504,12 +520,16 @@ class TTProjectionPlan:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 tr.append((label, ev))
+        warm = self.warm_start and self.refine and self._warm_valid
+        self._warm_valid = False            # set again by collect() once this update is known to have converged
         mark('start')
         ph.mark('unfold')
         rt.unfold_add(self.t_unfold)
         for wi, wave in enumerate(self.waves):
             ph.mark('gram')
             rt.gram(wave['gram'])
+            if warm:
+                rt.gemm_f64(wave['warm'])
             mark('w{} eig begin'.format(wi))
             ph.mark('eig')
             rt.jacobi_eigh_async(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
@@ -549,6 +569,7 @@ class TTProjectionPlan:
             off += n6
             for q, li in enumerate(wave['idx']):
                 self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
+        self._warm_valid = True
 
     def cores(self, li):
         """Cores of layer `li` after `run()` as tensors shaped (r_i, s_i, r_{i+1}) (ten2tt's return)."""

@@ -35,7 +35,9 @@ SELECT_TASK = np.dtype([('x', P), ('e', P), ('et', P), ('se', P), ('sigma', P), 
                         ('k', np.int32), ('ld', np.int32), ('r', np.int32), ('pad_', np.int32)], align=True)
 GEMM_TASK = np.dtype([('a', P), ('b', P), ('c', P), ('colscale', P), ('sai', np.int64), ('sak', np.int64),
                       ('sbk', np.int64), ('sbj', np.int64), ('ldc', np.int64), ('M', np.int32),
-                      ('N', np.int32), ('K', np.int32), ('pad_', np.int32)], align=True)
+                      ('N', np.int32), ('K', np.int32), ('flags', np.int32)], align=True)
+GEMM_STORE_F32 = 1     # tta_gemm_f64_batched: c is a float array
+GEMM_GUARD = 2         # tta_gemm_f64_batched: colscale points to one double; the task is skipped when it is 0
 SQNORM_TASK = np.dtype([('x', P), ('n', np.int64)], align=True)
 REFINE_TASK = np.dtype([('x', P), ('qt', P), ('s', P), ('t', P), ('c', P), ('lam', P), ('lam0', P), ('e64', P),
                         ('e', P), ('et', P), ('se', P), ('sigma', P), ('isigma', P), ('k', np.int32),

@@ -183,8 +183,13 @@ typedef struct {
   float* c;
   const float* colscale; /* nullable */
   int64_t sai, sak, sbk, sbj, ldc;
-  int32_t M, N, K, pad_;
+  int32_t M, N, K;
+  int32_t flags;         /* tta_gemm_f64_batched only: TTA_GEMM_STORE_F32 -- c is a float array, results are rounded
+                          * on store; TTA_GEMM_GUARD -- colscale is not a scale but points to ONE double: the task
+                          * is skipped when that value is 0 */
 } tta_gemm_task;
+#define TTA_GEMM_STORE_F32 1
+#define TTA_GEMM_GUARD 2
 
 int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
                      void* stream);

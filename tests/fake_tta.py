@@ -134,10 +134,10 @@ class FakeTTA:
         for i, tk in enumerate(_table(thost, n, rt.EIG_TASK)):
             k, ld, kpad = int(tk['k']), int(tk['ld']), int(tk['kpad'])
             x = _view(tk['x'], ld * kpad).reshape(kpad, ld)
-            g = x[:k, :k].T.astype(np.float64)
-            g = 0.5 * (g + g.T)
-            lam, v = np.linalg.eigh(g)
-            lam = np.maximum(lam, 0.0)
+            # one-sided Jacobi on the columns of M (= G, or G Q_prev with a warm start): M J = U S with
+            # orthogonal columns, i.e. the left singular vectors scaled by the singular values
+            m = x[:k, :k].T.astype(np.float64)
+            v, lam, _ = np.linalg.svd(m)
             order = rng.permutation(k) if self.scramble else np.arange(k)
             x[:k, :k] = (v[:, order] * lam[order]).T.astype(np.float32)
             if sw is not None:
@@ -261,16 +261,21 @@ class FakeTTA:
         isz = np.dtype(dt).itemsize
         for tk in _table(thost, n, rt.GEMM_TASK):
             M, N, K = int(tk['M']), int(tk['N']), int(tk['K'])
+            guarded = dt == np.float64 and int(tk['flags']) & rt.GEMM_GUARD
+            if guarded and float(_view(tk['colscale'], 1, np.float64)[0]) == 0.0:
+                continue
             sai, sak, sbk, sbj, ldc = (int(tk[f]) for f in ('sai', 'sak', 'sbk', 'sbj', 'ldc'))
             abase = _view(tk['a'], (M - 1) * sai + (K - 1) * sak + 1, dt)
             bbase = _view(tk['b'], (K - 1) * sbk + (N - 1) * sbj + 1, dt)
             a = np.lib.stride_tricks.as_strided(abase, shape=(M, K), strides=(isz * sai, isz * sak))
             b = np.lib.stride_tricks.as_strided(bbase, shape=(K, N), strides=(isz * sbk, isz * sbj))
             c = (a @ b).astype(dt)
-            if tk['colscale']:
+            if tk['colscale'] and not guarded:
                 c = c * _view(tk['colscale'], N, dt)[None, :]
-            cbase = _view(tk['c'], (M - 1) * ldc + N, dt)
-            np.lib.stride_tricks.as_strided(cbase, shape=(M, N), strides=(isz * ldc, isz))[:] = c
+            odt = np.float32 if (dt == np.float64 and int(tk['flags']) & rt.GEMM_STORE_F32) else dt
+            osz = np.dtype(odt).itemsize
+            cbase = _view(tk['c'], (M - 1) * ldc + N, odt)
+            np.lib.stride_tricks.as_strided(cbase, shape=(M, N), strides=(osz * ldc, osz))[:] = c.astype(odt)
         return 0
 
     def tta_sqnorm_batched(self, tdev, thost, n, out, stream):

@@ -194,3 +194,36 @@ def test_update_from_host_matches_update_on_gpu():
         assert torch.equal(a.z[n], b.z[n]) and torch.equal(a.u[n], b.u[n]), n
         assert torch.equal(host_z[n], b.z[n].cpu()), n
         assert rel_fro(c.z[n].cpu().numpy(), b.z[n].cpu().numpy()) <= 1e-6, n
+
+
+def test_warm_start_after_a_rank_deficient_update():
+    """The Jacobi warm start (X = G Q_prev) must not lose directions: after an update on exactly low-rank weights
+    (null columns in the previous eigenbasis) an update on full-rank weights still matches the oracle, and a second
+    update on unchanged inputs (the best case of the warm start) gives the same Z as the first."""
+    from admm import ADMM
+    wb, hb, fmt = workloads.CONFIGS['resnet50_tt']
+    names = ['layer2.0.conv2.weight', 'layer3.0.conv1.weight']
+    full = {n: w for n, w in wb().items() if n in names}
+    a = ADMM(workloads.ParamBag(full, device=DEV), 1e-3, hb(), fmt, DEV)
+    a.update(update_u=False)
+    low = {n: a.z[n].clone() for n in names}                    # exactly on the rank manifold
+    params = dict(a.model.named_parameters())
+    for n in names:
+        params[n].data.copy_(low[n])
+    a.update(update_u=False)                                    # Gram matrices with null eigenvalues
+    a.update(update_u=False)                                    # warm-started on the same input
+    for n in names:
+        assert rel_fro(a.z[n].cpu().numpy(), low[n].cpu().numpy()) <= Z_TOL, n      # idempotence
+    g = torch.Generator().manual_seed(5)
+    fresh = {n: torch.randn(full[n].shape, generator=g) * 0.05 for n in names}
+    for n in names:
+        params[n].data.copy_(fresh[n].to(DEV))
+    a.update(update_u=False)
+    z1 = {n: a.z[n].clone() for n in names}
+    a.update(update_u=False)                                    # unchanged input: few sweeps, same answer
+    assert max(max(v) for v in a.sweeps.values()) <= 4
+    o = port.OracleADMM({n: fresh[n].numpy() for n in names}, 1e-3, hb(), fmt)
+    o.update(update_u=False)
+    for n in names:
+        assert rel_fro(z1[n].cpu().numpy(), o.z[n]) <= Z_TOL, n
+        assert rel_fro(a.z[n].cpu().numpy(), o.z[n]) <= Z_TOL, n
