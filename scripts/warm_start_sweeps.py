@@ -34,4 +34,7 @@ for warm in (False, True):
         sw = [s for v in admm.sweeps.values() for s in v]
         line.append('{:.1f}ms/{}'.format(a.elapsed_time(b), max(sw)))
     print('warm' if warm else 'cold', key, ' '.join(line), flush=True)
+    for n, v in admm.sweeps.items():
+        if 'layer4' in n or 'layer3.0' in n or 'blocks.0.' in n:
+            print('   ', n, v)
     del admm, model
