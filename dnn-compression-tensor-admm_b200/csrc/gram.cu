@@ -83,7 +83,11 @@ __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task
 #pragma unroll
       for (int j = 0; j < TT; ++j) acc[i][j] = 0.0;
 
-    for (int64_t rr = rbeg; rr < rend; rr += kGramBK) {
+    // the global loads of chunk c + 1 are issued into registers before the DFMAs of chunk c (otherwise every
+    // chunk pays a full load -> barrier -> compute -> barrier round trip: the kernel was latency bound at
+    // 1/30 of the bytes it could stream)
+    float ra[kLoads], rb[kLoads];
+    auto fetch = [&](int64_t rr) {
 #pragma unroll
       for (int q = 0; q < kLoads; ++q) {
         const int e = q * kGramThreads + tid;
@@ -92,15 +96,22 @@ __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task
         const int64_t rho = rr + kk;
         const bool rok = rho < rend;
         const int64_t off = rok ? gram_off(tk, rho) : 0;
-        float va = 0.f, vb = 0.f;
-        if (rok && (i0 + row) < tk.k) va = __ldg(tk.a + (int64_t)(i0 + row) * tk.si + off);
-        As[kk][row] = (double)va;
-        if (!diag) {
-          if (rok && (j0 + row) < tk.k) vb = __ldg(tk.a + (int64_t)(j0 + row) * tk.si + off);
-          Bs[kk][row] = (double)vb;
-        }
+        ra[q] = (rok && (i0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(i0 + row) * tk.si + off) : 0.f;
+        rb[q] = (!diag && rok && (j0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(j0 + row) * tk.si + off) : 0.f;
+      }
+    };
+    fetch(rbeg);
+    for (int64_t rr = rbeg; rr < rend; rr += kGramBK) {
+#pragma unroll
+      for (int q = 0; q < kLoads; ++q) {
+        const int e = q * kGramThreads + tid;
+        int row, kk;
+        if (rowfast) { kk = e >> kRowBits; row = e & (TS - 1); } else { row = e >> 4; kk = e & 15; }
+        As[kk][row] = (double)ra[q];
+        if (!diag) Bs[kk][row] = (double)rb[q];
       }
       __syncthreads();
+      if (rr + kGramBK < rend) fetch(rr + kGramBK);
       const double(*Bp)[TS + 2] = diag ? As : Bs;
 #pragma unroll
       for (int kk = 0; kk < kGramBK; ++kk) {

@@ -303,6 +303,10 @@ class TTProjectionPlan:
         # criterion either way.  TTA_WARM_START=0 disables it.
         self.warm_start = bool(refine) and os.environ.get('TTA_WARM_START', '1') != '0'
         self._warm_valid = False
+        self._warm_used = False      # the update being collected was warm-started
+        self._cold_sweeps = {}       # (wave, slot) -> sweeps of the last cold solve
+        self._nowarm = {}            # (wave, slot) -> updates left of a cold-start penalty (the warm start did not pay)
+        self._strikes = {}           # (wave, slot) -> consecutive warm updates whose sweep count barely dropped
         self._alloc()
 
     # -- workspace ---------------------------------------------------------------------------------
@@ -475,7 +479,10 @@ class TTProjectionPlan:
                 wave['dgemm_ys_t'] = rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev)   # independent: one launch
                 wave['dgemm_s'] = rt.TaskTable(dg[1], dev)
                 wave['dgemm_e'] = rt.TaskTable(dg[3], dev)
-                wave['warm'] = rt.TaskTable(wg, dev)
+                wave['warm_rows'] = wg
+                keep = [q for q in range(len(idx)) if (wv, q) not in self._nowarm]
+                wave['warm_q'] = keep
+                wave['warm'] = rt.TaskTable(wg[keep], dev)
             nbytes = rt.jacobi_scratch_bytes(wave['eig'])
             wave['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
             self.waves.append(wave)
@@ -522,13 +529,14 @@ class TTProjectionPlan:
                 tr.append((label, ev))
         warm = self.warm_start and self.refine and self._warm_valid
         self._warm_valid = False            # set again by collect() once this update is known to have converged
+        self._warm_used = warm
         mark('start')
         ph.mark('unfold')
         rt.unfold_add(self.t_unfold)
         for wi, wave in enumerate(self.waves):
             ph.mark('gram')
             rt.gram(wave['gram'])
-            if warm:
+            if warm and wave['warm'].n:
                 rt.gemm_f64(wave['warm'])
             mark('w{} eig begin'.format(wi))
             ph.mark('eig')
@@ -563,12 +571,41 @@ class TTProjectionPlan:
             return
         flat = torch.cat([w['scratch'][:6 * w['eig'].n] for w in live]).cpu().numpy()     # one D2H copy per plan
         off = 0
-        for wave in live:
+        for wi, wave in enumerate(self.waves):
+            if not wave['eig'].n:
+                continue
             n6 = 6 * wave['eig'].n
             sw = rt.jacobi_results_from_host(flat[off:off + n6], wave['eig'], self.max_sweeps)
             off += n6
             for q, li in enumerate(wave['idx']):
                 self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
+            if self.refine:
+                # adaptive warm start: the G * Q_prev product costs 2 k^3 fp64 flops per problem; a problem whose
+                # sweep count barely drops (unstable eigenvectors: flat spectrum, basis changes upstream in the TT
+                # chain) goes back to the cold start: two such updates in a row -> 16 cold updates, then it is probed again
+                warmed = set(wave['warm_q']) if self._warm_used else set()
+                dirty = False
+                for q in range(len(wave['idx'])):
+                    key = (wi, q)
+                    if q not in warmed:
+                        self._cold_sweeps[key] = int(sw[q])
+                        if key in self._nowarm:
+                            self._nowarm[key] -= 1
+                            if self._nowarm[key] <= 0:
+                                del self._nowarm[key]
+                                dirty = True
+                    elif int(sw[q]) > 0.7 * self._cold_sweeps.get(key, 1 << 30):
+                        self._strikes[key] = self._strikes.get(key, 0) + 1
+                        if self._strikes[key] >= 2:
+                            self._strikes[key] = 0
+                            self._nowarm[key] = 16
+                            dirty = True
+                    else:
+                        self._strikes[key] = 0
+                if dirty:
+                    keep = [q for q in range(len(wave['idx'])) if (wi, q) not in self._nowarm]
+                    wave['warm_q'] = keep
+                    wave['warm'] = rt.TaskTable(wave['warm_rows'][keep], self.device)
         self._warm_valid = True
 
     def cores(self, li):
