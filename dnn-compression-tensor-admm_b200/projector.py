@@ -635,6 +635,7 @@ class EigBatch:
         self.device = device
         self.tol = tol
         self.max_sweeps = max_sweeps
+        self.warm_start = os.environ.get('TTA_WARM_START', '1') != '0'
         self.bufs = {}
         self.tables = {}
 
@@ -665,6 +666,7 @@ class EigBatch:
         e = np.zeros(n, dtype=rt.EIG_TASK)
         rf = np.zeros(n, dtype=rt.REFINE_TASK)
         dg = [np.zeros(n, dtype=rt.GEMM_TASK) for _ in range(4)]
+        wg = np.zeros(n, dtype=rt.GEMM_TASK)
         for q, (b, op) in enumerate(problems):
             k, r = b['k'], b['r']
             g[q] = (op['a'], b['part'].ptr, b['X'].ptr, b['g64'].ptr, op['si'], op['sb'], op['sc'], k,
@@ -678,18 +680,29 @@ class EigBatch:
             dg[1][q] = (b['y'].ptr, qt, b['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
             dg[2][q] = (qt, qt, b['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
             dg[3][q] = (b['c'].ptr, qt, b['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)
+            # warm start X = G Q_prev (see TTProjectionPlan), guarded by the smallest previous eigenvalue estimate
+            wg[q] = (qt, b['g64'].ptr, b['X'].ptr, b['lam0'].ptr + 8 * (k - 1), k, 1, k, 1, b['ld'], k, k, k,
+                     rt.GEMM_STORE_F32 | rt.GEMM_GUARD)
         tabs = dict(gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev), refine=rt.TaskTable(rf, dev),
                     d_yt=rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev), d_s=rt.TaskTable(dg[1], dev),
-                    d_e=rt.TaskTable(dg[3], dev))
+                    d_e=rt.TaskTable(dg[3], dev), warm=rt.TaskTable(wg, dev),
+                    big=any(b['k'] > 512 for b, _ in problems))
         nbytes = rt.jacobi_scratch_bytes(tabs['eig'])
         tabs['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
         self.tables[sig] = tabs
         return tabs
 
-    def enqueue(self, tabs):
-        """Same as `run` without the host synchronisation; sweep counts via `results(tabs)` after a sync."""
+    def enqueue(self, tabs, warm=False):
+        """Same as `run` without the host synchronisation; sweep counts via `results(tabs)` after a sync.
+        warm: start the Jacobi iteration from G * (eigenvectors of the previous solve in the same buffers) -- the
+        Gram matrices of successive HOOI sweeps differ less and less, so the later sweeps need 2-3 Jacobi sweeps."""
         rt.gram(tabs['gram'])
-        rt.jacobi_eigh_async(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
+        if warm and self.warm_start:
+            rt.gemm_f64(tabs['warm'])
+        if tabs['big']:      # k > 512: the multi-launch solver synchronises per sweep and reports through the call
+            tabs['_sweeps'] = rt.jacobi_eigh(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
+        else:
+            rt.jacobi_eigh_async(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
         rt.refine_prepare(tabs['refine'])
         rt.gemm_f64(tabs['d_yt'])
         rt.gemm_f64(tabs['d_s'])
@@ -698,6 +711,8 @@ class EigBatch:
         rt.refine_finalize(tabs['refine'])
 
     def results(self, tabs):
+        if tabs['big']:
+            return tabs['_sweeps']
         return rt.jacobi_results(tabs['eig'], tabs['scratch'], self.max_sweeps)
 
     def run(self, tabs):
@@ -845,9 +860,9 @@ class TKProjectionPlan:
             # both eigensolves are only enqueued, their sweep counts are read after the norm has arrived
             t0, t1 = self._eig_tabs('sweep0', active), self._eig_tabs('sweep1', active)
             rt.gemm(self._tab('p0', active))
-            self.eig.enqueue(t0)
+            self.eig.enqueue(t0, warm=True)          # previous solve of the same mode: HOSVD init or the last sweep
             rt.gemm(self._tab('p1', active))
-            self.eig.enqueue(t1)
+            self.eig.enqueue(t1, warm=True)
             rt.gemm(self._tab('core', active))
             out = self.norms[n:n + len(active)]
             out.zero_()
