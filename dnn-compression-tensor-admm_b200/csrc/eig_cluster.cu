@@ -54,7 +54,7 @@ template <int NV>
 __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* __restrict__ cols, int* s_rot,
                                              int* s_total, int* s_counts, const tta_eig_task& tk, int prob,
                                              int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
-                                             float fl, float tol2, int max_sweeps) {
+                                             float fl, float tol2, float stop2, int max_sweeps) {
   const int P = (int)cluster.num_blocks();
   const int c = (int)cluster.block_rank();
   const int bw = tk.bw, ld = tk.ld;
@@ -82,9 +82,9 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
   if (tid == 0) printf("[cl] blk %d P %d c %d prob %d bw %d ld %d top_dst %d bot_dst %d\n", (int)blockIdx.x, P, c, prob, bw, ld, top_dst, bot_dst);
 #endif
   while (sweep < max_sweeps) {
-    int nrot = jacobi_block<NV>(cols, nrm, 0, 2, bw, ld, warp, lane, tol2, fl);     // pairs inside both blocks
+    int nrot = jacobi_block<NV>(cols, nrm, 0, 2, bw, ld, warp, lane, tol2, fl, stop2);     // pairs inside both blocks
     for (int round = 0; round < 2 * P - 1; ++round) {
-      nrot += jacobi_block<NV>(cols, nrm, 1, 2, bw, ld, warp, lane, tol2, fl);      // top x bottom pairs
+      nrot += jacobi_block<NV>(cols, nrm, 1, 2, bw, ld, warp, lane, tol2, fl, stop2);      // top x bottom pairs
       if (P > 1) {
         // jacobi_block ends with __syncthreads(): shared columns are final for this round
         if (c != 0) cl_copy_block(tk.x + (int64_t)top_dst * blk, top, blk4, tid, nthreads, false);
@@ -124,7 +124,11 @@ __device__ __forceinline__ void cluster_body(cg::cluster_group& cluster, float* 
 #ifdef TTA_DEBUG_CLUSTER
     if (tid == 0 && sweep <= 12) printf("[cl] c %d sweep %d total %d\n", c, sweep, total);
 #endif
-    if (total == 0) {
+    // `total` = rotations of the sweep + 65536 per rotation of a pair that was further from orthogonal than the
+    // stop threshold (seen before rotating).  No such pair => the sweep left off-diagonals of order stop^2
+    // (quadratic convergence), the same rule as the gram-rotate-apply solver: stop instead of spending two or
+    // three more sweeps at the fp32 noise floor waiting for a sweep without any rotation.
+    if (total == 0 || (total >> 16) == 0) {
       converged = 1;
       break;
     }
@@ -145,7 +149,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
     jacobi_cluster_kernel(const tta_eig_task* __restrict__ tasks, const int32_t* __restrict__ prob_ids,
                           int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
-                          const float* __restrict__ floor2, float tol2, int max_sweeps) {
+                          const float* __restrict__ floor2, float tol2, float stop2, int max_sweeps) {
   extern __shared__ __align__(16) float cols[];
   __shared__ int s_rot;
   __shared__ int s_total;
@@ -155,10 +159,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
   const tta_eig_task tk = tasks[prob];
   const float fl = floor2[prob] * (kJacFloorRel * kJacFloorRel);
   switch ((tk.ld + 127) >> 7) {
-    case 1: cluster_body<1>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
-    case 2: cluster_body<2>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
-    case 3: cluster_body<3>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
-    default: cluster_body<4>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, max_sweeps); break;
+    case 1: cluster_body<1>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, stop2, max_sweeps); break;
+    case 2: cluster_body<2>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, stop2, max_sweeps); break;
+    case 3: cluster_body<3>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, stop2, max_sweeps); break;
+    default: cluster_body<4>(cluster, cols, &s_rot, &s_total, s_counts, tk, prob, sweeps_out, status_out, fl, tol2, stop2, max_sweeps); break;
   }
 }
 
@@ -215,7 +219,7 @@ bool jacobi_cluster_eligible(const tta_eig_task& tk) {
 
 // One launch (on `gs`) of the column-rotation cluster kernel for problems that all use cluster size P.
 static int cluster_enqueue(const tta_eig_task* tasks_dev, const tta_eig_task* th, const std::vector<int>& probs, int P,
-                           float tol2, int max_sweeps, const int32_t* ids_dev, int32_t* sweeps_dev,
+                           float tol2, float stop2, int max_sweeps, const int32_t* ids_dev, int32_t* sweeps_dev,
                            int32_t* status_dev, const float* floor2, cudaStream_t gs) {
   static bool attr_set = false;
   static size_t smem_set[2] = {0, 0};
@@ -259,11 +263,11 @@ static int cluster_enqueue(const tta_eig_task* tasks_dev, const tta_eig_task* th
   cfg.numAttrs = 1;
   if (!big)
     rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<512>, tasks_dev, ids_dev, sweeps_dev, status_dev,
-                                       floor2, tol2, max_sweeps),
+                                       floor2, tol2, stop2, max_sweeps),
                     "jacobi cluster launch");
   else
     rc = check_cuda(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<1024>, tasks_dev, ids_dev, sweeps_dev, status_dev,
-                                       floor2, tol2, max_sweeps),
+                                       floor2, tol2, stop2, max_sweeps),
                     "jacobi cluster launch");
   if (rc) return rc;
   count_launch();
@@ -332,7 +336,7 @@ int jacobi_cluster_run(const tta_eig_task* tasks_dev, const tta_eig_task* th, co
     if (key >= 100)
       rc = jacobi_gra_enqueue(tasks_dev, th, g, key - 100, tol2, stop2, max_sweeps, ids, sweeps_dev, status_dev, floor2, gs);
     else
-      rc = cluster_enqueue(tasks_dev, th, g, key, tol2, max_sweeps, ids, sweeps_dev, status_dev, floor2, gs);
+      rc = cluster_enqueue(tasks_dev, th, g, key, tol2, stop2, max_sweeps, ids, sweeps_dev, status_dev, floor2, gs);
     if (rc) return rc;
   }
   for (int si = 0; si < kPoolStreams; ++si) {

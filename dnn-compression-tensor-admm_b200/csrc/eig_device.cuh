@@ -108,10 +108,12 @@ __device__ __forceinline__ float dot_regs(const float4 (&x)[NV], const float4 (&
 // column to `x` makes pairs chase each other across blocks and the sweep count explodes.)
 template <int NV>
 __device__ __forceinline__ int rotate_regs(float4 (&x)[NV], float4 (&y)[NV], float& a, float& b, float tol2,
-                                           float floor2) {
+                                           float floor2, float stop2 = 0.f) {
   const float c = dot_regs<NV>(x, y);
   float sn, tau, t;
   if (!jacobi_params(a, b, c, tol2, floor2, sn, tau, t)) return 0;
+  // 1 per rotation; + 65536 when the pair was further from orthogonal than the stop threshold (see cluster_body)
+  const int ret = 1 + ((c * c > (stop2 * a) * b) ? 65536 : 0);
   const float2 sp = make_float2(sn, sn), sm = make_float2(-sn, -sn);
   const float2 tp = make_float2(tau, tau), tm = make_float2(-tau, -tau);
 #pragma unroll
@@ -126,12 +128,12 @@ __device__ __forceinline__ int rotate_regs(float4 (&x)[NV], float4 (&y)[NV], flo
   const float d = t * c;
   a = fmaxf(a - d, 0.f);
   b = fmaxf(b + d, 0.f);
-  return 1;
+  return ret;
 }
 
 // Generic fallback for long columns (ld > 512): two passes over shared memory.
 __device__ __forceinline__ int rotate_smem(float* __restrict__ x, float* __restrict__ y, int ld, int lane, float tol2,
-                                           float floor2) {
+                                           float floor2, float stop2 = 0.f) {
   float a = 0.f, b = 0.f, c = 0.f;
   for (int e = lane * 4; e < ld; e += 128) {
     const float4 xv = *reinterpret_cast<const float4*>(x + e);
@@ -145,6 +147,7 @@ __device__ __forceinline__ int rotate_smem(float* __restrict__ x, float* __restr
   c = warp_sum(c);
   float sn, tau, t;
   if (!jacobi_params(a, b, c, tol2, floor2, sn, tau, t)) return 0;
+  const int ret = 1 + ((c * c > (stop2 * a) * b) ? 65536 : 0);
   for (int e = lane * 4; e < ld; e += 128) {
     const float4 xv = *reinterpret_cast<const float4*>(x + e);
     const float4 yv = *reinterpret_cast<const float4*>(y + e);
@@ -156,14 +159,15 @@ __device__ __forceinline__ int rotate_smem(float* __restrict__ x, float* __restr
     *reinterpret_cast<float4*>(x + e) = xn;
     *reinterpret_cast<float4*>(y + e) = yn;
   }
-  return 1;
+  return ret;
 }
 
 // All pair rotations of one staged block pair.  NV > 0: register-resident columns (ld <= 128*NV) with
 // cached squared norms in `nrm` (2*bw floats of shared memory behind the columns).
 template <int NV>
 __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, float* __restrict__ nrm, int kind, int nblk,
-                                            int bw, int ld, int warp, int lane, float tol2, float fl) {
+                                            int bw, int ld, int warp, int lane, float tol2, float fl,
+                                            float stop2 = 0.f) {
   constexpr int N = NV > 0 ? NV : 1;
   int nrot = 0;
   if (kind == 1) {
@@ -190,13 +194,13 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, float* __r
           float4 y[N];
           load_col<N>(ycol, ld, lane, y);
           float yb = nrm[bw + yslot];
-          if (rotate_regs<N>(x, y, xa, yb, tol2, fl)) {
+          if (const int rr = rotate_regs<N>(x, y, xa, yb, tol2, fl, stop2)) {
             store_col<N>(ycol, ld, lane, y);
             if (lane == 0) nrm[bw + yslot] = yb;
-            ++nrot;
+            nrot += rr;
           }
         } else {
-          nrot += rotate_smem(xcol, ycol, ld, lane, tol2, fl);
+          nrot += rotate_smem(xcol, ycol, ld, lane, tol2, fl, stop2);
         }
       }
       __syncthreads();
@@ -227,17 +231,17 @@ __device__ __forceinline__ int jacobi_block(float* __restrict__ cols, float* __r
           load_col<N>(xcol, ld, lane, x);
           load_col<N>(ycol, ld, lane, y);
           float xa = nrm[xi], yb = nrm[yi];
-          if (rotate_regs<N>(x, y, xa, yb, tol2, fl)) {
+          if (const int rr = rotate_regs<N>(x, y, xa, yb, tol2, fl, stop2)) {
             store_col<N>(xcol, ld, lane, x);
             store_col<N>(ycol, ld, lane, y);
             if (lane == 0) {
               nrm[xi] = xa;
               nrm[yi] = yb;
             }
-            ++nrot;
+            nrot += rr;
           }
         } else {
-          nrot += rotate_smem(xcol, ycol, ld, lane, tol2, fl);
+          nrot += rotate_smem(xcol, ycol, ld, lane, tol2, fl, stop2);
         }
       }
       __syncthreads();
