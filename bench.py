@@ -263,6 +263,9 @@ def run_ours(args):
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1) / args.steps
+    for n in admm._names:      # the host copy of Z (local and exchanged layers alike) is the device result
+        if not torch.equal(host_z[n], admm.z[n].cpu()):
+            raise SystemExit('bench.py: host Z of {} differs from the device tensor'.format(n))
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

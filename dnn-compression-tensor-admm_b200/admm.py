@@ -99,6 +99,7 @@ class ADMM:
         self.sweeps = {}
         self._shard = None
         self._streams = None
+        self._copy_stream = None
         self.concurrent_groups = True    # additive: False runs all TT layers as one lock-step plan
 
     # ------------------------------------------------------------------------------------------
@@ -193,18 +194,38 @@ class ADMM:
             self._shard = sharding.LayerSharding(self, self._names)
             self._plans = self._build_plans(self._shard.local_names)
         with torch.no_grad():
-            if _host_in is not None:      # parameters this rank does not project are only read by the dual update
-                local = set(self._shard.local_names)
-                for n in self._names:
-                    if n not in local:
-                        self._params[n].data.copy_(_host_in[n], non_blocking=True)
+            local = set(self._shard.local_names)
+            remote = [n for n in self._names if n not in local]
+            side = main = up_done = None
+            if remote and (_host_in is not None or _host_out is not None) and not rt.backend_is_emulated():
+                # parameters this rank does not project are only read by the dual update, and their Z arrives with
+                # the exchange: their transfers run on a copy stream of their own instead of delaying the local
+                # projection (they were 7/8 of the bytes on 8 GPUs)
+                dev = self._state_device()
+                main = torch.cuda.current_stream(dev)
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                side = self._copy_stream
+            if _host_in is not None and remote:
+                if side is not None:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        self._copy(_host_in, remote, True)
+                        up_done = torch.cuda.Event()
+                        up_done.record(side)
+                else:
+                    self._copy(_host_in, remote, True)
             self._run_plans(_host_in, _host_out)
             self._shard.exchange(self.z)
-            if _host_out is not None:
-                local = set(self._shard.local_names)
-                for n in self._names:
-                    if n not in local:
-                        _host_out[n].copy_(self.z[n], non_blocking=True)
+            if up_done is not None:
+                main.wait_event(up_done)
+            if _host_out is not None and remote:
+                if side is not None:
+                    side.wait_stream(main)                     # Z of the other ranks is complete after the exchange
+                    with torch.cuda.stream(side):
+                        self._copy(_host_out, remote, False)
+                else:
+                    self._copy(_host_out, remote, False)
             if update_u:
                 want_norm = self.log or self.verbose
                 sq = torch.zeros(len(self._names), dtype=torch.float64, device=self._state_device()) if want_norm else None
@@ -216,6 +237,8 @@ class ADMM:
                             self.logger[n].append(float(v))
                         if self.verbose:
                             print('*INFO: {} in ADMM, norm(w-z)={}'.format(n, v))
+            if side is not None:
+                main.wait_stream(side)       # the caller synchronises the current stream before reading host_z
 
     def _run_plans(self, host_in=None, host_out=None):
         """Z-update of the local layers.  Several TT plans (layer groups) are enqueued on side streams -- the
