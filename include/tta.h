@@ -113,7 +113,10 @@ int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_task* tasks_
  * Symmetric eigensolver: one-sided (Hestenes) block Jacobi on the columns of X = G
  * (replaces numpy.linalg.svd / LAPACK gesdd of ttd.py:17, admm.py:131,143 and tensorly partial_svd)
  * On return the columns of X are mutually orthogonal: x_j = lambda_j * v_j (column order arbitrary).
- * Synchronises `stream` at least once (convergence status is read back).
+ * X need not be G itself: any X = G * Q with Q orthogonal is a valid start (warm start from the eigenvectors of
+ * a previous, similar problem) -- the iteration converges to G * Q * J = V * Lambda all the same.
+ * Synchronises `stream` once when sweeps_out is given (convergence status is read back); see below for the
+ * enqueue-only mode.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   float* x;         /* kpad columns of length ld                       */
