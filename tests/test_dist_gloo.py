@@ -33,7 +33,14 @@ def _worker(rank, world, port, key, out_dir):
     a = ADMM(workloads.ParamBag(weights), 1e-3, hb(), fmt, 'cpu')
     a.update(update_u=False)
     a.update()
-    a.update()
+    # the last update goes through the host-buffer entry point: the parameters are zeroed first, so the result can
+    # only be right if update_from_host uploads the local AND the exchanged layers' weights
+    host_z = {n: torch.empty_like(w) for n, w in weights.items()}
+    for n, prm in a.model.named_parameters():
+        prm.data.zero_()
+    a.update_from_host(weights, host_z)
+    for n in names:
+        assert torch.equal(host_z[n], a.z[n]), n
     local = list(a._shard.local_names)
     np.savez(os.path.join(out_dir, 'rank{}.npz'.format(rank)), local=np.array(local),
              n_proj=np.array(fake.calls.count('jacobi')),
