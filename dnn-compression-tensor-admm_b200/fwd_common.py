@@ -305,6 +305,15 @@ def _pack_bf16(w):
     return m, ld
 
 
+def _mm_f32(a, b):
+    """bf16 x bf16 -> fp32 product (library GEMM): the token-dimension reductions of the weight gradients keep
+    their fp32 accumulator instead of being rounded to bf16 on store."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError, NotImplementedError):
+        return (a @ b).float()
+
+
 class LowRank2Fn(torch.autograd.Function):
     """Training path of the two-factor layers (backward of the fused forwards):
     y = (x W1^T) W2^T + bias with the forward AND the input gradient on the fused TMA + tcgen05 kernel.
@@ -354,10 +363,10 @@ class LowRank2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             v = torch.zeros(R, n1p, dtype=torch.bfloat16, device=dev)
             rt.gemm_bf16_tc(xb, w1b, v, R, N1, K1, lda=K1, ldb=ld1, ldc=n1p)          # V = x W1^T
-            dw2 = (dyb.t() @ v[:, :N1]).to(w2dt)
+            dw2 = _mm_f32(dyb.t(), v[:, :N1]).to(w2dt)
             dv = torch.zeros(R, n1p, dtype=torch.bfloat16, device=dev)
             rt.gemm_bf16_tc(dyb, w2t, dv, R, N1, N2, lda=N2, ldb=N2, ldc=n1p)         # dV = dY W2
-            dw1 = (dv[:, :N1].t() @ xb).to(w1dt)
+            dw1 = _mm_f32(dv[:, :N1].t(), xb).to(w1dt)
         db = dy.sum(0).to(bdt) if has_bias and ctx.needs_input_grad[3] else None
         return dx, dw1, dw2, db
 
