@@ -396,6 +396,15 @@ int tta_jacobi_eigh_batched(const tta_eig_task* tasks_dev, const tta_eig_task* t
     done_h[p] = status_h[p];
     all_done = all_done && status_h[p];
   }
+  if (n_legacy) {
+    // the multi-launch solver tracks convergence in done[]; mirror it into the status slots, which is what
+    // tta_jacobi_read_results (the plans' collect step) inspects
+    rc = check_cuda(cudaMemcpyAsync(cl_status, done_h.data(), n_tasks * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+                    "jacobi status upload");
+    if (rc) return rc;
+    rc = check_cuda(cudaStreamSynchronize(st), "jacobi status sync");
+    if (rc) return rc;
+  }
   if (sweeps_out) memcpy(sweeps_out, sweeps_h.data(), n_tasks * sizeof(int32_t));
   if (!all_done) {
     int bad = 0;

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "eig_device.cuh"
+#include "stream_pool.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -166,28 +167,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
   }
 }
 
-constexpr int kPoolStreams = 8;
-
-struct StreamPool {
-  cudaStream_t s[kPoolStreams] = {};
-  cudaEvent_t fork = nullptr;
-  cudaEvent_t join[kPoolStreams] = {};
-  int base_prio = 0, prio_lo = 0;
-  cudaStream_t get(int i) {
-    if (!s[i]) {
-      int prio = base_prio + i;
-      if (prio > prio_lo) prio = prio_lo;
-      if (cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
-      if (cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
-    return s[i];
-  }
-};
-
 // One pool per (device, calling stream): independent callers (the layer groups of admm.ADMM.update run on
 // their own streams) must not share internal streams, or the launches of one caller would queue behind
 // the other's in stream order although the problems are independent.
-static StreamPool* pool_for(int dev, cudaStream_t caller) {
+StreamPool* pool_for(int dev, cudaStream_t caller) {
   static std::map<std::pair<int, cudaStream_t>, StreamPool*> pools;
   const auto key = std::make_pair(dev, caller);
   auto it = pools.find(key);

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restri
       v = (float)s;
       if (tk.g64) tk.g64[(int64_t)row * tk.k + col] = s;
     }
-    tk.x[e] = v;
+    if (tk.x) tk.x[e] = v;
   }
 }
 
@@ -312,7 +312,7 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
     for (int t = 0; t < cnt; ++t) {
       const tta_gram_task& tk = tasks_host[first + t];
       if (tk.k <= 0 || tk.nb <= 0 || tk.nc <= 0 || tk.nsplit <= 0 || tk.ld < tk.k || tk.kpad < tk.k ||
-          (tk.ld & 3) || !tk.a || !tk.part || !tk.x) {
+          (tk.ld & 3) || !tk.a || !tk.part || (!tk.x && !tk.g64)) {
         set_error("gram: task %d invalid (k=%d nb=%d nc=%d nsplit=%d ld=%d kpad=%d)", first + t, tk.k, tk.nb,
                   tk.nc, tk.nsplit, tk.ld, tk.kpad);
         return TTA_E_INVALID;

@@ -153,13 +153,20 @@ __global__ void __launch_bounds__(256) refine_finalize_kernel(const tta_refine_t
   }
 }
 
-static int validate(const tta_refine_task* th, int n, const char* what) {
+static int validate(const tta_refine_task* th, int n, const char* what, bool finalize_only = false) {
   if (n < 0 || (n > 0 && !th)) {
     set_error("%s: bad task table", what);
     return TTA_E_INVALID;
   }
   for (int t = 0; t < n; ++t) {
     const tta_refine_task& tk = th[t];
+    if (finalize_only) {   // also the output stage of tta_symeig_top_batched: only e64 / lam / outputs are read
+      if (tk.k <= 0 || tk.r <= 0 || tk.r > tk.k || !tk.lam || !tk.e64 || !tk.e) {
+        set_error("%s: task %d invalid (k=%d r=%d)", what, t, tk.k, tk.r);
+        return TTA_E_INVALID;
+      }
+      continue;
+    }
     if (tk.k <= 0 || tk.r <= 0 || tk.r > tk.k || tk.wnd < tk.r || tk.wnd > tk.k || tk.ld < tk.k || !tk.x || !tk.qt ||
         !tk.s || !tk.t || !tk.c || !tk.lam || !tk.lam0 || !tk.e64 || !tk.e) {
       set_error("%s: task %d invalid (k=%d r=%d wnd=%d ld=%d)", what, t, tk.k, tk.r, tk.wnd, tk.ld);
@@ -218,7 +225,7 @@ int tta_refine_coeff_batched(const tta_refine_task* tasks_dev, const tta_refine_
 int tta_refine_finalize_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host, int n_tasks,
                                 void* stream) {
   using namespace tta;
-  int rc = validate(tasks_host, n_tasks, "refine_finalize");
+  int rc = validate(tasks_host, n_tasks, "refine_finalize", true);
   if (rc || n_tasks == 0) return rc;
   int mx = 0;
   for (int t = 0; t < n_tasks; ++t) mx = tasks_host[t].r > mx ? tasks_host[t].r : mx;

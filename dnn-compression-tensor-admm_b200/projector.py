@@ -124,6 +124,29 @@ def wave_makespan_ms(ks):
     return end
 
 
+TRD_MIN_K = 33          # k <= 32 stays on the one-CTA Jacobi solver (eig_cluster.cu)
+
+
+def default_solver():
+    """'trd' (fp64 tridiagonalisation route, csrc/trd.cu) or 'jacobi' (TTA_EIG_SOLVER=jacobi: the round-1 path)."""
+    return 'jacobi' if os.environ.get('TTA_EIG_SOLVER', 'trd').lower().startswith('j') else 'trd'
+
+
+_TRD_MAX_K = []
+
+
+def uses_trd(k, solver):
+    if solver != 'trd' or k < TRD_MIN_K:
+        return False
+    if not _TRD_MAX_K:
+        _TRD_MAX_K.append(rt.symeig_max_k())
+    return k <= _TRD_MAX_K[0]
+
+
+class EigClusterFlag(Exception):
+    """The fp64 solver met eigenvalues it cannot separate (status 1 of tta_symeig_task): rerun on the Jacobi solver."""
+
+
 def refine_window(k, r):
     """Rows of S / T the refinement forms: the r selectable vectors plus a margin that is far wider
     than the ordering error of the fp32 eigenvalue estimates (include/tta.h, tta_refine_task)."""
@@ -288,7 +311,7 @@ class TTProjectionPlan:
         self.refine = bool(refine)
         # A step that keeps r == min(m, n) singular triplets truncates nothing: U S V^T is the
         # unfolding itself, so the step is served by the exact factorisation A = I * A (m <= n) or
-        # A = A * I (m > n) without an eigensolve.  ttd.ten2tt switches this off to hand out
+        # A = A * I (m > n) without an eigensolve.  ttd.ten2tt passes skip_full_rank=False to hand out
         # orthonormal cores like the reference's SVD does; the product of the cores is the same.
         self.skip_full_rank = bool(skip_full_rank)
         self.sweeps = {}
@@ -302,6 +325,11 @@ class TTProjectionPlan:
         # nearly orthogonal already and the solver needs fewer sweeps.  Results are converged to the same
         # criterion either way.  TTA_WARM_START=0 disables it.
         self.warm_start = bool(refine) and os.environ.get('TTA_WARM_START', '1') != '0'
+        # eigensolver of the steps with 32 < k <= tta_symeig_max_k(): 'trd' = fp64 Householder tridiagonalisation +
+        # bisection + twisted factorisation (no refinement, no warm start needed), 'jacobi' = round-1 path.  A plan
+        # whose trd solve reports inseparable eigenvalues (exactly repeated singular values) switches to 'jacobi'.
+        self.solver = default_solver() if refine else 'jacobi'
+        self._last = None
         self._warm_valid = False
         self._warm_used = False      # the update being collected was warm-started
         self._cold_sweeps = {}       # (wave, slot) -> sweeps of the last cold solve
@@ -332,13 +360,22 @@ class TTProjectionPlan:
                     continue
                 ld, kpad, bw = eig_geometry(k)
                 nsplit = gram_splits(k, max(m, n))
-                st = dict(m=m, n=n, k=k, r=r, identity=False, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, A=carry,
-                          X=_Buf(ld * kpad, dev), part=_Buf(nsplit * k * k, dev, torch.float64),
+                trd = uses_trd(k, self.solver)
+                if trd:
+                    ld, kpad, bw = _round_up(k, 4), k, 0
+                st = dict(m=m, n=n, k=k, r=r, identity=False, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, A=carry, trd=trd,
+                          X=None if trd else _Buf(ld * kpad, dev), part=_Buf(nsplit * k * k, dev, torch.float64),
                           E=_Buf(r * k, dev), core=_Buf(m * r, dev), carry=_Buf(r * n, dev))
                 if m > n:
                     st['sigma'] = _Buf(r, dev)
                     st['isigma'] = _Buf(r, dev)
-                if self.refine:
+                if trd:
+                    f64 = torch.float64
+                    st['g64'] = _Buf(k * k, dev, f64)
+                    st['work'] = _Buf(rt.symeig_work_doubles(k, r), dev, f64)
+                    st['e64'] = _Buf(r * k, dev, f64)
+                    st['lam'] = _Buf(r, dev, f64)
+                elif self.refine:
                     f64 = torch.float64
                     wnd = refine_window(k, r)
                     st['wnd'] = wnd
@@ -430,60 +467,82 @@ class TTProjectionPlan:
         nwaves, sched = self._schedule()
         for wv in range(nwaves):
             members = [(li, i) for li in range(nL) for i, w_ in sched[li].items() if w_ == wv]
+            steps = [self.ws[li]['steps'][si] for li, si in members]
             idx = [li for li, _ in members]
+            jq = [q for q, st in enumerate(steps) if not st['trd']]        # Jacobi (+ refinement) members
+            tq = sorted((q for q, st in enumerate(steps) if st['trd']), key=lambda q: -steps[q]['k'])   # fp64 solver
             g = np.zeros(len(idx), dtype=rt.GRAM_TASK)
-            e = np.zeros(len(idx), dtype=rt.EIG_TASK)
-            s = np.zeros(len(idx), dtype=rt.SELECT_TASK)
             mm = np.zeros(len(idx), dtype=rt.GEMM_TASK)
-            rf = np.zeros(len(idx), dtype=rt.REFINE_TASK)
-            dg = [np.zeros(len(idx), dtype=rt.GEMM_TASK) for _ in range(4)]
-            wg = np.zeros(len(idx), dtype=rt.GEMM_TASK)
-            for q, (li, si) in enumerate(members):
-                st = self.ws[li]['steps'][si]
+            sel = np.zeros(len(idx), dtype=rt.SELECT_TASK)
+            for q, st in enumerate(steps):
                 m, n, k, r = st['m'], st['n'], st['k'], st['r']
                 a = st['A'].ptr
-                g64 = st['g64'].ptr if self.refine else 0
+                x = st['X'].ptr if st['X'] is not None else 0
+                g64 = st['g64'].ptr if 'g64' in st else 0
                 if m <= n:   # row Gram A A^T
-                    g[q] = (a, st['part'].ptr, st['X'].ptr, g64, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'])
-                    s[q] = (st['X'].ptr, st['E'].ptr, st['core'].ptr, 0, 0, 0, k, st['ld'], r, 0)
+                    g[q] = (a, st['part'].ptr, x, g64, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'])
+                    sel[q] = (x, st['E'].ptr, st['core'].ptr, 0, 0, 0, k, st['ld'], r, 0)
                     # carry' (r x n) = E (r x m) * A (m x n)
                     mm[q] = (st['E'].ptr, a, st['carry'].ptr, 0, m, 1, n, 1, n, r, n, m, 0)
                 else:        # column Gram A^T A
-                    g[q] = (a, st['part'].ptr, st['X'].ptr, g64, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'])
-                    s[q] = (st['X'].ptr, st['E'].ptr, 0, st['carry'].ptr, st['sigma'].ptr, st['isigma'].ptr,
-                            k, st['ld'], r, 0)
+                    g[q] = (a, st['part'].ptr, x, g64, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'])
+                    sel[q] = (x, st['E'].ptr, 0, st['carry'].ptr, st['sigma'].ptr, st['isigma'].ptr,
+                              k, st['ld'], r, 0)
                     # core (m x r) = A (m x n) * E^T (n x r) * diag(1/sigma)
                     mm[q] = (a, st['E'].ptr, st['core'].ptr, st['isigma'].ptr, n, 1, 1, n, r, m, r, n, 0)
-                e[q] = (st['X'].ptr, k, st['ld'], st['kpad'], st['bw'])
+            # -- Jacobi members --
+            nj = len(jq)
+            e = np.zeros(nj, dtype=rt.EIG_TASK)
+            rf = np.zeros(nj, dtype=rt.REFINE_TASK)
+            dg = [np.zeros(nj, dtype=rt.GEMM_TASK) for _ in range(4)]
+            wg = np.zeros(nj, dtype=rt.GEMM_TASK)
+            for jj, q in enumerate(jq):
+                st = steps[q]
+                k, r = st['k'], st['r']
+                e[jj] = (st['X'].ptr, k, st['ld'], st['kpad'], st['bw'])
                 if self.refine:
-                    sel = s[q]
+                    sl = sel[q]
                     wnd = st['wnd']
-                    rf[q] = (st['X'].ptr, st['qt'].ptr, st['s'].ptr, st['t'].ptr, st['c'].ptr, st['lam'].ptr,
-                             st['lam0'].ptr, st['e64'].ptr, sel['e'], sel['et'], sel['se'], sel['sigma'],
-                             sel['isigma'], k, st['ld'], r, wnd)
+                    rf[jj] = (st['X'].ptr, st['qt'].ptr, st['s'].ptr, st['t'].ptr, st['c'].ptr, st['lam'].ptr,
+                              st['lam0'].ptr, st['e64'].ptr, sl['e'], sl['et'], sl['se'], sl['sigma'],
+                              sl['isigma'], k, st['ld'], r, wnd)
                     qt = st['qt'].ptr
-                    dg[0][q] = (qt, st['g64'].ptr, st['y'].ptr, 0, k, 1, k, 1, k, wnd, k, k, 0)    # y = qt[:wnd] * g64
-                    dg[1][q] = (st['y'].ptr, qt, st['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)      # s = y * qt^T
-                    dg[2][q] = (qt, qt, st['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)               # t = qt[:wnd] * qt^T
-                    dg[3][q] = (st['c'].ptr, qt, st['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)      # e64 = c * qt
+                    dg[0][jj] = (qt, st['g64'].ptr, st['y'].ptr, 0, k, 1, k, 1, k, wnd, k, k, 0)    # y = qt[:wnd] * g64
+                    dg[1][jj] = (st['y'].ptr, qt, st['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)      # s = y * qt^T
+                    dg[2][jj] = (qt, qt, st['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)               # t = qt[:wnd] * qt^T
+                    dg[3][jj] = (st['c'].ptr, qt, st['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)      # e64 = c * qt
                     # warm start: X (column j at x + j*ld, fp32) = G q_j, i.e. rows of qt * g64 (G symmetric)
                     # guarded by the smallest eigenvalue estimate of the previous solve (lam0 is sorted, descending):
                     # a null column is stored as a zero row of qt, and a rank-deficient start could not recover
                     # directions that become non-null later -- such a problem starts cold (X = G stays in place)
-                    wg[q] = (qt, st['g64'].ptr, st['X'].ptr, st['lam0'].ptr + 8 * (k - 1), k, 1, k, 1, st['ld'], k, k, k,
-                             rt.GEMM_STORE_F32 | rt.GEMM_GUARD)
-            wave = dict(idx=idx, gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev),
-                        select=rt.TaskTable(s, dev), gemm=rt.TaskTable(mm, dev))
+                    wg[jj] = (qt, st['g64'].ptr, st['X'].ptr, st['lam0'].ptr + 8 * (k - 1), k, 1, k, 1, st['ld'], k, k, k,
+                              rt.GEMM_STORE_F32 | rt.GEMM_GUARD)
+            # -- fp64 tridiagonalisation members (sorted by descending k: equal cluster sizes are adjacent) --
+            nt = len(tq)
+            sy = np.zeros(nt, dtype=rt.SYMEIG_TASK)
+            fin = np.zeros(nt, dtype=rt.REFINE_TASK)
+            status = torch.zeros(max(nt, 1), dtype=torch.int32, device=dev)
+            for tt, q in enumerate(tq):
+                st = steps[q]
+                sl = sel[q]
+                sy[tt] = (st['g64'].ptr, st['work'].ptr, st['lam'].ptr, st['e64'].ptr, status.data_ptr() + 4 * tt,
+                          st['k'], st['r'])
+                fin[tt] = (0, 0, 0, 0, 0, st['lam'].ptr, 0, st['e64'].ptr, sl['e'], sl['et'], sl['se'], sl['sigma'],
+                           sl['isigma'], st['k'], st['ld'], st['r'], st['r'])
+            wave = dict(idx=idx, jidx=[idx[q] for q in jq], tidx=[idx[q] for q in tq],
+                        gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev),
+                        select=rt.TaskTable(sel[jq] if nj else sel[:0], dev), gemm=rt.TaskTable(mm, dev),
+                        symeig=rt.TaskTable(sy, dev), symfin=rt.TaskTable(fin, dev), status=status)
             if self.refine:
                 wave['refine'] = rt.TaskTable(rf, dev)
                 wave['dgemm_ys_t'] = rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev)   # independent: one launch
                 wave['dgemm_s'] = rt.TaskTable(dg[1], dev)
                 wave['dgemm_e'] = rt.TaskTable(dg[3], dev)
                 wave['warm_rows'] = wg
-                keep = [q for q in range(len(idx)) if (wv, q) not in self._nowarm]
+                keep = [q for q in range(nj) if (wv, q) not in self._nowarm]
                 wave['warm_q'] = keep
                 wave['warm'] = rt.TaskTable(wg[keep], dev)
-            nbytes = rt.jacobi_scratch_bytes(wave['eig'])
+            nbytes = rt.jacobi_scratch_bytes(wave['eig']) if nj else 0
             wave['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
             self.waves.append(wave)
 
@@ -519,6 +578,7 @@ class TTProjectionPlan:
     def enqueue(self, w_list, u_list, z_list):
         """Enqueue the whole projection on the current stream; no host synchronisation."""
         self.bind(w_list, u_list, z_list)
+        self._last = (w_list, u_list, z_list)
         ph = _Phases(self.profile)
         tr = self.trace            # None, or a list that receives (label, CUDA event) marks of this stream (diagnostics)
 
@@ -536,22 +596,28 @@ class TTProjectionPlan:
         for wi, wave in enumerate(self.waves):
             ph.mark('gram')
             rt.gram(wave['gram'])
-            if warm and wave['warm'].n:
-                rt.gemm_f64(wave['warm'])
             mark('w{} eig begin'.format(wi))
             ph.mark('eig')
-            rt.jacobi_eigh_async(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
+            if wave['symeig'].n:
+                rt.symeig_top(wave['symeig'])
+            if wave['eig'].n:
+                if warm and wave['warm'].n:
+                    rt.gemm_f64(wave['warm'])
+                rt.jacobi_eigh_async(wave['eig'], wave['scratch'], self.tol, self.max_sweeps)
             mark('w{} eig end'.format(wi))
             ph.mark('select')
-            if self.refine:
-                rt.refine_prepare(wave['refine'])
-                rt.gemm_f64(wave['dgemm_ys_t'])
-                rt.gemm_f64(wave['dgemm_s'])
-                rt.refine_coeff(wave['refine'])
-                rt.gemm_f64(wave['dgemm_e'])
-                rt.refine_finalize(wave['refine'])
-            else:
-                rt.select(wave['select'])
+            if wave['symeig'].n:
+                rt.refine_finalize(wave['symfin'])
+            if wave['eig'].n:
+                if self.refine:
+                    rt.refine_prepare(wave['refine'])
+                    rt.gemm_f64(wave['dgemm_ys_t'])
+                    rt.gemm_f64(wave['dgemm_s'])
+                    rt.refine_coeff(wave['refine'])
+                    rt.gemm_f64(wave['dgemm_e'])
+                    rt.refine_finalize(wave['refine'])
+                else:
+                    rt.select(wave['select'])
             ph.mark('project')
             rt.gemm(wave['gemm'])
         ph.mark('recon')
@@ -566,26 +632,36 @@ class TTProjectionPlan:
     def collect(self):
         """The one host synchronisation of an update: sweep counts / convergence status of every wave."""
         self.sweeps = {}
-        live = [w for w in self.waves if w['eig'].n]
+        live = [w for w in self.waves if w['eig'].n or w['symeig'].n]
         if not live:
             return
-        flat = torch.cat([w['scratch'][:6 * w['eig'].n] for w in live]).cpu().numpy()     # one D2H copy per plan
+        parts = []
+        for w in live:
+            parts.append(w['scratch'][:6 * w['eig'].n])
+            parts.append(w['status'][:w['symeig'].n])
+        flat = torch.cat(parts).cpu().numpy()     # one D2H copy per plan
         off = 0
+        flagged = False
         for wi, wave in enumerate(self.waves):
-            if not wave['eig'].n:
+            nj, nt = wave['eig'].n, wave['symeig'].n
+            if not (nj or nt):
                 continue
-            n6 = 6 * wave['eig'].n
-            sw = rt.jacobi_results_from_host(flat[off:off + n6], wave['eig'], self.max_sweeps)
+            n6 = 6 * nj
+            sw = rt.jacobi_results_from_host(flat[off:off + n6], wave['eig'], self.max_sweeps) if nj else []
             off += n6
-            for q, li in enumerate(wave['idx']):
+            flagged = flagged or bool(np.any(flat[off:off + nt] != 0))
+            off += nt
+            for q, li in enumerate(wave['jidx']):
                 self.sweeps.setdefault(self.layers[li].name, []).append(int(sw[q]))
-            if self.refine:
+            for li in wave['tidx']:
+                self.sweeps.setdefault(self.layers[li].name, []).append(0)
+            if self.refine and nj:
                 # adaptive warm start: the G * Q_prev product costs 2 k^3 fp64 flops per problem; a problem whose
                 # sweep count barely drops (unstable eigenvectors: flat spectrum, basis changes upstream in the TT
                 # chain) goes back to the cold start: two such updates in a row -> 16 cold updates, then it is probed again
                 warmed = set(wave['warm_q']) if self._warm_used else set()
                 dirty = False
-                for q in range(len(wave['idx'])):
+                for q in range(nj):
                     key = (wi, q)
                     if q not in warmed:
                         self._cold_sweeps[key] = int(sw[q])
@@ -603,9 +679,18 @@ class TTProjectionPlan:
                     else:
                         self._strikes[key] = 0
                 if dirty:
-                    keep = [q for q in range(len(wave['idx'])) if (wi, q) not in self._nowarm]
+                    keep = [q for q in range(nj) if (wi, q) not in self._nowarm]
                     wave['warm_q'] = keep
                     wave['warm'] = rt.TaskTable(wave['warm_rows'][keep], self.device)
+        if flagged:
+            # exactly repeated singular values (structured weights): the twisted factorisation may have returned
+            # parallel vectors for them.  This plan moves to the Jacobi solver for good and redoes the update.
+            self.solver = 'jacobi'
+            self._bound = None
+            self._cold_sweeps, self._nowarm, self._strikes = {}, {}, {}
+            self._alloc()
+            self.enqueue(*self._last)
+            return self.collect()
         self._warm_valid = True
 
     def cores(self, li):
@@ -625,17 +710,19 @@ class TTProjectionPlan:
 # Tucker-2 (HOOI) projection                                   admm.py:113-127 -> tensorly partial_tucker
 # ==================================================================================================
 class EigBatch:
-    """Gram -> Jacobi -> fp64 refinement -> dominant-r selection for a list of independent problems.
+    """Gram -> dominant-r eigenvectors for a list of independent problems: the fp64 tridiagonalisation solver
+    (33 <= k <= tta_symeig_max_k()) or Jacobi -> fp64 refinement -> selection (everything else).
 
     Each problem: dict(a=ptr, k=, r=, si=, sb=, sc=, nb=, nc=) describing the Gram operand as in
     include/tta.h (tta_gram_task); outputs E (r x k, rows = dominant eigenvectors) and optionally ET.
     """
 
-    def __init__(self, device, tol=5e-7, max_sweeps=40):
+    def __init__(self, device, tol=5e-7, max_sweeps=40, solver=None):
         self.device = device
         self.tol = tol
         self.max_sweeps = max_sweeps
         self.warm_start = os.environ.get('TTA_WARM_START', '1') != '0'
+        self.solver = solver or default_solver()
         self.bufs = {}
         self.tables = {}
 
@@ -643,16 +730,23 @@ class EigBatch:
         if key in self.bufs:
             return self.bufs[key]
         dev = self.device
-        ld, kpad, bw = eig_geometry(k)
         nsplit = gram_splits(k, red_len)
         f64 = torch.float64
-        wnd = refine_window(k, r)
-        b = dict(k=k, r=r, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, wnd=wnd, X=_Buf(ld * kpad, dev),
-                 part=_Buf(nsplit * k * k, dev, f64), E=_Buf(r * k, dev),
-                 ET=_Buf(r * k, dev) if want_et else None,
-                 g64=_Buf(k * k, dev, f64), qt=_Buf(k * k, dev, f64), y=_Buf(wnd * k, dev, f64),
-                 s=_Buf(wnd * k, dev, f64), t=_Buf(wnd * k, dev, f64), c=_Buf(r * k, dev, f64),
-                 e64=_Buf(r * k, dev, f64), lam=_Buf(r, dev, f64), lam0=_Buf(k, dev, f64))
+        if uses_trd(k, self.solver):
+            b = dict(k=k, r=r, ld=_round_up(k, 4), kpad=k, bw=0, nsplit=nsplit, trd=True, X=None,
+                     part=_Buf(nsplit * k * k, dev, f64), E=_Buf(r * k, dev),
+                     ET=_Buf(r * k, dev) if want_et else None, g64=_Buf(k * k, dev, f64),
+                     work=_Buf(rt.symeig_work_doubles(k, r), dev, f64), e64=_Buf(r * k, dev, f64),
+                     lam=_Buf(r, dev, f64))
+        else:
+            ld, kpad, bw = eig_geometry(k)
+            wnd = refine_window(k, r)
+            b = dict(k=k, r=r, ld=ld, kpad=kpad, bw=bw, nsplit=nsplit, wnd=wnd, trd=False, X=_Buf(ld * kpad, dev),
+                     part=_Buf(nsplit * k * k, dev, f64), E=_Buf(r * k, dev),
+                     ET=_Buf(r * k, dev) if want_et else None,
+                     g64=_Buf(k * k, dev, f64), qt=_Buf(k * k, dev, f64), y=_Buf(wnd * k, dev, f64),
+                     s=_Buf(wnd * k, dev, f64), t=_Buf(wnd * k, dev, f64), c=_Buf(r * k, dev, f64),
+                     e64=_Buf(r * k, dev, f64), lam=_Buf(r, dev, f64), lam0=_Buf(k, dev, f64))
         self.bufs[key] = b
         return b
 
@@ -663,68 +757,102 @@ class EigBatch:
         dev = self.device
         n = len(problems)
         g = np.zeros(n, dtype=rt.GRAM_TASK)
-        e = np.zeros(n, dtype=rt.EIG_TASK)
-        rf = np.zeros(n, dtype=rt.REFINE_TASK)
-        dg = [np.zeros(n, dtype=rt.GEMM_TASK) for _ in range(4)]
-        wg = np.zeros(n, dtype=rt.GEMM_TASK)
         for q, (b, op) in enumerate(problems):
+            g[q] = (op['a'], b['part'].ptr, b['X'].ptr if b['X'] is not None else 0, b['g64'].ptr, op['si'], op['sb'],
+                    op['sc'], b['k'], op['nb'], op['nc'], b['nsplit'], b['ld'], b['kpad'])
+        jq = [q for q, (b, _) in enumerate(problems) if not b['trd']]
+        tq = sorted((q for q, (b, _) in enumerate(problems) if b['trd']), key=lambda q: -problems[q][0]['k'])
+        nj, nt = len(jq), len(tq)
+        e = np.zeros(nj, dtype=rt.EIG_TASK)
+        rf = np.zeros(nj, dtype=rt.REFINE_TASK)
+        dg = [np.zeros(nj, dtype=rt.GEMM_TASK) for _ in range(4)]
+        wg = np.zeros(nj, dtype=rt.GEMM_TASK)
+        for jj, q in enumerate(jq):
+            b = problems[q][0]
             k, r = b['k'], b['r']
-            g[q] = (op['a'], b['part'].ptr, b['X'].ptr, b['g64'].ptr, op['si'], op['sb'], op['sc'], k,
-                    op['nb'], op['nc'], b['nsplit'], b['ld'], b['kpad'])
-            e[q] = (b['X'].ptr, k, b['ld'], b['kpad'], b['bw'])
+            e[jj] = (b['X'].ptr, k, b['ld'], b['kpad'], b['bw'])
             wnd = b['wnd']
-            rf[q] = (b['X'].ptr, b['qt'].ptr, b['s'].ptr, b['t'].ptr, b['c'].ptr, b['lam'].ptr, b['lam0'].ptr,
-                     b['e64'].ptr, b['E'].ptr, b['ET'].ptr if b['ET'] is not None else 0, 0, 0, 0, k, b['ld'], r, wnd)
+            rf[jj] = (b['X'].ptr, b['qt'].ptr, b['s'].ptr, b['t'].ptr, b['c'].ptr, b['lam'].ptr, b['lam0'].ptr,
+                      b['e64'].ptr, b['E'].ptr, b['ET'].ptr if b['ET'] is not None else 0, 0, 0, 0, k, b['ld'], r, wnd)
             qt = b['qt'].ptr
-            dg[0][q] = (qt, b['g64'].ptr, b['y'].ptr, 0, k, 1, k, 1, k, wnd, k, k, 0)
-            dg[1][q] = (b['y'].ptr, qt, b['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
-            dg[2][q] = (qt, qt, b['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
-            dg[3][q] = (b['c'].ptr, qt, b['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)
+            dg[0][jj] = (qt, b['g64'].ptr, b['y'].ptr, 0, k, 1, k, 1, k, wnd, k, k, 0)
+            dg[1][jj] = (b['y'].ptr, qt, b['s'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
+            dg[2][jj] = (qt, qt, b['t'].ptr, 0, k, 1, 1, k, k, wnd, k, k, 0)
+            dg[3][jj] = (b['c'].ptr, qt, b['e64'].ptr, 0, k, 1, k, 1, k, r, k, k, 0)
             # warm start X = G Q_prev (see TTProjectionPlan), guarded by the smallest previous eigenvalue estimate
-            wg[q] = (qt, b['g64'].ptr, b['X'].ptr, b['lam0'].ptr + 8 * (k - 1), k, 1, k, 1, b['ld'], k, k, k,
-                     rt.GEMM_STORE_F32 | rt.GEMM_GUARD)
-        tabs = dict(gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev), refine=rt.TaskTable(rf, dev),
+            wg[jj] = (qt, b['g64'].ptr, b['X'].ptr, b['lam0'].ptr + 8 * (k - 1), k, 1, k, 1, b['ld'], k, k, k,
+                      rt.GEMM_STORE_F32 | rt.GEMM_GUARD)
+        sy = np.zeros(nt, dtype=rt.SYMEIG_TASK)
+        fin = np.zeros(nt, dtype=rt.REFINE_TASK)
+        status = torch.zeros(max(nt, 1), dtype=torch.int32, device=dev)
+        for tt, q in enumerate(tq):
+            b = problems[q][0]
+            sy[tt] = (b['g64'].ptr, b['work'].ptr, b['lam'].ptr, b['e64'].ptr, status.data_ptr() + 4 * tt, b['k'], b['r'])
+            fin[tt] = (0, 0, 0, 0, 0, b['lam'].ptr, 0, b['e64'].ptr, b['E'].ptr, b['ET'].ptr if b['ET'] is not None else 0,
+                       0, 0, 0, b['k'], b['ld'], b['r'], b['r'])
+        tabs = dict(n=n, jq=jq, tq=tq, gram=rt.TaskTable(g, dev), eig=rt.TaskTable(e, dev), refine=rt.TaskTable(rf, dev),
                     d_yt=rt.TaskTable(np.concatenate([dg[0], dg[2]]), dev), d_s=rt.TaskTable(dg[1], dev),
                     d_e=rt.TaskTable(dg[3], dev), warm=rt.TaskTable(wg, dev),
-                    big=any(b['k'] > 512 for b, _ in problems))
-        nbytes = rt.jacobi_scratch_bytes(tabs['eig'])
+                    symeig=rt.TaskTable(sy, dev), symfin=rt.TaskTable(fin, dev), status=status,
+                    big=any(problems[q][0]['k'] > 512 for q in jq))
+        nbytes = rt.jacobi_scratch_bytes(tabs['eig']) if nj else 0
         tabs['scratch'] = torch.empty(max(nbytes // 4 + 16, 16), dtype=torch.int32, device=dev)
         self.tables[sig] = tabs
         return tabs
+
+    def _refine(self, tabs):
+        rt.refine_prepare(tabs['refine'])
+        rt.gemm_f64(tabs['d_yt'])
+        rt.gemm_f64(tabs['d_s'])
+        rt.refine_coeff(tabs['refine'])
+        rt.gemm_f64(tabs['d_e'])
+        rt.refine_finalize(tabs['refine'])
 
     def enqueue(self, tabs, warm=False):
         """Same as `run` without the host synchronisation; sweep counts via `results(tabs)` after a sync.
         warm: start the Jacobi iteration from G * (eigenvectors of the previous solve in the same buffers) -- the
         Gram matrices of successive HOOI sweeps differ less and less, so the later sweeps need 2-3 Jacobi sweeps."""
         rt.gram(tabs['gram'])
+        if tabs['symeig'].n:
+            rt.symeig_top(tabs['symeig'])
+            rt.refine_finalize(tabs['symfin'])
+        if not tabs['eig'].n:
+            return
         if warm and self.warm_start:
             rt.gemm_f64(tabs['warm'])
         if tabs['big']:      # k > 512: the multi-launch solver synchronises per sweep and reports through the call
             tabs['_sweeps'] = rt.jacobi_eigh(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
         else:
             rt.jacobi_eigh_async(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
-        rt.refine_prepare(tabs['refine'])
-        rt.gemm_f64(tabs['d_yt'])
-        rt.gemm_f64(tabs['d_s'])
-        rt.refine_coeff(tabs['refine'])
-        rt.gemm_f64(tabs['d_e'])
-        rt.refine_finalize(tabs['refine'])
+        self._refine(tabs)
+
+    def _merge(self, tabs, jac_sweeps):
+        """Sweep counts in problem order (0 for the fp64 solver); raises EigClusterFlag on a reported cluster."""
+        if tabs['symeig'].n:
+            if bool(tabs['status'][:tabs['symeig'].n].ne(0).any().item()):
+                raise EigClusterFlag()
+        out = np.zeros(tabs['n'], dtype=np.int32)
+        for jj, q in enumerate(tabs['jq']):
+            out[q] = int(jac_sweeps[jj])
+        return out
 
     def results(self, tabs):
+        if not tabs['eig'].n:
+            return self._merge(tabs, [])
         if tabs['big']:
-            return tabs['_sweeps']
-        return rt.jacobi_results(tabs['eig'], tabs['scratch'], self.max_sweeps)
+            return self._merge(tabs, tabs['_sweeps'])
+        return self._merge(tabs, rt.jacobi_results(tabs['eig'], tabs['scratch'], self.max_sweeps))
 
     def run(self, tabs):
         rt.gram(tabs['gram'])
-        sweeps = rt.jacobi_eigh(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
-        rt.refine_prepare(tabs['refine'])
-        rt.gemm_f64(tabs['d_yt'])
-        rt.gemm_f64(tabs['d_s'])
-        rt.refine_coeff(tabs['refine'])
-        rt.gemm_f64(tabs['d_e'])
-        rt.refine_finalize(tabs['refine'])
-        return sweeps
+        if tabs['symeig'].n:
+            rt.symeig_top(tabs['symeig'])
+            rt.refine_finalize(tabs['symfin'])
+        sweeps = []
+        if tabs['eig'].n:
+            sweeps = rt.jacobi_eigh(tabs['eig'], tabs['scratch'], self.tol, self.max_sweeps)
+            self._refine(tabs)
+        return self._merge(tabs, sweeps)
 
 
 class TKLayer:
@@ -763,11 +891,15 @@ class TKProjectionPlan:
         self.device = torch.device(device)
         self.n_iter_max = int(n_iter_max)
         self.hooi_tol = float(hooi_tol)
-        self.eig = EigBatch(self.device, tol, max_sweeps)
+        self.tol, self.max_sweeps = tol, max_sweeps
         self.sweeps = {}
         self.hooi_sweeps = {}
         self.errors = {}
         self.profile = None
+        self._alloc(None)
+
+    def _alloc(self, solver):
+        self.eig = EigBatch(self.device, self.tol, self.max_sweeps, solver)
         self._bound = None
         dev = self.device
         self.ws = []
@@ -836,6 +968,14 @@ class TKProjectionPlan:
         return self.eig.build((which, active), probs)
 
     def run(self, w_list, u_list, z_list):
+        try:
+            self._run(w_list, u_list, z_list)
+        except EigClusterFlag:
+            # exactly repeated singular values: redo the projection on the Jacobi solver, and stay there
+            self._alloc('jacobi')
+            self._run(w_list, u_list, z_list)
+
+    def _run(self, w_list, u_list, z_list):
         self.bind(w_list, u_list, z_list)
         n = len(self.layers)
         everyone = tuple(range(n))

@@ -43,10 +43,14 @@ REFINE_TASK = np.dtype([('x', P), ('qt', P), ('s', P), ('t', P), ('c', P), ('lam
                         ('e', P), ('et', P), ('se', P), ('sigma', P), ('isigma', P), ('k', np.int32),
                         ('ld', np.int32), ('r', np.int32), ('wnd', np.int32)], align=True)
 
+SYMEIG_TASK = np.dtype([('g', P), ('work', P), ('lam', P), ('e64', P), ('status', P), ('k', np.int32), ('r', np.int32)],
+                       align=True)
+
 STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.itemsize,
                 'tta_gram_task': GRAM_TASK.itemsize, 'tta_eig_task': EIG_TASK.itemsize,
                 'tta_select_task': SELECT_TASK.itemsize, 'tta_gemm_task': GEMM_TASK.itemsize,
-                'tta_sqnorm_task': SQNORM_TASK.itemsize, 'tta_refine_task': REFINE_TASK.itemsize}
+                'tta_sqnorm_task': SQNORM_TASK.itemsize, 'tta_refine_task': REFINE_TASK.itemsize,
+                'tta_symeig_task': SYMEIG_TASK.itemsize}
 
 EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_device', 'tta_jacobi_profile_enable',
            'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch', 'tta_jacobi_enable_gra',
@@ -57,7 +61,7 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
            'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd',
-           'tta_lowrank2_fwd']
+           'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k']
 
 
 class TtaError(RuntimeError):
@@ -119,8 +123,11 @@ def _load():
     lib.tta_select_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_gemm_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_sqnorm_batched.argtypes = [vp, vp, ci, vp, vp]
+    lib.tta_symeig_work_doubles.argtypes = [ci, ci]
+    lib.tta_symeig_work_doubles.restype = cs
+    lib.tta_symeig_max_k.argtypes = []
     for nm in ('tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
-               'tta_refine_finalize_batched'):
+               'tta_refine_finalize_batched', 'tta_symeig_top_batched'):
         getattr(lib, nm).argtypes = [vp, vp, ci, vp]
     i64 = ctypes.c_int64
     lib.tta_gemm_bf16_tc.argtypes = [vp, i64, vp, i64, vp, i64, ci, ci, ci, vp, ci, vp]
@@ -132,7 +139,7 @@ def _load():
     lib.tta_ttconv_fused_fwd.argtypes = [vp] * 6 + [ci] * 10 + [vp]
     lib.tta_lowrank2_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, ci, i64, ci, ci, ci, vp]
     for name in EXPORTS:
-        if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count',
+        if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count', 'tta_symeig_work_doubles',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
                         'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc'):
             getattr(lib, name).restype = ci
@@ -293,6 +300,19 @@ def refine_coeff(tab):
 def refine_finalize(tab):
     _check(lib().tta_refine_finalize_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()),
            'tta_refine_finalize_batched')
+
+
+def symeig_top(tab):
+    """fp64 dominant-r eigensolver (tridiagonalisation route) for every task of the table; enqueue only."""
+    _check(lib().tta_symeig_top_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()), 'tta_symeig_top_batched')
+
+
+def symeig_work_doubles(k, r):
+    return int(lib().tta_symeig_work_doubles(int(k), int(r)))
+
+
+def symeig_max_k():
+    return int(lib().tta_symeig_max_k())
 
 
 def _p(t):

@@ -28,12 +28,16 @@ def ten2tt(x, tt_shapes, tt_ranks):
     x = np.ascontiguousarray(x, dtype=np.float32)
     numel = int(x.size)
     layer = projector.TTLayer('ten2tt', (shapes[0], numel // shapes[0]), shapes, list(tt_ranks))
-    for i, r in enumerate(layer.ranks):   # in-place clip, ttd.py:18-19
-        tt_ranks[i] = r
+    for i, r in enumerate(layer.ranks):   # in-place clip, ttd.py:18-19: only a clipped entry is written (a tuple
+        if int(tt_ranks[i]) != r:         # raises TypeError exactly when the reference would)
+            tt_ranks[i] = r
     dev = _device()
     xt = torch.from_numpy(x.reshape(shapes[0], -1)).to(dev).contiguous()
     zt = torch.empty_like(xt)
-    plan = projector.TTProjectionPlan([layer], dev)
+    # skip_full_rank off: a step that keeps every singular triplet still gets its eigensolve, so that core i
+    # reshaped to (r_i * s_i, r_{i+1}) has orthonormal columns like the U of ttd.py:21-25 (the projection plans of
+    # admm.py serve such steps by A = I * A, which gives the same product but identity / raw-carry cores)
+    plan = projector.TTProjectionPlan([layer], dev, skip_full_rank=False)
     plan.run([xt], [None], [zt])
     return [c.detach().cpu().numpy().copy() for c in plan.cores(0)]
 

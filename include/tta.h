@@ -99,8 +99,8 @@ int tta_fold_store_batched(const tta_fold_task* tasks_dev, const tta_fold_task* 
 typedef struct {
   const float* a;
   double* part;
-  float* x;
-  double* g64; /* nullable: G as a k x k row-major fp64 matrix (input of the refinement step) */
+  float* x;    /* nullable when g64 is given (the fp64 eigensolver reads g64 only) */
+  double* g64; /* nullable: G as a k x k row-major fp64 matrix (input of the refinement step / tta_symeig_top_batched) */
   int64_t si, sb, sc;
   int32_t k, nb, nc, nsplit;
   int32_t ld, kpad;
@@ -246,6 +246,36 @@ int tta_refine_coeff_batched(const tta_refine_task* tasks_dev, const tta_refine_
                              int n_tasks, void* stream);
 int tta_refine_finalize_batched(const tta_refine_task* tasks_dev, const tta_refine_task* tasks_host,
                                 int n_tasks, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dominant-r symmetric eigensolver in fp64 (replaces numpy.linalg.svd / LAPACK gesdd of ttd.py:17,
+ * admm.py:131,143 and tensorly's partial_svd behind admm.py:116,124 for 3 <= k <= tta_symeig_max_k()):
+ * Householder tridiagonalisation of G on a thread-block cluster, multisection on the Sturm count for the r
+ * largest eigenvalues, twisted factorisation for their eigenvectors, back-transformation.  Everything is
+ * fp64, so no refinement step follows; tta_refine_finalize_batched (only its e64 / lam / k / r / output
+ * fields are read) converts the result into the fp32 outputs of the projection.
+ *   g      k x k row-major fp64, symmetric (tta_gram_task.g64); not modified
+ *   work   tta_symeig_work_doubles(k, r) doubles of scratch
+ *   lam    r eigenvalues, descending
+ *   e64    r x k row-major: row p = eigenvector of the p-th largest eigenvalue (not normalised)
+ *   status one int32 per task: 0, or 1 when two of the r eigenvalues above the zero cut are closer than 1e-9 |G|
+ *          (their computed vectors may be parallel: the caller falls back to the Jacobi solver)
+ * Tasks with equal cluster size should be adjacent in the table (sort by descending k): every run of
+ * equal geometry is one launch.  Only enqueues work.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const double* g;
+  double* work;
+  double* lam;
+  double* e64;
+  int32_t* status;
+  int32_t k, r;
+} tta_symeig_task;
+
+int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_task* tasks_host, int n_tasks,
+                           void* stream);
+size_t tta_symeig_work_doubles(int k, int r);
+int tta_symeig_max_k(void);
 
 /* out[t] = sum of squares of n floats (fp64): tensorly `tl.norm(core, 2)**2` in the HOOI stopping rule. */
 typedef struct {

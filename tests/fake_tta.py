@@ -116,9 +116,10 @@ class FakeTTA:
             a = a.reshape(k, nb * nc).astype(np.float64)
             g = a @ a.T
             ld, kpad = int(tk['ld']), int(tk['kpad'])
-            x = _view(tk['x'], ld * kpad).reshape(kpad, ld)
-            x[:] = 0
-            x[:k, :k] = g.T.astype(np.float32)
+            if tk['x']:
+                x = _view(tk['x'], ld * kpad).reshape(kpad, ld)
+                x[:] = 0
+                x[:k, :k] = g.T.astype(np.float32)
             if tk['g64']:
                 _view(tk['g64'], k * k, np.float64).reshape(k, k)[:] = g
         return 0
@@ -153,6 +154,25 @@ class FakeTTA:
         if _val(sweeps_out):
             _view(_val(sweeps_out), n, np.int32)[:] = sc[2 * n:3 * n]
         return 0 if np.all(sc[5 * n:6 * n] != 0) else -4
+
+    # ---- fp64 dominant-r eigensolver (tridiagonalisation route on the GPU): exact eigh here ----
+    def tta_symeig_work_doubles(self, k, r):
+        kp = (k + 31) // 32 * 32
+        return 8 + 4 * kp + k * kp + 2 * k * r
+
+    def tta_symeig_max_k(self):
+        return 608
+
+    def tta_symeig_top_batched(self, tdev, thost, n, stream):
+        self.calls.append('symeig')
+        for tk in _table(thost, n, rt.SYMEIG_TASK):
+            k, r = int(tk['k']), int(tk['r'])
+            g = _view(tk['g'], k * k, np.float64).reshape(k, k)
+            lam, v = np.linalg.eigh(g)
+            _view(tk['lam'], r, np.float64)[:] = lam[::-1][:r]
+            _view(tk['e64'], r * k, np.float64).reshape(r, k)[:] = v[:, ::-1][:, :r].T * 1.7    # not normalised
+            _view(tk['status'], 1, np.int32)[0] = 0
+        return 0
 
     def tta_select_batched(self, tdev, thost, n, stream):
         self.calls.append('select')

@@ -388,3 +388,68 @@ def test_jacobi_cluster_and_multilaunch_paths_agree(multilaunch):
         Xn = X[np.argsort(-np.linalg.norm(X, axis=1))[:k]]
         Q = Xn / np.linalg.norm(Xn, axis=1, keepdims=True)
         assert np.max(np.abs(Q @ Q.T - np.eye(k))) <= 5e-6            # columns mutually orthogonal (tol 5e-7)
+
+
+# ---- fp64 dominant-r eigensolver (csrc/trd.cu) against numpy.linalg.eigh -------------------------------------
+def _symeig_run(gs, rs):
+    """gs: list of k x k fp64 SPD matrices; returns (lam, E) per problem through tta_symeig_top_batched."""
+    order = sorted(range(len(gs)), key=lambda i: -gs[i].shape[0])
+    bufs, tab = [], np.zeros(len(gs), dtype=rt.SYMEIG_TASK)
+    status = torch.full((len(gs),), 7, dtype=torch.int32, device=DEV)
+    for slot, i in enumerate(order):
+        k, r = gs[i].shape[0], rs[i]
+        g = _t(gs[i])
+        work = torch.empty(rt.symeig_work_doubles(k, r), dtype=torch.float64, device=DEV)
+        lam = torch.empty(r, dtype=torch.float64, device=DEV)
+        e64 = torch.empty(r * k, dtype=torch.float64, device=DEV)
+        bufs.append((g, work, lam, e64))
+        tab[slot] = (g.data_ptr(), work.data_ptr(), lam.data_ptr(), e64.data_ptr(), status.data_ptr() + 4 * slot, k, r)
+    rt.symeig_top(rt.TaskTable(tab, DEV))
+    torch.cuda.synchronize()
+    out = [None] * len(gs)
+    st = status.cpu().numpy()
+    for slot, i in enumerate(order):
+        k, r = gs[i].shape[0], rs[i]
+        out[i] = (bufs[slot][2].cpu().numpy(), bufs[slot][3].cpu().numpy().reshape(r, k), int(st[slot]))
+    return out
+
+
+@pytest.mark.parametrize('ks', [(33, 64, 65), (100, 130, 256), (300, 384), (480, 512), (513, 608), (3, 5, 40)])
+def test_symeig_top_matches_eigh(ks):
+    """Dominant-r invariant subspace and eigenvalues of flat-spectrum Gram matrices: eigenvalues to 1e-12 |G|,
+    orthonormality and the spectral projector to 1e-9 (fp64 end to end)."""
+    rng = np.random.RandomState(11)
+    gs, rs = [], []
+    for k in ks:
+        a = rng.randn(k, 3 * k + 7).astype(np.float32).astype(np.float64)
+        gs.append(a @ a.T)
+        rs.append(max(1, k // 4 + 1))
+    for (lam, e, status), g, r in zip(_symeig_run(gs, rs), gs, rs):
+        w, v = np.linalg.eigh(g)
+        w, v = w[::-1], v[:, ::-1]
+        assert status == 0
+        assert np.max(np.abs(lam - w[:r])) <= 1e-12 * w[0]
+        e = e / np.linalg.norm(e, axis=1, keepdims=True)
+        assert np.max(np.abs(e @ e.T - np.eye(r))) <= 1e-9
+        assert np.linalg.norm(e.T @ e - v[:, :r] @ v[:, :r].T) <= 1e-9 * max(1.0, w[0] / (w[r - 1] - w[r]) * 1e-3)
+
+
+def test_symeig_rank_deficient_and_cluster_flag():
+    """A rank-deficient Gram matrix keeps its live eigenpairs exact (the null vectors are the caller's to drop);
+    exactly repeated eigenvalues above the zero cut raise the status flag."""
+    rng = np.random.RandomState(12)
+    k = 96
+    a = rng.randn(k, 20).astype(np.float64)
+    g = a @ a.T                                          # rank 20
+    (lam, e, status), = _symeig_run([g], [40])
+    w, v = np.linalg.eigh(g)
+    w, v = w[::-1], v[:, ::-1]
+    assert np.max(np.abs(lam[:20] - w[:20])) <= 1e-12 * w[0]
+    assert np.max(np.abs(lam[20:])) <= 1e-12 * w[0]
+    e = e[:20] / np.linalg.norm(e[:20], axis=1, keepdims=True)
+    assert np.linalg.norm(e.T @ e - v[:, :20] @ v[:, :20].T) <= 1e-8
+    q, _ = np.linalg.qr(rng.randn(k, k))
+    d = np.linspace(1.0, 2.0, k)
+    d[-3:] = 2.0                                          # a triple dominant eigenvalue
+    (lam, e, status), = _symeig_run([(q * d) @ q.T], [10])
+    assert status == 1

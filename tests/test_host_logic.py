@@ -240,3 +240,75 @@ def test_tt_layer_groups_partition():
     layers = [projector.TTLayer(n, weights[n].shape, hp.tt_shapes[n], list(hp.ranks[n])) for n in hp.ranks]
     groups = projector.tt_layer_groups(layers)
     assert sorted(i for g in groups for i in g) == list(range(48)) and len(groups) <= 6
+
+
+def test_state_dict_roundtrip_and_adjust_rho(emulated_backend):
+    """Additive checkpointing of the ADMM state (the reference drops u / z on resume, engines.py:216-245) and
+    `adjust_rho` (admm.py:87-89: rho = factor * init_rho once epoch > int(0.85 * epochs))."""
+    from admm import ADMM
+    wb, hb, fmt = workloads.CONFIGS['resnet32_tt']
+    names = ['layer3.0.conv2.weight', 'layer3.1.conv1.weight']       # lossy layers: U moves on every update
+    weights = _subset(wb(), names)
+    a = ADMM(workloads.ParamBag(weights), 1e-3, hb(), fmt, 'cpu')
+    a.update(update_u=False)
+    a.update()
+    a.adjust_rho(90, 100)
+    assert a.rho == pytest.approx(5e-3) and a.init_rho == 1e-3
+    state = a.state_dict()
+    assert set(state) == {'rho', 'init_rho', 'u', 'z'} and set(state['u']) == set(names)
+    snap_u = {n: a.u[n].clone() for n in names}
+    snap_z = {n: a.z[n].clone() for n in names}
+    a.update()                                             # moves u and z away from the snapshot
+    assert any(not torch.equal(a.u[n], snap_u[n]) for n in names)
+    for n in names:                                        # the snapshot is a copy, not a view of the live state
+        assert torch.equal(state['u'][n], snap_u[n]) and torch.equal(state['z'][n], snap_z[n])
+
+    b = ADMM(workloads.ParamBag(weights), 1e-3, hb(), fmt, 'cpu')   # a resumed run: U = 0, Z = W (admm.py:32-40)
+    b.load_state_dict(state)
+    assert b.rho == pytest.approx(5e-3) and b.init_rho == 1e-3
+    for n in names:
+        assert torch.equal(b.u[n], snap_u[n]) and torch.equal(b.z[n], snap_z[n])
+    # the restored state drives the next update and the penalty exactly like the original object
+    a.load_state_dict(state)
+    a.update()
+    b.update()
+    for n in names:
+        assert torch.equal(a.u[n], b.u[n]) and torch.equal(a.z[n], b.z[n])
+    la = a.append_admm_loss(torch.zeros(()))
+    lb = b.append_admm_loss(torch.zeros(()))
+    assert float(la) == float(lb) and float(la) > 0.0
+
+
+@pytest.mark.parametrize('epoch,epochs,expect', [(0, 100, 1.0), (85, 100, 1.0), (86, 100, 5.0), (9, 10, 5.0),
+                                                 (8, 10, 1.0)])
+def test_adjust_rho_threshold(emulated_backend, epoch, epochs, expect):
+    from admm import ADMM
+    weights = _subset(workloads.resnet32_weights(), ['layer1.0.conv1.weight'])
+    a = ADMM(workloads.ParamBag(weights), 2e-3, hp_tables.tt_resnet32_3x(), 'tt', 'cpu')
+    a.adjust_rho(epoch, epochs)
+    assert a.rho == pytest.approx(expect * 2e-3)
+    a.adjust_rho(epochs, epochs, factor=7)
+    assert a.rho == pytest.approx(7 * 2e-3)
+
+
+def test_ten2tt_cores_are_orthonormal_like_the_reference(emulated_backend):
+    """ttd.py:21-25 hands out U[:, :r] of each SVD: every core but the last, reshaped to (r_i * s_i, r_{i+1}),
+    has orthonormal columns -- also on steps that keep every singular triplet (where the projection plans of
+    admm.py skip the eigensolve).  A tuple of ranks raises only when a clip would write into it (ttd.py:18-19)."""
+    import ttd
+    rng = np.random.RandomState(4)
+    x = rng.randn(8, 6, 10).astype(np.float32)
+    for ranks_in in ([1, 8, 10, 1], [1, 5, 7, 1]):
+        ranks = list(ranks_in)
+        cores = ttd.ten2tt(x, [8, 6, 10], ranks)
+        ref = port.tt_svd(x, [8, 6, 10], list(ranks_in))
+        assert ranks == [1, min(ranks_in[1], 8), min(ranks_in[2], 10), 1]
+        for c, rc in zip(cores, ref):
+            assert c.shape == rc.shape
+        for c in cores[:-1]:
+            m = c.reshape(-1, c.shape[-1]).astype(np.float64)
+            assert np.max(np.abs(m.T @ m - np.eye(m.shape[1]))) <= 1e-5
+        assert rel_fro(ttd.tt2ten(cores, x.shape), port.tt_contract(ref, x.shape)) <= 1e-5
+    ttd.ten2tt(x, [8, 6, 10], (1, 5, 7, 1))                      # no clip needed: a tuple is fine
+    with pytest.raises(TypeError):
+        ttd.ten2tt(x, [8, 6, 10], (1, 9, 7, 1))                  # clip 9 -> 8 must write into the tuple
