@@ -56,19 +56,73 @@ __device__ __forceinline__ void trd_cluster_sync() {
 
 __device__ __forceinline__ double trd_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// a[t] for a warp-uniform runtime t (register arrays need static indices)
-template <int NR>
-__device__ __forceinline__ double trd_pick(const double (&a)[NR], int t) {
-  double r = 0.0;
-#pragma unroll
-  for (int q = 0; q < NR; ++q)
-    if (q == t) r = a[q];
+// ---- mbarrier / distributed-shared-memory helpers (PTX: no CUDA C++ spelling for st.async) ----
+__device__ __forceinline__ uint32_t trd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t trd_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
+}
+__device__ __forceinline__ void trd_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void trd_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void trd_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TRD_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TRD_DONE_%=;\n"
+      "bra TRD_WAIT_%=;\n"
+      "TRD_DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// 16-byte store into another CTA's shared memory that signals that CTA's mbarrier (complete_tx has release
+// semantics at cluster scope): data and notification travel together, no fence, no cluster barrier
+__device__ __forceinline__ void trd_st_async_pair(uint32_t remote_addr, double a, double b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(remote_bar)
+               : "memory");
+}
+
+__device__ __forceinline__ double trd_rcp(double x) {   // 1/x to ~1 ulp for normal x: MUFU seed + 2 Newton steps
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // A. tridiagonalisation
+//
+// Shared memory of a CTA: its columns A (nclmax x KP doubles), the exchange buffers ps[2][KP] of (p_i, s_i)
+// pairs (s_i = element i of row j + 1 before the update of step j), vsh[2][KP] = the current reflector
+// (so that scalars of it are plain broadcast loads), two mbarriers.
+// Step j:  F_j  every warp updates its columns with (v_{j-1}, w_{j-1}), takes their dot products with v_j and
+//               sends (p_i, s_i) to every CTA with st.async (the receiving CTA's mbarrier counts the bytes);
+//          wait on the own mbarrier of parity j & 1: all k - 1 - j pairs of the step have landed;
+//          S_j  every warp rebuilds w_j, column j + 1 and v_{j+1} in registers, redundantly.
+// Buffers alternate by step parity.  A CTA can only send step j + 2 after it has received all of step j + 1,
+// which every warp of every CTA sends after it is done reading step j: two buffers suffice.
+//
+// Register vectors live in a frame RELATIVE to the first live chunk of 32 rows: element [u] of a lane is row
+// 32 (tb + u) + lane, tb = (j + 1) / 32.  The two special entries of a step (rows j + 1 and j + 2) are then
+// always in chunks 0 / 1, so the only per-lane masks are there, and the dead rows are chunks that have been
+// shifted out (one register shift every 32 steps) instead of predicates on every element -- the ALU pipe
+// (16 lanes per scheduler) was the bottleneck of the version that masked every chunk.  The chunks past the
+// end of the matrix are skipped by picking, per step, the smallest of four unrolled variants that covers the
+// live chunks; only its last NR / 4 chunks carry a (uniform) predicate.
 // ------------------------------------------------------------------------------------------------------
+template <int N>
+struct TrdInt { static constexpr int value = N; };
+
 template <int NR, int NT, int MC>
 __global__ void __launch_bounds__(NT, 1) trd_reduce_kernel(const tta_symeig_task* __restrict__ tasks, int first) {
   extern __shared__ __align__(16) double trd_sm[];
@@ -79,143 +133,195 @@ __global__ void __launch_bounds__(NT, 1) trd_reduce_kernel(const tta_symeig_task
   const int k = tk.k;
   constexpr int KP = NR * 32;
   constexpr int NW = NT / 32;
+  constexpr int QU = NR >= 4 ? NR / 4 : 1;       // chunk granularity of the unrolled variants
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nclmax = (k + P - 1) / P;
   const int ncl = (k - c + P - 1) / P;          // own columns: global index i = c + P * li
-  double* A = trd_sm;                           // nclmax columns of KP rows
-  double* pbuf = A + (size_t)nclmax * KP;       // [2][KP]  p_i of the step, by parity
-  double* sbuf = pbuf + 2 * KP;                 // [2][KP]  row j + 1 of the matrix before the update of step j
+  double* A = trd_sm;                                                   // nclmax columns of KP rows
+  double2* ps = reinterpret_cast<double2*>(A + (size_t)nclmax * KP);    // [2][KP]
+  double* vsh = reinterpret_cast<double*>(ps + 2 * KP);                 // [2][KP]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(vsh + 2 * KP);   // [2]
   const TrdLayout L = trd_layout(k, tk.r);
   double* gd = tk.work + L.d;
   double* ge = tk.work + L.e;
   double* gtau = tk.work + L.tau;
   double* gv = tk.work + L.v;
+  const int kchunks = L.kp >> 5;                // chunks that exist in the global reflector rows
 
   for (int li = warp; li < ncl; li += NW) {
     const double* src = tk.g + (int64_t)(c + P * li) * k;   // row i == column i
     double* dst = A + (size_t)li * KP;
     for (int r = lane; r < KP; r += 32) dst[r] = r < k ? src[r] : 0.0;
   }
-  for (int e = tid; e < 2 * KP; e += NT) {
-    pbuf[e] = 0.0;
-    sbuf[e] = 0.0;
+  // virtual step -1 (parity 1): no update, p = 0, "row 0 before the update" = column 0 of G
+  for (int e = tid; e < KP; e += NT) {
+    ps[e] = make_double2(0.0, 0.0);
+    ps[KP + e] = make_double2(0.0, e < k ? tk.g[e] : 0.0);
+    vsh[e] = 0.0;
+    vsh[KP + e] = 0.0;
   }
-  if (c == 0 && tid == 0) *tk.status = 0;
+  if (tid == 0) {
+    trd_mbar_init(trd_smem_u32(bars), 1);
+    trd_mbar_init(trd_smem_u32(bars + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (c == 0) *tk.status = 0;
+  }
   __syncthreads();
-  // virtual step -1 (parity 1): no update, "row 0 before the update" = column 0 of G
-  for (int r = tid; r < k; r += NT) sbuf[KP + r] = tk.g[r];
-  __syncthreads();
-  trd_cluster_sync();   // every CTA's exchange buffers are initialised before the first remote store
+  trd_cluster_sync();   // every CTA's buffers and barriers exist before the first remote store
 
-  double vprev[NR], wprev[NR], vcur[NR];
+  const uint32_t bar_local = trd_smem_u32(bars);
+  uint32_t rps = 0, rbar = 0;     // lane < P: exchange buffer and barriers of CTA `lane`
+  if (lane < P) {
+    rps = trd_mapa(trd_smem_u32(ps), (uint32_t)lane);
+    rbar = trd_mapa(bar_local, (uint32_t)lane);
+  }
+
+  double va[NR], vb[NR], wq[NR];
 #pragma unroll
-  for (int t = 0; t < NR; ++t) vprev[t] = wprev[t] = vcur[t] = 0.0;
+  for (int u = 0; u < NR; ++u) va[u] = vb[u] = wq[u] = 0.0;
   double tau_cur = 0.0;
   double vcolp[MC], wcolp[MC];   // v_{j-1}, w_{j-1} at this warp's own column indices
 #pragma unroll
   for (int m = 0; m < MC; ++m) vcolp[m] = wcolp[m] = 0.0;
 
-  for (int j = -1; j <= k - 3; ++j) {
-    if (j >= 0) {
-      // ---- fused pass: update of step j - 1, dot products of step j, row j + 1 ----
-      const int t0 = (j + 1) >> 5;
-      double dot[MC], sv[MC];
+  // ---- F_j + wait ----   vc = v_j, vo = v_{j-1}, wq = w_{j-1};  U = unrolled chunk count >= live chunks
+  auto fused = [&](auto utag, const int j, const double(&vc)[NR], const double(&vo)[NR]) {
+    constexpr int U = decltype(utag)::value;
+    const int par = j & 1;
+    if (tid == 0) trd_mbar_expect_tx(bar_local + 8 * par, 16u * (uint32_t)(k - 1 - j));
+    const int j1 = j + 1;
+    const int tb = j1 >> 5;
+    const int nlive = NR - tb;
+    double dot[MC], sv[MC];
+    double* colp[MC];
+    bool on[MC];
 #pragma unroll
-      for (int m = 0; m < MC; ++m) {
-        dot[m] = 0.0;
-        sv[m] = 0.0;
-        const int li = warp + NW * m;
-        const int i = c + P * li;
-        if (li < ncl && i > j) {   // warp-uniform
-          double* colp = A + (size_t)li * KP + lane;
-          const double wc = wcolp[m], vc = vcolp[m];
-#pragma unroll
-          for (int t = 0; t < NR; ++t) {
-            if (t >= t0) {
-              double a = colp[32 * t];
-              a = fma(-vprev[t], wc, a);
-              a = fma(-wprev[t], vc, a);
-              colp[32 * t] = a;
-              dot[m] = fma(a, vcur[t], dot[m]);
-              if (lane + 32 * t == j + 1) sv[m] = a;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int m = 0; m < MC; ++m) {
-        dot[m] = warp_sum(dot[m]) * tau_cur;
-        sv[m] = trd_bcast(sv[m], (j + 1) & 31);
-      }
-      if (lane < P) {
-        double* rp = cluster.map_shared_rank(pbuf, lane) + (j & 1) * KP;
-        double* rs = cluster.map_shared_rank(sbuf, lane) + (j & 1) * KP;
-#pragma unroll
-        for (int m = 0; m < MC; ++m) {
-          const int li = warp + NW * m;
-          const int i = c + P * li;
-          if (li < ncl && i > j) {
-            rp[i] = dot[m];
-            rs[i] = sv[m];
-          }
-        }
-      }
-      trd_cluster_sync();
+    for (int m = 0; m < MC; ++m) {
+      const int li = warp + NW * m;
+      on[m] = li < ncl && (c + P * li) > j;   // warp-uniform
+      colp[m] = A + (size_t)(on[m] ? li : 0) * KP + 32 * tb + lane;
+      dot[m] = 0.0;
     }
+    double an[MC];
+#pragma unroll
+    for (int m = 0; m < MC; ++m) an[m] = on[m] ? colp[m][0] : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool lv = (u < U - QU) || (u < nlive);           // compile-time true except in the last QU chunks
+      const bool lvn = (u + 1 < U - QU) || (u + 1 < nlive);
+      double ac[MC];
+#pragma unroll
+      for (int m = 0; m < MC; ++m) ac[m] = an[m];
+      if (u + 1 < U) {
+#pragma unroll
+        for (int m = 0; m < MC; ++m)
+          if (on[m] && lvn) an[m] = colp[m][32 * (u + 1)];    // next chunk's loads before this chunk's stores
+      }
+#pragma unroll
+      for (int m = 0; m < MC; ++m) {
+        double a = ac[m];
+        a = fma(-vo[u], wcolp[m], a);
+        a = fma(-wq[u], vcolp[m], a);
+        if (on[m] && lv) colp[m][32 * u] = a;
+        dot[m] = fma(a, vc[u], dot[m]);
+        if (u == 0) sv[m] = a;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MC; ++m) {
+      dot[m] = warp_sum(dot[m]) * tau_cur;
+      sv[m] = trd_bcast(sv[m], j1 & 31);
+    }
+    if (lane < P) {
+#pragma unroll
+      for (int m = 0; m < MC; ++m) {
+        const int i = c + P * (warp + NW * m);
+        if (on[m]) trd_st_async_pair(rps + (uint32_t)(par * KP + i) * 16u, dot[m], sv[m], rbar + 8 * par);
+      }
+    }
+    trd_mbar_wait(bar_local + 8 * par, (uint32_t)((j >> 1) & 1));
+  };
 
-    // ---- scalar phase of step j (every warp, redundantly): w_j, column j + 1, reflector v_{j+1} ----
-    const double* pb = pbuf + (j & 1) * KP;
-    const double* sb = sbuf + (j & 1) * KP;
-    double w[NR], col[NR];
+  // ---- S_j ----   in: vc = v_j;  out: wq = w_j, vo = v_{j+1}, tau_cur = tau_{j+1}, own-column scalars of (v_j, w_j)
+  auto scalar = [&](auto utag, const int j, const double(&vc)[NR], double(&vo)[NR]) {
+    constexpr int U = decltype(utag)::value;
+    const int par = j & 1;
+    const int j1 = j + 1, j2 = j + 2;
+    const int tb = j1 >> 5;
+    const int nlive = NR - tb;
+    const double2* psb = ps + par * KP;
+    const double* vs = vsh + par * KP;
+    const double2* psl = psb + 32 * tb + lane;
+    const int lim = j2 - 32 * tb;            // rows of chunk 0 (and lane 0 of chunk 1 when lim == 32) up to j2
+    double col[NR];
     double acc = 0.0;
 #pragma unroll
-    for (int t = 0; t < NR; ++t) {
-      const int idx = lane + 32 * t;
-      w[t] = pb[idx];
-      col[t] = sb[idx];
-      acc = fma(w[t], vcur[t], acc);
+    for (int u = 0; u < U; ++u) {
+      const bool lv = (u < U - QU) || (u < nlive);
+      double2 q = make_double2(0.0, 0.0);
+      if (lv) q = psl[32 * u];
+      wq[u] = q.x;     // stale for rows <= j, where v_j is zero
+      col[u] = q.y;
+      acc = fma(q.x, vc[u], acc);
     }
     acc = warp_sum(acc);
     const double K = 0.5 * tau_cur * acc;
+    const double2 q1 = psb[j1];
+    const double v1 = vs[j1];                       // 1 (0 in the virtual step)
+    const double wj1 = fma(-K, v1, q1.x);
+    const double dj1 = (q1.y - wj1) - wj1 * v1;
 #pragma unroll
-    for (int t = 0; t < NR; ++t) w[t] = (lane + 32 * t > j) ? fma(-K, vcur[t], w[t]) : 0.0;
-    const int j1 = j + 1;
-    const double wj1 = trd_bcast(trd_pick<NR>(w, j1 >> 5), j1 & 31);
-#pragma unroll
-    for (int t = 0; t < NR; ++t) col[t] = (col[t] - w[t]) - wj1 * vcur[t];   // column j1 after update j, entries >= j1
-    const double dj1 = trd_bcast(trd_pick<NR>(col, j1 >> 5), j1 & 31);
-    double tau_n = 0.0, beta = 0.0;
-    double vnew[NR];
+    for (int u = 0; u < U; ++u) {
+      const double w = fma(-K, vc[u], wq[u]);       // garbage only in rows where v is zero from now on
+      wq[u] = w;
+      col[u] = (col[u] - w) - wj1 * vc[u];          // column j1 after update j (rows >= j1 are meaningful)
+    }
+    double tau_n = 0.0, beta;
     if (j1 <= k - 3) {
-      const int j2 = j1 + 1;
-      const double alpha = trd_bcast(trd_pick<NR>(col, j2 >> 5), j2 & 31);
+      const double2 q2 = psb[j2];
+      const double v2 = vs[j2];
+      const double w2 = fma(-K, v2, q2.x);
+      const double alpha = (q2.y - w2) - wj1 * v2;
+      if (lane <= lim) col[0] = 0.0;
+      if (U > 1 && lane <= lim - 32) col[1] = 0.0;
       double sg = 0.0;
 #pragma unroll
-      for (int t = 0; t < NR; ++t)
-        if (lane + 32 * t > j2) sg = fma(col[t], col[t], sg);
+      for (int u = 0; u < U; ++u) sg = fma(col[u], col[u], sg);
       sg = warp_sum(sg);
       double inv = 0.0;
       beta = alpha;
       if (sg > 0.0) {
-        beta = -copysign(sqrt(fma(alpha, alpha, sg)), alpha);
-        tau_n = (beta - alpha) / beta;
-        inv = 1.0 / (alpha - beta);
+        const double x = fma(alpha, alpha, sg);
+        const double rs = rsqrt(x);
+        beta = -copysign(x * rs, alpha);
+        tau_n = (beta - alpha) * -copysign(rs, alpha);     // (beta - alpha) / beta
+        inv = trd_rcp(alpha - beta);
       }
 #pragma unroll
-      for (int t = 0; t < NR; ++t) {
-        const int idx = lane + 32 * t;
-        vnew[t] = idx > j2 ? col[t] * inv : (idx == j2 ? 1.0 : 0.0);
+      for (int u = 0; u < U; ++u) vo[u] = col[u] * inv;
+      if (lane == lim) vo[0] = 1.0;
+      if (U > 1 && lane == lim - 32) vo[1] = 1.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool lv = (u < U - QU) || (u < nlive);
+        if ((u % NW) == warp && lv) vsh[(par ^ 1) * KP + 32 * (tb + u) + lane] = vo[u];
       }
       if (c == (j1 % P) && warp == NW - 1) {
-        double* row = gv + (int64_t)j1 * L.kp;
+        double* row = gv + (int64_t)j1 * L.kp + 32 * tb + lane;
 #pragma unroll
-        for (int t = 0; t < NR; ++t)
-          if (lane + 32 * t < L.kp) row[lane + 32 * t] = vnew[t];
+        for (int u = 0; u < U; ++u)
+          if (tb + u < kchunks) row[32 * u] = vo[u];
       }
-    } else {   // j1 == k - 2: the last off-diagonal element, no reflector
-      beta = trd_bcast(trd_pick<NR>(col, (k - 1) >> 5), (k - 1) & 31);
-#pragma unroll
-      for (int t = 0; t < NR; ++t) vnew[t] = 0.0;
+    } else {   // j1 == k - 2: last off-diagonal element and d[k-1]; no reflector
+      const int kl = k - 1;
+      const double2 ql = psb[kl];
+      const double vl = vs[kl];
+      const double wl = fma(-K, vl, ql.x);
+      beta = (ql.y - wl) - wj1 * vl;
+      if (c == kl % P && warp == (kl / P) % NW && lane == 0) {
+        gd[kl] = A[(size_t)(kl / P) * KP + kl] - 2.0 * vl * wl;   // pending update of step k - 3
+        ge[kl] = 0.0;
+      }
     }
     if (c == 0 && tid == 0) {
       gd[j1] = dj1;
@@ -223,53 +329,124 @@ __global__ void __launch_bounds__(NT, 1) trd_reduce_kernel(const tta_symeig_task
       gtau[j1] = tau_n;
     }
 #pragma unroll
-    for (int t = 0; t < NR; ++t) {
-      vprev[t] = vcur[t];
-      wprev[t] = w[t];
-      vcur[t] = vnew[t];
-    }
-    tau_cur = tau_n;
-#pragma unroll
     for (int m = 0; m < MC; ++m) {
       const int i = c + P * (warp + NW * m);
       const int ii = i < KP ? i : 0;
-      vcolp[m] = trd_bcast(trd_pick<NR>(vprev, ii >> 5), ii & 31);
-      wcolp[m] = trd_bcast(trd_pick<NR>(wprev, ii >> 5), ii & 31);
+      const double vi = vs[ii];
+      vcolp[m] = vi;
+      wcolp[m] = fma(-K, vi, psb[ii].x);
     }
-  }
-
-  // d[k-1]: element (k-1, k-1) after the pending update of step k - 3
+    tau_cur = tau_n;
+    __syncwarp();   // the lanes that send in F_{j+1} release this warp's vsh stores with them
+    if ((j2 & 31) == 0) {   // row j + 2 opens a new chunk: the frame moves up by one chunk
 #pragma unroll
-  for (int m = 0; m < MC; ++m) {
-    const int li = warp + NW * m;
-    const int i = c + P * li;
-    if (li < ncl && i == k - 1 && lane == ((k - 1) & 31)) {
-      gd[k - 1] = A[(size_t)li * KP + (k - 1)] - 2.0 * vcolp[m] * wcolp[m];
-      ge[k - 1] = 0.0;
+      for (int u = 0; u + 1 < NR; ++u) {
+        va[u] = va[u + 1];
+        vb[u] = vb[u + 1];
+        wq[u] = wq[u + 1];
+      }
+      va[NR - 1] = vb[NR - 1] = wq[NR - 1] = 0.0;
     }
+  };
+
+  // one step with the smallest unrolled variant that covers the live chunks
+  auto step = [&](const int j, double(&vc)[NR], double(&vo)[NR]) {
+    const int nlive = NR - ((j + 1) >> 5);
+    if (nlive > NR - QU) {
+      if (j >= 0) fused(TrdInt<NR>{}, j, vc, vo);
+      scalar(TrdInt<NR>{}, j, vc, vo);
+    } else if (NR - QU >= 1 && nlive > NR - 2 * QU) {
+      fused(TrdInt<(NR - QU >= 1 ? NR - QU : 1)>{}, j, vc, vo);
+      scalar(TrdInt<(NR - QU >= 1 ? NR - QU : 1)>{}, j, vc, vo);
+    } else if (NR - 2 * QU >= 1 && nlive > NR - 3 * QU) {
+      fused(TrdInt<(NR - 2 * QU >= 1 ? NR - 2 * QU : 1)>{}, j, vc, vo);
+      scalar(TrdInt<(NR - 2 * QU >= 1 ? NR - 2 * QU : 1)>{}, j, vc, vo);
+    } else {
+      fused(TrdInt<(NR - 3 * QU >= 1 ? NR - 3 * QU : 1)>{}, j, vc, vo);
+      scalar(TrdInt<(NR - 3 * QU >= 1 ? NR - 3 * QU : 1)>{}, j, vc, vo);
+    }
+  };
+
+  step(-1, vb, va);                      // virtual step: v_0 -> va
+  for (int j = 0; j <= k - 3; j += 2) {
+    step(j, va, vb);                     // v_{j+1} -> vb
+    if (j + 1 <= k - 3) step(j + 1, vb, va);   // v_{j+2} -> va
   }
+  trd_cluster_sync();   // no CTA leaves while stores into its shared memory may still be in flight
 }
 
 // ------------------------------------------------------------------------------------------------------
-// B. eigenvalues: 128 shifts per eigenvalue and pass (7 bits), 8 passes
+// B. eigenvalues: one CTA (4 warps) per eigenvalue, 128 shifts per pass (7 bits), 8 passes.  The fp64 pipe
+// issues one warp instruction per 2 cycles per scheduler, so few warps per SM is what keeps the 3-instruction
+// step of the Sturm recurrence at its 8-cycle DFMA latency.  The same launch carries one extra CTA per group
+// of four reflectors: the six inner products the back-transformation needs (they are the same for every
+// vector).
 // ------------------------------------------------------------------------------------------------------
-constexpr int kTrdEvalThreads = 512;
-constexpr int kTrdEvalPerBlock = 4;
+constexpr int kTrdEvalThreads = 128;
 constexpr int kTrdEvalPasses = 8;
+
+// Sturm count without the pivmin guard (device hot loop): zeros only arise for exactly decoupled blocks with a
+// shift equal to a diagonal entry; the count is then off by one for that single shift.  Renormalised every
+// eighth step (signs are all that matters), branch-free; |T| <= 1 bounds the growth by 3^8 in between.
+__device__ __forceinline__ int trd_sturm_fast(const double* __restrict__ dd, const double* __restrict__ ee2, int k,
+                                              double x) {
+  double pp = 1.0;
+  double p = dd[0] - x;
+  int cnt = p < 0.0 ? 1 : 0;
+  auto one = [&](int i) {
+    const double pn = fma(dd[i] - x, p, -(ee2[i] * pp));
+    cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+    pp = p;
+    p = pn;
+  };
+  int i = 1;
+  for (; i + 8 <= k; i += 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) one(i + q);
+    const int ex = trd_exponent(p);
+    const double sc = (ex > 64 || (ex < -64 && ex > -1023)) ? trd_pow2(-ex) : 1.0;
+    p *= sc;
+    pp *= sc;
+  }
+  for (; i < k; ++i) one(i);
+  return cnt;
+}
 
 __global__ void __launch_bounds__(kTrdEvalThreads) trd_eigval_kernel(const tta_symeig_task* __restrict__ tasks) {
   extern __shared__ __align__(16) double ev_sm[];
   __shared__ double s_red[kTrdEvalThreads / 32];
-  __shared__ int s_cnt[kTrdEvalPerBlock][4];
+  __shared__ int s_cnt[kTrdEvalThreads / 32];
   const tta_symeig_task tk = tasks[blockIdx.y];
   const int k = tk.k, r = tk.r;
-  if ((int)blockIdx.x * kTrdEvalPerBlock >= r) return;
+  const int p = blockIdx.x;
   const TrdLayout L = trd_layout(k, r);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p >= r) {
+    // ---- inner products of the reflectors of group g (rows j0, j0-1, j0-2, j0-3) ----
+    const int g = p - r;
+    const int j0 = k - 3 - 4 * g;
+    if (j0 < 0) return;
+    const double* gv = tk.work + L.v;
+    double* out = tk.work + L.cross + 8 * (int64_t)g;
+    // pair list: (b,a) (c,a) (c,b) (d,a) (d,b) (d,c) -> rows (j0 - x, j0 - y)
+    for (int q = warp; q < 6; q += kTrdEvalThreads / 32) {
+      const int xr = q == 0 ? 1 : (q < 3 ? 2 : 3);
+      const int yr = q == 0 ? 0 : (q == 1 ? 0 : (q == 2 ? 1 : q - 3));
+      double acc = 0.0;
+      if (j0 - xr >= 0) {
+        const double* rx = gv + (int64_t)(j0 - xr) * L.kp;
+        const double* ry = gv + (int64_t)(j0 - yr) * L.kp;
+        for (int idx = (j0 & ~31) + lane; idx < L.kp; idx += 32) acc = fma(rx[idx], ry[idx], acc);   // both zero below j0
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[q] = acc;
+    }
+    return;
+  }
   double* dd = ev_sm;
   double* ee2 = ev_sm + L.kp;
   const double* gd = tk.work + L.d;
   const double* ge = tk.work + L.e;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // |T|_inf bound -> power-of-two scale (exact), so that every eigenvalue lies in [-1, 1]
   double mx = 0.0;
@@ -293,37 +470,39 @@ __global__ void __launch_bounds__(kTrdEvalThreads) trd_eigval_kernel(const tta_s
   }
   __syncthreads();
 
-  const int g = tid >> 7, s = tid & 127;
-  const int p = blockIdx.x * kTrdEvalPerBlock + g;
-  const bool live = p < r;
   const int m = k - 1 - p;            // ascending index of the p-th largest eigenvalue
   double lo = -1.0 - 1e-9, hi = 1.0 + 1e-9;
   for (int pass = 0; pass < kTrdEvalPasses; ++pass) {
-    const double step = (hi - lo) * (1.0 / 129.0);
-    const double x = fma(step, (double)(s + 1), lo);
-    const int cnt = live ? trd_sturm_count(dd, ee2, k, x) : 0;
-    const unsigned b = __ballot_sync(0xffffffffu, live && cnt <= m);   // x <= lambda_m
-    if (lane == 0) s_cnt[g][warp & 3] = __popc(b);
+    const double step = (hi - lo) * (1.0 / (kTrdEvalThreads + 1));
+    const double x = fma(step, (double)(tid + 1), lo);
+    const int cnt = trd_sturm_fast(dd, ee2, k, x);
+    const unsigned b = __ballot_sync(0xffffffffu, cnt <= m);   // x <= lambda_m
+    if (lane == 0) s_cnt[warp] = __popc(b);
     __syncthreads();
-    const int nle = s_cnt[g][0] + s_cnt[g][1] + s_cnt[g][2] + s_cnt[g][3];
+    int nle = 0;
+#pragma unroll
+    for (int q = 0; q < kTrdEvalThreads / 32; ++q) nle += s_cnt[q];
     __syncthreads();
     const double nlo = fma(step, (double)nle, lo);
-    const double nhi = nle < 128 ? fma(step, (double)(nle + 1), lo) : hi;
+    const double nhi = nle < kTrdEvalThreads ? fma(step, (double)(nle + 1), lo) : hi;
     lo = nlo;
     hi = nhi;
   }
-  if (live && s == 0) {
+  if (tid == 0) {
     const double lam = 0.5 * (lo + hi);
     tk.work[L.lams + p] = lam;
     tk.lam[p] = lam * trd_pow2(ex);
+    if (p == 0) tk.work[L.hdr] = sc;
   }
-  if (blockIdx.x == 0 && tid == 0) tk.work[L.hdr] = sc;
 }
 
 // ------------------------------------------------------------------------------------------------------
-// C. eigenvectors of T: twisted factorisation, two threads (forward / backward sweep) per vector
+// C. eigenvectors of T: twisted factorisation, two threads (forward / backward sweep) per vector, one warp
+// per CTA (16 vectors): the sweeps are chains of k dependent reciprocals, and a lone warp keeps them at the
+// latency of the fp64 pipe.  The pivots stay in shared memory (element i of vector v at [i][v]).
 // ------------------------------------------------------------------------------------------------------
-constexpr int kTrdEvecThreads = 128;
+constexpr int kTrdEvecThreads = 32;
+constexpr int kTrdEvecPer = kTrdEvecThreads / 2;
 constexpr double kTrdClusterGap = 1e-9;    // scaled units: closer eigenvalue pairs are reported (status 1)
 constexpr double kTrdLiveRel = 4e-7;       // same cut as refine.cu: smaller eigenvalues count as zero
 
@@ -331,39 +510,42 @@ __global__ void __launch_bounds__(kTrdEvecThreads) trd_eigvec_kernel(const tta_s
   extern __shared__ __align__(16) double evc_sm[];
   const tta_symeig_task tk = tasks[blockIdx.y];
   const int k = tk.k, r = tk.r;
-  if ((int)blockIdx.x * (kTrdEvecThreads / 2) >= r) return;
+  if ((int)blockIdx.x * kTrdEvecPer >= r) return;
   const TrdLayout L = trd_layout(k, r);
   double* dd = evc_sm;
   double* ee = evc_sm + L.kp;
+  double* e2 = evc_sm + 2 * L.kp;
+  double* Ssm = evc_sm + 3 * L.kp;                       // [k][16] forward pivots
+  double* Psm = Ssm + (size_t)k * kTrdEvecPer;           // [k][16] backward pivots
   const double sc = tk.work[L.hdr];
   const int tid = threadIdx.x;
   for (int i = tid; i < k; i += kTrdEvecThreads) {
     dd[i] = tk.work[L.d + i] * sc;
-    ee[i] = i < k - 1 ? tk.work[L.e + i] * sc : 0.0;
+    const double e = i < k - 1 ? tk.work[L.e + i] * sc : 0.0;
+    ee[i] = e;
+    e2[i] = e * e;
   }
-  __syncthreads();
-  const int p = blockIdx.x * (kTrdEvecThreads / 2) + (tid >> 1);
+  __syncwarp();
+  const int vloc = tid >> 1;
+  const int p = blockIdx.x * kTrdEvecPer + vloc;
   const int dir = tid & 1;
   const bool live = p < r;
-  const int pc = live ? p : r - 1;
-  const double lam = tk.work[L.lams + pc];
-  double* S = tk.work + L.s + pc;
-  double* Pv = tk.work + L.p + pc;
-  if (live) {
-    if (dir == 0) {
-      double q = trd_guard(dd[0] - lam);
-      S[0] = q;
-      for (int i = 0; i < k - 1; ++i) {
-        q = trd_guard((dd[i + 1] - lam) - ee[i] * ee[i] / q);
-        S[(int64_t)(i + 1) * r] = q;
-      }
-    } else {
-      double q = trd_guard(dd[k - 1] - lam);
-      Pv[(int64_t)(k - 1) * r] = q;
-      for (int i = k - 2; i >= 0; --i) {
-        q = trd_guard((dd[i] - lam) - ee[i] * ee[i] / q);
-        Pv[(int64_t)i * r] = q;
-      }
+  const double lam = tk.work[L.lams + (live ? p : r - 1)];
+  double* S = Ssm + vloc;
+  double* Pv = Psm + vloc;
+  if (dir == 0) {
+    double q = trd_guard(dd[0] - lam);
+    S[0] = q;
+    for (int i = 0; i < k - 1; ++i) {
+      q = trd_guard(fma(-e2[i], trd_rcp(q), dd[i + 1] - lam));
+      S[(i + 1) * kTrdEvecPer] = q;
+    }
+  } else {
+    double q = trd_guard(dd[k - 1] - lam);
+    Pv[(k - 1) * kTrdEvecPer] = q;
+    for (int i = k - 2; i >= 0; --i) {
+      q = trd_guard(fma(-e2[i], trd_rcp(q), dd[i] - lam));
+      Pv[i * kTrdEvecPer] = q;
     }
   }
   __syncwarp();
@@ -372,13 +554,12 @@ __global__ void __launch_bounds__(kTrdEvecThreads) trd_eigvec_kernel(const tta_s
   const int ibeg = dir == 0 ? 0 : half, iend = dir == 0 ? half : k;
   double best = 1e300;
   int bi = ibeg;
-  if (live) {
-    for (int i = ibeg; i < iend; ++i) {
-      const double gm = fabs(S[(int64_t)i * r] + Pv[(int64_t)i * r] - (dd[i] - lam));
-      if (gm < best) {
-        best = gm;
-        bi = i;
-      }
+#pragma unroll 4
+  for (int i = ibeg; i < iend; ++i) {
+    const double gm = fabs(S[i * kTrdEvecPer] + Pv[i * kTrdEvecPer] - (dd[i] - lam));
+    if (gm < best) {
+      best = gm;
+      bi = i;
     }
   }
   const double ob = __shfl_xor_sync(0xffffffffu, best, 1);
@@ -389,8 +570,9 @@ __global__ void __launch_bounds__(kTrdEvecThreads) trd_eigvec_kernel(const tta_s
     double z = 1.0;
     if (dir == 0) {
       out[tw] = 1.0;
+#pragma unroll 4
       for (int i = tw - 1; i >= 0; --i) {
-        z = -(ee[i] / S[(int64_t)i * r]) * z;
+        z = -(ee[i] * trd_rcp(S[i * kTrdEvecPer])) * z;
         out[i] = z;
       }
       if (p + 1 < r) {
@@ -398,8 +580,9 @@ __global__ void __launch_bounds__(kTrdEvecThreads) trd_eigvec_kernel(const tta_s
         if (lam > kTrdLiveRel * l0 && lam - ln < kTrdClusterGap) atomicOr(tk.status, 1);
       }
     } else {
+#pragma unroll 4
       for (int i = tw; i < k - 1; ++i) {
-        z = -(ee[i] / Pv[(int64_t)(i + 1) * r]) * z;
+        z = -(ee[i] * trd_rcp(Pv[(i + 1) * kTrdEvecPer])) * z;
         out[i + 1] = z;
       }
     }
@@ -407,83 +590,107 @@ __global__ void __launch_bounds__(kTrdEvecThreads) trd_eigvec_kernel(const tta_s
 }
 
 // ------------------------------------------------------------------------------------------------------
-// D. back-transformation, in place on e64: one warp per two vectors, two reflectors per reduction
+// D. back-transformation x = H_0 ... H_{k-3} z, in place on e64.  One warp per vector (x in registers,
+// lane-strided), four reflectors per reduction round: with a, b, c, d = v_j, v_{j-1}, v_{j-2}, v_{j-3}
+//     fa = ta (a.x);  fb = tb (b.x - fa b.a);  fc = tc (c.x - fa c.a - fb c.b);  fd = td (d.x - fa d.a - fb d.b - fc d.c)
+//     x <- x - fa a - fb b - fc c - fd d
+// (the inner products of the reflectors come precomputed from the eigenvalue launch).  The four rows are staged
+// through shared memory with cp.async, two groups ahead, shared by the warps of the CTA; the staging buffers
+// start zeroed and only the non-zero chunks of a row are ever copied, so no element needs a predicate.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kTrdBtWarps = 2;
+constexpr int kTrdBtWarps = 4;
+constexpr int kTrdBtStages = 3;
 
 template <int NR>
 __global__ void __launch_bounds__(32 * kTrdBtWarps) trd_backtransform_kernel(const tta_symeig_task* __restrict__ tasks,
                                                                             int first) {
+  extern __shared__ __align__(16) double bt_sm[];     // [stages][4][KP]
+  constexpr int KP = NR * 32;
   const tta_symeig_task tk = tasks[first + blockIdx.y];
   const int k = tk.k, r = tk.r;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p0 = 2 * (blockIdx.x * kTrdBtWarps + warp), p1 = p0 + 1;
-  if (p0 >= r) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((int)blockIdx.x * kTrdBtWarps >= r) return;
+  const int p = blockIdx.x * kTrdBtWarps + warp;
+  const bool live = p < r;
   const TrdLayout L = trd_layout(k, r);
   const double* gv = tk.work + L.v;
   const double* gtau = tk.work + L.tau;
-  double x0[NR], x1[NR];
+  const double* gcross = tk.work + L.cross;
+  for (int e = tid; e < kTrdBtStages * 4 * KP; e += 32 * kTrdBtWarps) bt_sm[e] = 0.0;
+  double x[NR];
 #pragma unroll
   for (int t = 0; t < NR; ++t) {
     const int idx = lane + 32 * t;
-    x0[t] = idx < k ? tk.e64[(int64_t)p0 * k + idx] : 0.0;
-    x1[t] = (idx < k && p1 < r) ? tk.e64[(int64_t)p1 * k + idx] : 0.0;
+    x[t] = (live && idx < k) ? tk.e64[(int64_t)p * k + idx] : 0.0;
   }
-  double an[NR], bn[NR];   // prefetched reflector pair
-  auto fetch = [&](int j) {
-    const int t0 = (j > 0 ? j : 0) >> 5;   // row j - 1 is non-zero from index j on
-    const double* ra = gv + (int64_t)j * L.kp + lane;
-    const double* rb = gv + (int64_t)(j > 0 ? j - 1 : 0) * L.kp + lane;
-#pragma unroll
-    for (int t = 0; t < NR; ++t) {
-      const bool in = t >= t0 && 32 * t < L.kp;
-      an[t] = in ? __ldg(ra + 32 * t) : 0.0;
-      bn[t] = (in && j > 0) ? __ldg(rb + 32 * t) : 0.0;
+  __syncthreads();
+  const int nref = k - 2;                       // reflectors 0 .. k-3
+  const int ngroups = (nref + 3) / 4;           // group g holds rows j0, j0-1, j0-2, j0-3 with j0 = k-3-4g
+  // stage loader: rows below 0 do not exist (their slots keep the zeros / stale rows, tau = 0 for them)
+  auto load = [&](int g) {
+    if (g < ngroups) {
+      double* dst = bt_sm + (size_t)(g % kTrdBtStages) * 4 * KP;
+      const int j0 = k - 3 - 4 * g;
+      const int nch = L.kp / 2;
+      for (int q = 0; q < 4; ++q) {
+        const int row = j0 - q;
+        if (row < 0) break;
+        const double* src = gv + (int64_t)row * L.kp;
+        const int c0 = (row >> 5) * 16;   // the reduction wrote row `row` from the 32-row chunk of index `row` on
+        for (int ch = c0 + tid; ch < nch; ch += 32 * kTrdBtWarps) {
+          const uint32_t d = trd_smem_u32(dst + q * KP + 2 * ch);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * ch) : "memory");
+        }
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  int j = k - 3;
-  if (j >= 0) fetch(j);
-  for (; j >= 0; j -= 2) {
-    double a[NR], b[NR];
+  load(0);
+  load(1);
+  for (int g = 0; g < ngroups; ++g) {
+    load(g + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncthreads();
+    const double* st = bt_sm + (size_t)(g % kTrdBtStages) * 4 * KP + lane;
+    const int j0 = k - 3 - 4 * g;
+    const double ta = gtau[j0], tb = j0 >= 1 ? gtau[j0 - 1] : 0.0, tc = j0 >= 2 ? gtau[j0 - 2] : 0.0,
+                 td = j0 >= 3 ? gtau[j0 - 3] : 0.0;
+    const double2 c01 = *reinterpret_cast<const double2*>(gcross + 8 * g);
+    const double2 c23 = *reinterpret_cast<const double2*>(gcross + 8 * g + 2);
+    const double2 c45 = *reinterpret_cast<const double2*>(gcross + 8 * g + 4);
+    double a[NR], b[NR], cc_[NR], d[NR];
+    double ax = 0, bx = 0, cx = 0, dx = 0;
 #pragma unroll
     for (int t = 0; t < NR; ++t) {
-      a[t] = an[t];
-      b[t] = bn[t];
-    }
-    const double ta = gtau[j], tb = j > 0 ? gtau[j - 1] : 0.0;
-    if (j - 2 >= 0) fetch(j - 2);
-    double ax0 = 0.0, ax1 = 0.0, bx0 = 0.0, bx1 = 0.0, ba = 0.0;
-#pragma unroll
-    for (int t = 0; t < NR; ++t) {
-      ax0 = fma(a[t], x0[t], ax0);
-      ax1 = fma(a[t], x1[t], ax1);
-      bx0 = fma(b[t], x0[t], bx0);
-      bx1 = fma(b[t], x1[t], bx1);
-      ba = fma(b[t], a[t], ba);
+      a[t] = st[32 * t];
+      b[t] = st[KP + 32 * t];
+      cc_[t] = st[2 * KP + 32 * t];
+      d[t] = st[3 * KP + 32 * t];
+      ax = fma(a[t], x[t], ax);
+      bx = fma(b[t], x[t], bx);
+      cx = fma(cc_[t], x[t], cx);
+      dx = fma(d[t], x[t], dx);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      ax0 += __shfl_xor_sync(0xffffffffu, ax0, o);
-      ax1 += __shfl_xor_sync(0xffffffffu, ax1, o);
-      bx0 += __shfl_xor_sync(0xffffffffu, bx0, o);
-      bx1 += __shfl_xor_sync(0xffffffffu, bx1, o);
-      ba += __shfl_xor_sync(0xffffffffu, ba, o);
+      ax += __shfl_xor_sync(0xffffffffu, ax, o);
+      bx += __shfl_xor_sync(0xffffffffu, bx, o);
+      cx += __shfl_xor_sync(0xffffffffu, cx, o);
+      dx += __shfl_xor_sync(0xffffffffu, dx, o);
     }
-    // x <- (I - tb b b^T)(I - ta a a^T) x
-    const double ca0 = ta * ax0, ca1 = ta * ax1;
-    const double cb0 = tb * fma(-ca0, ba, bx0), cb1 = tb * fma(-ca1, ba, bx1);
+    const double fa = ta * ax;
+    const double fb = tb * fma(-fa, c01.x, bx);
+    const double fc = tc * fma(-fb, c23.x, fma(-fa, c01.y, cx));
+    const double fd = td * fma(-fc, c45.y, fma(-fb, c45.x, fma(-fa, c23.y, dx)));
+#pragma unroll
+    for (int t = 0; t < NR; ++t) x[t] = fma(-fd, d[t], fma(-fc, cc_[t], fma(-fb, b[t], fma(-fa, a[t], x[t]))));
+    __syncthreads();   // the stage is free for the load of group g + 3
+  }
+  if (live) {
 #pragma unroll
     for (int t = 0; t < NR; ++t) {
-      x0[t] = fma(-cb0, b[t], fma(-ca0, a[t], x0[t]));
-      x1[t] = fma(-cb1, b[t], fma(-ca1, a[t], x1[t]));
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < NR; ++t) {
-    const int idx = lane + 32 * t;
-    if (idx < k) {
-      tk.e64[(int64_t)p0 * k + idx] = x0[t];
-      if (p1 < r) tk.e64[(int64_t)p1 * k + idx] = x1[t];
+      const int idx = lane + 32 * t;
+      if (idx < k) tk.e64[(int64_t)p * k + idx] = x[t];
     }
   }
 }
@@ -493,7 +700,8 @@ __global__ void __launch_bounds__(32 * kTrdBtWarps) trd_backtransform_kernel(con
 // ------------------------------------------------------------------------------------------------------
 static size_t trd_reduce_smem(int k, int P, int nr) {
   const int nclmax = (k + P - 1) / P;
-  return ((size_t)nclmax * nr * 32 + 4 * (size_t)nr * 32) * sizeof(double);
+  // columns + ps[2][KP] (16 B) + vsh[2][KP] + two mbarriers
+  return ((size_t)nclmax * nr * 32 + 6 * (size_t)nr * 32 + 2) * sizeof(double);
 }
 
 template <int NR, int NT, int MC>
@@ -543,20 +751,32 @@ static int trd_reduce_dispatch(int nr, const tta_symeig_task* tasks_dev, int fir
   }
 }
 
-static int trd_backtransform_dispatch(int nr, const tta_symeig_task* tasks_dev, int first, int count, int rmax,
-                                      cudaStream_t st) {
-  const dim3 grid((unsigned)((rmax + 2 * kTrdBtWarps - 1) / (2 * kTrdBtWarps)), (unsigned)count);
-  const int nt = 32 * kTrdBtWarps;
-  switch (nr) {
-    case 2: trd_backtransform_kernel<2><<<grid, nt, 0, st>>>(tasks_dev, first); break;
-    case 4: trd_backtransform_kernel<4><<<grid, nt, 0, st>>>(tasks_dev, first); break;
-    case 8: trd_backtransform_kernel<8><<<grid, nt, 0, st>>>(tasks_dev, first); break;
-    case 12: trd_backtransform_kernel<12><<<grid, nt, 0, st>>>(tasks_dev, first); break;
-    case 16: trd_backtransform_kernel<16><<<grid, nt, 0, st>>>(tasks_dev, first); break;
-    default: trd_backtransform_kernel<20><<<grid, nt, 0, st>>>(tasks_dev, first); break;
+template <int NR>
+static int trd_launch_backtransform(const tta_symeig_task* tasks_dev, int first, int count, int rmax, cudaStream_t st) {
+  const size_t smem = (size_t)kTrdBtStages * 4 * NR * 32 * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    int rc = check_cuda(cudaFuncSetAttribute(trd_backtransform_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem), "symeig back-transform smem attribute");
+    if (rc) return rc;
+    attr_set = true;
   }
+  const dim3 grid((unsigned)((rmax + kTrdBtWarps - 1) / kTrdBtWarps), (unsigned)count);
+  trd_backtransform_kernel<NR><<<grid, 32 * kTrdBtWarps, smem, st>>>(tasks_dev, first);
   TTA_CHECK_LAUNCH("symeig back-transform launch");
   return TTA_OK;
+}
+
+static int trd_backtransform_dispatch(int nr, const tta_symeig_task* tasks_dev, int first, int count, int rmax,
+                                      cudaStream_t st) {
+  switch (nr) {
+    case 2: return trd_launch_backtransform<2>(tasks_dev, first, count, rmax, st);
+    case 4: return trd_launch_backtransform<4>(tasks_dev, first, count, rmax, st);
+    case 8: return trd_launch_backtransform<8>(tasks_dev, first, count, rmax, st);
+    case 12: return trd_launch_backtransform<12>(tasks_dev, first, count, rmax, st);
+    case 16: return trd_launch_backtransform<16>(tasks_dev, first, count, rmax, st);
+    default: return trd_launch_backtransform<20>(tasks_dev, first, count, rmax, st);
+  }
 }
 
 }  // namespace tta
@@ -643,12 +863,21 @@ int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_ta
       if (rc) return rc;
     }
   }
-  const size_t smem = (size_t)2 * ((kmax + 31) & ~31) * sizeof(double);
-  trd_eigval_kernel<<<dim3((unsigned)((rmax + kTrdEvalPerBlock - 1) / kTrdEvalPerBlock), (unsigned)n_tasks),
-                      kTrdEvalThreads, smem, st>>>(tasks_dev);
+  const int kpmax = (kmax + 31) & ~31;
+  const size_t smem = (size_t)2 * kpmax * sizeof(double);
+  // grid.x = eigenvalues of the widest task + one CTA per group of four reflectors of the largest task
+  trd_eigval_kernel<<<dim3((unsigned)(rmax + (kmax + 1) / 4), (unsigned)n_tasks), kTrdEvalThreads, smem, st>>>(tasks_dev);
   TTA_CHECK_LAUNCH("symeig eigenvalue launch");
-  trd_eigvec_kernel<<<dim3((unsigned)((rmax + kTrdEvecThreads / 2 - 1) / (kTrdEvecThreads / 2)), (unsigned)n_tasks),
-                      kTrdEvecThreads, smem, st>>>(tasks_dev);
+  const size_t smem_vec = ((size_t)3 * kpmax + (size_t)2 * kmax * kTrdEvecPer) * sizeof(double);
+  static size_t smem_vec_set = 48 * 1024;
+  if (smem_vec > smem_vec_set) {
+    rc = check_cuda(cudaFuncSetAttribute(trd_eigvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vec),
+                    "symeig eigenvector smem attribute");
+    if (rc) return rc;
+    smem_vec_set = smem_vec;
+  }
+  trd_eigvec_kernel<<<dim3((unsigned)((rmax + kTrdEvecPer - 1) / kTrdEvecPer), (unsigned)n_tasks), kTrdEvecThreads,
+                      smem_vec, st>>>(tasks_dev);
   TTA_CHECK_LAUNCH("symeig eigenvector launch");
   for (const Run& rn : runs) {
     rc = trd_backtransform_dispatch(rn.nr, tasks_dev, rn.first, rn.count, rn.rmax, st);

@@ -22,8 +22,8 @@ struct TrdLayout {
   int64_t tau;    // kp  Householder scalars (k - 2 used)
   int64_t lams;   // kp  the r dominant eigenvalues of the SCALED T, descending
   int64_t v;      // k x kp: row j = reflector j (zero up to index j, 1 at j + 1)
-  int64_t s;      // k x r: forward pivots of the twisted factorisation (element i of vector p at i * r + p)
-  int64_t p;      // k x r: backward pivots
+  int64_t cross;  // 8 doubles per group of four reflectors (rows j0, j0-1, j0-2, j0-3; j0 = k-3-4g):
+                  // b.a, c.a, c.b, d.a, d.b, d.c (back-transformation, trd.cu)
   int64_t total;
 };
 
@@ -36,9 +36,9 @@ TRD_HD TrdLayout trd_layout(int k, int r) {
   L.tau = L.e + L.kp;
   L.lams = L.tau + L.kp;
   L.v = L.lams + L.kp;
-  L.s = L.v + (int64_t)k * L.kp;
-  L.p = L.s + (int64_t)k * r;
-  L.total = L.p + (int64_t)k * r;
+  L.cross = L.v + (int64_t)k * L.kp;
+  L.total = L.cross + 8 * (int64_t)((k + 1) / 4 + 1);
+  (void)r;
   return L;
 }
 

@@ -22,7 +22,7 @@ def main():
         a = rng.randn(k, 9 * k).astype(np.float32).astype(np.float64)
         g_h = a @ a.T
         g = torch.from_numpy(g_h).to(DEV)
-        work = torch.zeros(rt.symeig_work_doubles(k, r), dtype=torch.float64, device=DEV)
+        work = torch.full((rt.symeig_work_doubles(k, r),), float("nan"), dtype=torch.float64, device=DEV)
         lam = torch.zeros(r, dtype=torch.float64, device=DEV)
         e64 = torch.zeros(r * k, dtype=torch.float64, device=DEV)
         status = torch.zeros(1, dtype=torch.int32, device=DEV)

@@ -158,7 +158,7 @@ class FakeTTA:
     # ---- fp64 dominant-r eigensolver (tridiagonalisation route on the GPU): exact eigh here ----
     def tta_symeig_work_doubles(self, k, r):
         kp = (k + 31) // 32 * 32
-        return 8 + 4 * kp + k * kp + 2 * k * r
+        return 8 + 4 * kp + k * kp + 8 * ((k + 1) // 4 + 1)
 
     def tta_symeig_max_k(self):
         return 608

@@ -399,7 +399,7 @@ def _symeig_run(gs, rs):
     for slot, i in enumerate(order):
         k, r = gs[i].shape[0], rs[i]
         g = _t(gs[i])
-        work = torch.empty(rt.symeig_work_doubles(k, r), dtype=torch.float64, device=DEV)
+        work = torch.full((rt.symeig_work_doubles(k, r),), float("nan"), dtype=torch.float64, device=DEV)   # scratch: contents must not matter
         lam = torch.empty(r, dtype=torch.float64, device=DEV)
         e64 = torch.empty(r * k, dtype=torch.float64, device=DEV)
         bufs.append((g, work, lam, e64))
