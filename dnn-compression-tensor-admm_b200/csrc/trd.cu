@@ -74,7 +74,7 @@ __device__ __forceinline__ void trd_mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "TRD_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra TRD_DONE_%=;\n"
       "bra TRD_WAIT_%=;\n"
       "TRD_DONE_%=:\n"
@@ -253,41 +253,50 @@ __global__ void __launch_bounds__(NT, 1) trd_reduce_kernel(const tta_symeig_task
     const double* vs = vsh + par * KP;
     const double2* psl = psb + 32 * tb + lane;
     const int lim = j2 - 32 * tb;            // rows of chunk 0 (and lane 0 of chunk 1 when lim == 32) up to j2
-    double col[NR];
-    double acc = 0.0;
+    // One pass, one shuffle tree.  With c1 = 1 + v[j1], A_i = (s_i - p_i) - p_j1 v_i and K = tau/2 sum p_i v_i:
+    //   w_i = p_i - K v_i,   column j1 after the update: col_i = A_i + K c1 v_i,
+    //   sigma = sum_{i > j2} col_i^2 = S_AA + 2 K c1 S_Av + (K c1)^2 S_vv      (sums over i > j2)
+    // so the norm of the next reflector does not wait for a second reduction behind K.
+    const double2 q1 = psb[j1];
+    const double v1 = vs[j1];                       // 1 (0 in the virtual step)
+    const double c1 = 1.0 + v1;
+    double s_pv = 0.0, s_aa = 0.0, s_av = 0.0, s_vv = 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const bool lv = (u < U - QU) || (u < nlive);
       double2 q = make_double2(0.0, 0.0);
       if (lv) q = psl[32 * u];
       wq[u] = q.x;     // stale for rows <= j, where v_j is zero
-      col[u] = q.y;
-      acc = fma(q.x, vc[u], acc);
+      double am = fma(-q1.x, vc[u], q.y - q.x);
+      double vm = vc[u];
+      if (u == 0 && lane <= lim) am = vm = 0.0;              // rows <= j2 do not enter the next reflector
+      if (u == 1 && lane <= lim - 32) am = vm = 0.0;
+      s_pv = fma(q.x, vc[u], s_pv);
+      s_aa = fma(am, am, s_aa);
+      s_av = fma(am, vm, s_av);
+      s_vv = fma(vm, vm, s_vv);
+      vo[u] = am;
     }
-    acc = warp_sum(acc);
-    const double K = 0.5 * tau_cur * acc;
-    const double2 q1 = psb[j1];
-    const double v1 = vs[j1];                       // 1 (0 in the virtual step)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_pv += __shfl_xor_sync(0xffffffffu, s_pv, o);
+      s_aa += __shfl_xor_sync(0xffffffffu, s_aa, o);
+      s_av += __shfl_xor_sync(0xffffffffu, s_av, o);
+      s_vv += __shfl_xor_sync(0xffffffffu, s_vv, o);
+    }
+    const double K = 0.5 * tau_cur * s_pv;
+    const double kc = K * c1;
     const double wj1 = fma(-K, v1, q1.x);
     const double dj1 = (q1.y - wj1) - wj1 * v1;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const double w = fma(-K, vc[u], wq[u]);       // garbage only in rows where v is zero from now on
-      wq[u] = w;
-      col[u] = (col[u] - w) - wj1 * vc[u];          // column j1 after update j (rows >= j1 are meaningful)
-    }
+    for (int u = 0; u < U; ++u) wq[u] = fma(-K, vc[u], wq[u]);   // w_j (garbage only in rows where v stays zero)
     double tau_n = 0.0, beta;
     if (j1 <= k - 3) {
       const double2 q2 = psb[j2];
       const double v2 = vs[j2];
       const double w2 = fma(-K, v2, q2.x);
       const double alpha = (q2.y - w2) - wj1 * v2;
-      if (lane <= lim) col[0] = 0.0;
-      if (U > 1 && lane <= lim - 32) col[1] = 0.0;
-      double sg = 0.0;
-#pragma unroll
-      for (int u = 0; u < U; ++u) sg = fma(col[u], col[u], sg);
-      sg = warp_sum(sg);
+      const double sg = fma(kc, fma(kc, s_vv, 2.0 * s_av), s_aa);
       double inv = 0.0;
       beta = alpha;
       if (sg > 0.0) {
@@ -297,8 +306,14 @@ __global__ void __launch_bounds__(NT, 1) trd_reduce_kernel(const tta_symeig_task
         tau_n = (beta - alpha) * -copysign(rs, alpha);     // (beta - alpha) / beta
         inv = trd_rcp(alpha - beta);
       }
+      const double kci = kc * inv;
 #pragma unroll
-      for (int u = 0; u < U; ++u) vo[u] = col[u] * inv;
+      for (int u = 0; u < U; ++u) {
+        double vm = vc[u];
+        if (u == 0 && lane <= lim) vm = 0.0;
+        if (u == 1 && lane <= lim - 32) vm = 0.0;
+        vo[u] = fma(kci, vm, vo[u] * inv);                 // (A_i + K c1 v_i) / (alpha - beta)
+      }
       if (lane == lim) vo[0] = 1.0;
       if (U > 1 && lane == lim - 32) vo[1] = 1.0;
 #pragma unroll
@@ -388,14 +403,14 @@ constexpr int kTrdEvalPasses = 8;
 // Sturm count without the pivmin guard (device hot loop): zeros only arise for exactly decoupled blocks with a
 // shift equal to a diagonal entry; the count is then off by one for that single shift.  Renormalised every
 // eighth step (signs are all that matters), branch-free; |T| <= 1 bounds the growth by 3^8 in between.
-__device__ __forceinline__ int trd_sturm_fast(const double* __restrict__ dd, const double* __restrict__ ee2, int k,
-                                              double x) {
+__device__ __forceinline__ int trd_sturm_fast(const double2* __restrict__ de, int k, double x) {
   double pp = 1.0;
-  double p = dd[0] - x;
-  int cnt = p < 0.0 ? 1 : 0;
+  double p = de[0].x - x;
+  int cnt = (int)((unsigned)__double2hiint(p) >> 31);
   auto one = [&](int i) {
-    const double pn = fma(dd[i] - x, p, -(ee2[i] * pp));
-    cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+    const double2 q = de[i];                                  // (d_i, e_{i-1}^2): one 16-byte broadcast load
+    const double pn = fma(q.x - x, p, -(q.y * pp));
+    cnt += (int)((unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31);   // sign change (integer pipe)
     pp = p;
     p = pn;
   };
@@ -443,8 +458,7 @@ __global__ void __launch_bounds__(kTrdEvalThreads) trd_eigval_kernel(const tta_s
     }
     return;
   }
-  double* dd = ev_sm;
-  double* ee2 = ev_sm + L.kp;
+  double2* de = reinterpret_cast<double2*>(ev_sm);
   const double* gd = tk.work + L.d;
   const double* ge = tk.work + L.e;
 
@@ -464,9 +478,8 @@ __global__ void __launch_bounds__(kTrdEvalThreads) trd_eigval_kernel(const tta_s
   ex = ex > 1000 ? 1000 : (ex < -1000 ? -1000 : ex);
   const double sc = trd_pow2(-ex);
   for (int i = tid; i < k; i += kTrdEvalThreads) {
-    dd[i] = gd[i] * sc;
     const double e = i > 0 ? ge[i - 1] * sc : 0.0;
-    ee2[i] = e * e;
+    de[i] = make_double2(gd[i] * sc, e * e);
   }
   __syncthreads();
 
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(kTrdEvalThreads) trd_eigval_kernel(const tta_s
   for (int pass = 0; pass < kTrdEvalPasses; ++pass) {
     const double step = (hi - lo) * (1.0 / (kTrdEvalThreads + 1));
     const double x = fma(step, (double)(tid + 1), lo);
-    const int cnt = trd_sturm_fast(dd, ee2, k, x);
+    const int cnt = trd_sturm_fast(de, k, x);
     const unsigned b = __ballot_sync(0xffffffffu, cnt <= m);   // x <= lambda_m
     if (lane == 0) s_cnt[warp] = __popc(b);
     __syncthreads();
@@ -604,8 +617,9 @@ constexpr int kTrdBtStages = 3;
 template <int NR>
 __global__ void __launch_bounds__(32 * kTrdBtWarps) trd_backtransform_kernel(const tta_symeig_task* __restrict__ tasks,
                                                                             int first) {
-  extern __shared__ __align__(16) double bt_sm[];     // [stages][4][KP]
+  extern __shared__ __align__(16) double bt_sm[];     // [stages][4 rows of KP | 4 taus | 6 inner products, pad]
   constexpr int KP = NR * 32;
+  constexpr int kStage = 4 * KP + 16;
   const tta_symeig_task tk = tasks[first + blockIdx.y];
   const int k = tk.k, r = tk.r;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -616,7 +630,7 @@ __global__ void __launch_bounds__(32 * kTrdBtWarps) trd_backtransform_kernel(con
   const double* gv = tk.work + L.v;
   const double* gtau = tk.work + L.tau;
   const double* gcross = tk.work + L.cross;
-  for (int e = tid; e < kTrdBtStages * 4 * KP; e += 32 * kTrdBtWarps) bt_sm[e] = 0.0;
+  for (int e = tid; e < kTrdBtStages * kStage; e += 32 * kTrdBtWarps) bt_sm[e] = 0.0;
   double x[NR];
 #pragma unroll
   for (int t = 0; t < NR; ++t) {
@@ -629,9 +643,18 @@ __global__ void __launch_bounds__(32 * kTrdBtWarps) trd_backtransform_kernel(con
   // stage loader: rows below 0 do not exist (their slots keep the zeros / stale rows, tau = 0 for them)
   auto load = [&](int g) {
     if (g < ngroups) {
-      double* dst = bt_sm + (size_t)(g % kTrdBtStages) * 4 * KP;
+      double* dst = bt_sm + (size_t)(g % kTrdBtStages) * kStage;
       const int j0 = k - 3 - 4 * g;
       const int nch = L.kp / 2;
+      if (tid < 4) {           // tau of rows j0 - tid (slots of rows below 0 keep an older, harmless tau: their
+        if (j0 - tid >= 0) {   // rows are stale as well, and the scalar below is forced to zero)
+          const uint32_t d = trd_smem_u32(dst + 4 * KP + tid);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gtau + j0 - tid) : "memory");
+        }
+      } else if (tid < 7) {
+        const uint32_t d = trd_smem_u32(dst + 4 * KP + 4 + 2 * (tid - 4));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gcross + 8 * g + 2 * (tid - 4)) : "memory");
+      }
       for (int q = 0; q < 4; ++q) {
         const int row = j0 - q;
         if (row < 0) break;
@@ -651,13 +674,14 @@ __global__ void __launch_bounds__(32 * kTrdBtWarps) trd_backtransform_kernel(con
     load(g + 2);
     asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncthreads();
-    const double* st = bt_sm + (size_t)(g % kTrdBtStages) * 4 * KP + lane;
+    const double* sb = bt_sm + (size_t)(g % kTrdBtStages) * kStage;
+    const double* st = sb + lane;
     const int j0 = k - 3 - 4 * g;
-    const double ta = gtau[j0], tb = j0 >= 1 ? gtau[j0 - 1] : 0.0, tc = j0 >= 2 ? gtau[j0 - 2] : 0.0,
-                 td = j0 >= 3 ? gtau[j0 - 3] : 0.0;
-    const double2 c01 = *reinterpret_cast<const double2*>(gcross + 8 * g);
-    const double2 c23 = *reinterpret_cast<const double2*>(gcross + 8 * g + 2);
-    const double2 c45 = *reinterpret_cast<const double2*>(gcross + 8 * g + 4);
+    const double ta = sb[4 * KP], tb = j0 >= 1 ? sb[4 * KP + 1] : 0.0, tc = j0 >= 2 ? sb[4 * KP + 2] : 0.0,
+                 td = j0 >= 3 ? sb[4 * KP + 3] : 0.0;
+    const double2 c01 = *reinterpret_cast<const double2*>(sb + 4 * KP + 4);
+    const double2 c23 = *reinterpret_cast<const double2*>(sb + 4 * KP + 6);
+    const double2 c45 = *reinterpret_cast<const double2*>(sb + 4 * KP + 8);
     double a[NR], b[NR], cc_[NR], d[NR];
     double ax = 0, bx = 0, cx = 0, dx = 0;
 #pragma unroll
@@ -753,7 +777,7 @@ static int trd_reduce_dispatch(int nr, const tta_symeig_task* tasks_dev, int fir
 
 template <int NR>
 static int trd_launch_backtransform(const tta_symeig_task* tasks_dev, int first, int count, int rmax, cudaStream_t st) {
-  const size_t smem = (size_t)kTrdBtStages * 4 * NR * 32 * sizeof(double);
+  const size_t smem = (size_t)kTrdBtStages * (4 * NR * 32 + 16) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set && smem > 48 * 1024) {
     int rc = check_cuda(cudaFuncSetAttribute(trd_backtransform_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
