@@ -178,15 +178,20 @@ class ADMM:
         return tab
 
     # ------------------------------------------------------------------------------------------
-    def update_from_host(self, host_w, host_z=None, update_u=True):
+    def update_from_host(self, host_w, host_z=None, update_u=True, gather_host_z=False):
         """Additive: `update()` for weights that live in (pinned) host memory.  `host_w[name]` is copied into the
         parameter and, when `host_z` is given, Z is copied back into `host_z[name]` -- group by group on the
         groups' own streams, so the transfers overlap the projection of the other groups (the critical group is
         uploaded first, and only its download is exposed at the end).  Synchronise the current stream before reading
-        `host_z`."""
-        self.update(update_u, _host_in=host_w, _host_out=host_z)
+        `host_z`.
 
-    def update(self, update_u=True, _host_in=None, _host_out=None):
+        Under torch.distributed every rank moves only ITS layers over PCIe: it uploads the weights of the layers it
+        projects, the other layers' weights arrive with a second all-gather over NVLink next to the one of Z (the dual
+        update needs W of every layer on every rank), and it downloads only the Z of its own layers -- the ranks' host
+        buffers together hold the result.  `gather_host_z=True` makes every rank download every layer's Z instead."""
+        self.update(update_u, _host_in=host_w, _host_out=host_z, _gather_host_z=gather_host_z)
+
+    def update(self, update_u=True, _host_in=None, _host_out=None, _gather_host_z=False):
         if not self._names:
             return
         import sharding
@@ -196,36 +201,13 @@ class ADMM:
         with torch.no_grad():
             local = set(self._shard.local_names)
             remote = [n for n in self._names if n not in local]
-            side = main = up_done = None
-            if remote and (_host_in is not None or _host_out is not None) and not rt.backend_is_emulated():
-                # parameters this rank does not project are only read by the dual update, and their Z arrives with
-                # the exchange: their transfers run on a copy stream of their own instead of delaying the local
-                # projection (they were 7/8 of the bytes on 8 GPUs)
-                dev = self._state_device()
-                main = torch.cuda.current_stream(dev)
-                if self._copy_stream is None:
-                    self._copy_stream = torch.cuda.Stream(device=dev)
-                side = self._copy_stream
-            if _host_in is not None and remote:
-                if side is not None:
-                    side.wait_stream(main)
-                    with torch.cuda.stream(side):
-                        self._copy(_host_in, remote, True)
-                        up_done = torch.cuda.Event()
-                        up_done.record(side)
-                else:
-                    self._copy(_host_in, remote, True)
             self._run_plans(_host_in, _host_out)
             self._shard.exchange(self.z)
-            if up_done is not None:
-                main.wait_event(up_done)
-            if _host_out is not None and remote:
-                if side is not None:
-                    side.wait_stream(main)                     # Z of the other ranks is complete after the exchange
-                    with torch.cuda.stream(side):
-                        self._copy(_host_out, remote, False)
-                else:
-                    self._copy(_host_out, remote, False)
+            if remote and _host_in is not None:
+                # W of the layers other ranks project: one all-gather of the weight slabs (NVLink), no PCIe traffic
+                self._shard.exchange_weights(self._params, self._shard.local_names, remote)
+            if remote and _host_out is not None and _gather_host_z:
+                self._copy(_host_out, remote, False)
             if update_u:
                 want_norm = self.log or self.verbose
                 sq = torch.zeros(len(self._names), dtype=torch.float64, device=self._state_device()) if want_norm else None
@@ -237,8 +219,6 @@ class ADMM:
                             self.logger[n].append(float(v))
                         if self.verbose:
                             print('*INFO: {} in ADMM, norm(w-z)={}'.format(n, v))
-            if side is not None:
-                main.wait_stream(side)       # the caller synchronises the current stream before reading host_z
 
     def _run_plans(self, host_in=None, host_out=None):
         """Z-update of the local layers.  Several TT plans (layer groups) are enqueued on side streams -- the

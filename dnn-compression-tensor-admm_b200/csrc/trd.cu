@@ -763,6 +763,11 @@ static int trd_launch_reduce(const tta_symeig_task* tasks_dev, int first, int co
   return TTA_OK;
 }
 
+// bench.py profiling aid: when enabled every trd_reduce launch is bracketed by CUDA events on the stream it runs on
+static bool g_trd_prof = false;
+struct TrdProfRec { cudaEvent_t a, b; };
+static std::vector<TrdProfRec> g_trd_recs;
+
 static int trd_reduce_dispatch(int nr, const tta_symeig_task* tasks_dev, int first, int count, int P, size_t smem,
                                cudaStream_t st) {
   switch (nr) {
@@ -813,6 +818,26 @@ size_t tta_symeig_work_doubles(int k, int r) {
 }
 
 int tta_symeig_max_k(void) { return tta::kTrdMaxK; }
+
+void tta_symeig_profile_enable(int on) { tta::g_trd_prof = on != 0; }
+
+void tta_symeig_profile_read(double* reduce_ms, unsigned long long* reduce_launches) {
+  using namespace tta;
+  double ms = 0.0;
+  unsigned long long n = 0;
+  for (TrdProfRec& r : g_trd_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms += t;
+      ++n;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_trd_recs.clear();
+  if (reduce_ms) *reduce_ms = ms;
+  if (reduce_launches) *reduce_launches = n;
+}
 
 int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_task* tasks_host, int n_tasks,
                            void* stream) {
@@ -875,8 +900,15 @@ int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_ta
         used[si] = true;
       }
     }
+    TrdProfRec rec = {nullptr, nullptr};
+    if (g_trd_prof && cudaEventCreate(&rec.a) == cudaSuccess && cudaEventCreate(&rec.b) == cudaSuccess)
+      cudaEventRecord(rec.a, gs);
     rc = trd_reduce_dispatch(rn.nr, tasks_dev, rn.first, rn.count, rn.P, trd_reduce_smem(rn.kmax, rn.P, rn.nr), gs);
     if (rc) return rc;
+    if (rec.b) {
+      cudaEventRecord(rec.b, gs);
+      g_trd_recs.push_back(rec);
+    }
   }
   if (pool) {
     for (int si = 0; si < kPoolStreams; ++si) {

@@ -64,6 +64,7 @@ class LayerSharding:
         self.names = list(names)
         self.group = group
         self.dist, self.rank, self.world = _dist_state()
+        self.flat_w = None
         if self.world == 1:
             self.local_names = list(self.names)
             self.owner = {n: 0 for n in self.names}
@@ -101,6 +102,26 @@ class LayerSharding:
             view.copy_(admm.z[n])
             admm.z[n] = view
         admm._ew_cache = None
+
+    def exchange_weights(self, params, local_names, remote_names):
+        """All-gather of the ranks' weight slabs (same layout as the Z buffer): after `update_from_host` uploaded
+        only the local layers' weights, every rank needs W of every layer for the dual update (admm.py:73)."""
+        if self.world == 1:
+            return
+        if self.flat_w is None:
+            self.flat_w = torch.zeros_like(self.flat)
+        view = lambda n: self.flat_w[self.owner[n] * self.slab + self.offset[n]:
+                                     self.owner[n] * self.slab + self.offset[n] + params[n].numel()].view(params[n].shape)
+        for n in local_names:
+            view(n).copy_(params[n].data)
+        mine = self.flat_w[self.rank * self.slab:(self.rank + 1) * self.slab]
+        if self.flat_w.is_cuda:
+            self.dist.all_gather_into_tensor(self.flat_w, mine, group=self.group)
+        else:
+            outs = [self.flat_w[r * self.slab:(r + 1) * self.slab] for r in range(self.world)]
+            self.dist.all_gather(outs, mine.clone(), group=self.group)
+        for n in remote_names:
+            params[n].data.copy_(view(n))
 
     def exchange(self, z):
         """One all-gather of the Z slabs (no-op for a single rank)."""

@@ -61,7 +61,8 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
            'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd',
-           'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k']
+           'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k',
+           'tta_symeig_profile_enable', 'tta_symeig_profile_read']
 
 
 class TtaError(RuntimeError):
@@ -126,6 +127,10 @@ def _load():
     lib.tta_symeig_work_doubles.argtypes = [ci, ci]
     lib.tta_symeig_work_doubles.restype = cs
     lib.tta_symeig_max_k.argtypes = []
+    lib.tta_symeig_profile_enable.argtypes = [ci]
+    lib.tta_symeig_profile_enable.restype = None
+    lib.tta_symeig_profile_read.argtypes = [vp, vp]
+    lib.tta_symeig_profile_read.restype = None
     for nm in ('tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
                'tta_refine_finalize_batched', 'tta_symeig_top_batched'):
         getattr(lib, nm).argtypes = [vp, vp, ci, vp]
@@ -140,6 +145,7 @@ def _load():
     lib.tta_lowrank2_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, ci, i64, ci, ci, ci, vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count', 'tta_symeig_work_doubles',
+                        'tta_symeig_profile_enable', 'tta_symeig_profile_read',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
                         'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc'):
             getattr(lib, name).restype = ci
@@ -313,6 +319,20 @@ def symeig_work_doubles(k, r):
 
 def symeig_max_k():
     return int(lib().tta_symeig_max_k())
+
+
+def symeig_profile(enable):
+    if _FAKE is None:
+        lib().tta_symeig_profile_enable(int(bool(enable)))
+
+
+def symeig_profile_read():
+    """(summed device ms of the tridiagonalisation launches, number of launches) since the last read."""
+    ms = ctypes.c_double(0.0)
+    n = ctypes.c_ulonglong(0)
+    if _FAKE is None:
+        lib().tta_symeig_profile_read(ctypes.byref(ms), ctypes.byref(n))
+    return ms.value, int(n.value)
 
 
 def _p(t):

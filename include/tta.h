@@ -276,6 +276,11 @@ int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_ta
                            void* stream);
 size_t tta_symeig_work_doubles(int k, int r);
 int tta_symeig_max_k(void);
+/* Profiling aid for bench.py: when enabled, every tridiagonalisation launch (the dominant kernel of an update) is
+ * bracketed by CUDA events on the stream it is launched on; `read` synchronises those events, returns the summed
+ * device time / number of launches since the last read and clears them. */
+void tta_symeig_profile_enable(int on);
+void tta_symeig_profile_read(double* reduce_ms, unsigned long long* reduce_launches);
 
 /* out[t] = sum of squares of n floats (fp64): tensorly `tl.norm(core, 2)**2` in the HOOI stopping rule. */
 typedef struct {

@@ -34,14 +34,24 @@ def _worker(rank, world, port, key, out_dir):
     a.update(update_u=False)
     a.update()
     # the last update goes through the host-buffer entry point: the parameters are zeroed first, so the result can
-    # only be right if update_from_host uploads the local AND the exchanged layers' weights
-    host_z = {n: torch.empty_like(w) for n, w in weights.items()}
+    # only be right if update_from_host uploads the local layers' weights AND the other ranks' weights arrive with
+    # the weight all-gather; every rank downloads only the Z of its own layers
+    host_z = {n: torch.full_like(w, float('nan')) for n, w in weights.items()}
     for n, prm in a.model.named_parameters():
         prm.data.zero_()
     a.update_from_host(weights, host_z)
-    for n in names:
-        assert torch.equal(host_z[n], a.z[n]), n
     local = list(a._shard.local_names)
+    for n, prm in a.model.named_parameters():
+        assert torch.equal(prm.data, weights[n]), n          # W of every layer is resident on every rank
+    for n in names:
+        if n in local:
+            assert torch.equal(host_z[n], a.z[n]), n
+        else:
+            assert bool(torch.isnan(host_z[n]).all()), n     # not this rank's to download
+    full_z = {n: torch.empty_like(w) for n, w in weights.items()}
+    a.update_from_host(weights, full_z, update_u=False, gather_host_z=True)
+    for n in names:
+        assert torch.equal(full_z[n], a.z[n]), n
     np.savez(os.path.join(out_dir, 'rank{}.npz'.format(rank)), local=np.array(local),
              n_proj=np.array(fake.calls.count('jacobi')),
              **{'z|' + n: a.z[n].numpy() for n in names}, **{'u|' + n: a.u[n].numpy() for n in names})
@@ -69,6 +79,7 @@ def test_sharded_update_matches_single_process(tmp_path, key):
     o.update(update_u=False)
     o.update()
     o.update()
+    o.update(update_u=False)            # the workers' fourth, Z-only update (gather_host_z variant)
     for n in names:
         assert np.array_equal(r0['z|' + n], r1['z|' + n]), n          # Z identical on every rank
         assert np.array_equal(r0['u|' + n], r1['u|' + n]), n          # U bit-identical across ranks
