@@ -46,11 +46,14 @@ REFINE_TASK = np.dtype([('x', P), ('qt', P), ('s', P), ('t', P), ('c', P), ('lam
 SYMEIG_TASK = np.dtype([('g', P), ('work', P), ('lam', P), ('e64', P), ('status', P), ('k', np.int32), ('r', np.int32)],
                        align=True)
 
+ORTH_TASK = np.dtype([('p', P), ('r', P), ('g', P), ('si', np.int64), ('st', np.int64), ('n', np.int32),
+                      ('len', np.int32)], align=True)
+
 STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.itemsize,
                 'tta_gram_task': GRAM_TASK.itemsize, 'tta_eig_task': EIG_TASK.itemsize,
                 'tta_select_task': SELECT_TASK.itemsize, 'tta_gemm_task': GEMM_TASK.itemsize,
                 'tta_sqnorm_task': SQNORM_TASK.itemsize, 'tta_refine_task': REFINE_TASK.itemsize,
-                'tta_symeig_task': SYMEIG_TASK.itemsize}
+                'tta_symeig_task': SYMEIG_TASK.itemsize, 'tta_orth_task': ORTH_TASK.itemsize}
 
 EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_device', 'tta_jacobi_profile_enable',
            'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch', 'tta_jacobi_enable_gra',
@@ -62,7 +65,8 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
            'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd',
            'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k',
-           'tta_symeig_profile_enable', 'tta_symeig_profile_read']
+           'tta_symeig_profile_enable', 'tta_symeig_profile_read', 'tta_orth_penalty_fwd_batched',
+           'tta_orth_penalty_bwd_batched']
 
 
 class TtaError(RuntimeError):
@@ -124,6 +128,8 @@ def _load():
     lib.tta_select_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_gemm_batched.argtypes = [vp, vp, ci, vp]
     lib.tta_sqnorm_batched.argtypes = [vp, vp, ci, vp, vp]
+    lib.tta_orth_penalty_fwd_batched.argtypes = [vp, vp, ci, cf, vp, vp]
+    lib.tta_orth_penalty_bwd_batched.argtypes = [vp, vp, ci, cf, vp, ci, vp]
     lib.tta_symeig_work_doubles.argtypes = [ci, ci]
     lib.tta_symeig_work_doubles.restype = cs
     lib.tta_symeig_max_k.argtypes = []
@@ -306,6 +312,18 @@ def refine_coeff(tab):
 def refine_finalize(tab):
     _check(lib().tta_refine_finalize_batched(tab.dev_ptr, tab.host_ptr, tab.n, stream_handle()),
            'tta_refine_finalize_batched')
+
+
+def orth_penalty_fwd(tab, rho, loss_out):
+    _check(lib().tta_orth_penalty_fwd_batched(tab.dev_ptr, tab.host_ptr, tab.n, float(rho),
+                                              ctypes.c_void_p(loss_out.data_ptr()), stream_handle()),
+           'tta_orth_penalty_fwd_batched')
+
+
+def orth_penalty_bwd(tab, rho, grad_scale, accumulate):
+    p = ctypes.c_void_p(grad_scale.data_ptr()) if grad_scale is not None else None
+    _check(lib().tta_orth_penalty_bwd_batched(tab.dev_ptr, tab.host_ptr, tab.n, float(rho), p, int(bool(accumulate)),
+                                              stream_handle()), 'tta_orth_penalty_bwd_batched')
 
 
 def symeig_top(tab):

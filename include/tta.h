@@ -68,6 +68,27 @@ int tta_penalty_bwd_multi(const tta_ew_task* tasks_dev, const tta_ew_task* tasks
                           float rho, const float* grad_scale, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Orthogonality regulariser of the decomposed layers' factor matrices (orthogonal.py:9-20; fine-tune loop
+ * engines.py:290-291,297-298).  One problem = n vectors of length len (element t of vector i at p + i*si + t*st; one
+ * of si, st is 1): a factor F with fewer rows than columns is its rows (si = cols, st = 1), otherwise its columns
+ * (si = 1, st = cols).     R = X X^T - I,   loss_out[0] += rho/2 * sum R^2   (fp64, caller zeroes it),
+ *                          g_i (+)= grad_scale[0] * 2 rho * sum_j R_ij x_j    (g laid out like p)
+ * fwd writes R into r (n*n floats per task), bwd reads it.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* p;
+  float* r;
+  float* g;       /* bwd only */
+  int64_t si, st;
+  int32_t n, len;
+} tta_orth_task;
+
+int tta_orth_penalty_fwd_batched(const tta_orth_task* tasks_dev, const tta_orth_task* tasks_host, int n_tasks,
+                                 float rho, double* loss_out, void* stream);
+int tta_orth_penalty_bwd_batched(const tta_orth_task* tasks_dev, const tta_orth_task* tasks_host, int n_tasks,
+                                 float rho, const float* grad_scale, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Unfold / fold (admm.py:45 + admm.py:96 and admm.py:99)
  * ------------------------------------------------------------------------------------------- */
 typedef struct {

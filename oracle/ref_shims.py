@@ -119,6 +119,8 @@ class Reference:
         self.TKConv = _load('TKConv')
         self.TKLinear = _load('TKLinear')
         self.resnet_cifar = _load('resnet_cifar')
+        self.SVDConv = _load('SVDConv')
+        self.orthogonal = _load('orthogonal')
 
     def hp_class(self, module, cls):
         full = 'refimpl_hp_' + module

@@ -298,6 +298,38 @@ class FakeTTA:
             np.lib.stride_tricks.as_strided(cbase, shape=(M, N), strides=(osz * ldc, osz))[:] = c.astype(odt)
         return 0
 
+    # ---- orthogonality regulariser ----
+    def _orth_x(self, tk):
+        n, ln, si, st = int(tk['n']), int(tk['len']), int(tk['si']), int(tk['st'])
+        base = _view(tk['p'], (n - 1) * si + (ln - 1) * st + 1)
+        return np.lib.stride_tricks.as_strided(base, shape=(n, ln), strides=(4 * si, 4 * st))
+
+    def tta_orth_penalty_fwd_batched(self, tdev, thost, n, rho, loss, stream):
+        self.calls.append('orth_fwd')
+        out = _view(_val(loss), 1, np.float64)
+        for tk in _table(thost, n, rt.ORTH_TASK):
+            x = self._orth_x(tk).astype(np.float32)
+            r = x @ x.T - np.eye(x.shape[0], dtype=np.float32)
+            _view(tk['r'], r.size)[:] = r.reshape(-1)
+            out[0] += 0.5 * float(np.float32(rho)) * float(np.sum(r.astype(np.float64) ** 2))
+        return 0
+
+    def tta_orth_penalty_bwd_batched(self, tdev, thost, n, rho, gscale, accumulate, stream):
+        self.calls.append('orth_bwd')
+        s = float(_view(_val(gscale), 1)[0]) if _val(gscale) else 1.0
+        for tk in _table(thost, n, rt.ORTH_TASK):
+            x = self._orth_x(tk).astype(np.float32)
+            nn, ln, si, st = int(tk['n']), int(tk['len']), int(tk['si']), int(tk['st'])
+            r = _view(tk['r'], nn * nn).reshape(nn, nn)
+            d = (np.float32(2.0 * rho * s) * (r @ x)).astype(np.float32)
+            gbase = _view(tk['g'], (nn - 1) * si + (ln - 1) * st + 1)
+            g = np.lib.stride_tricks.as_strided(gbase, shape=(nn, ln), strides=(4 * si, 4 * st))
+            if accumulate:
+                g += d
+            else:
+                g[:] = d
+        return 0
+
     def tta_sqnorm_batched(self, tdev, thost, n, out, stream):
         self.calls.append('sqnorm')
         o = _view(_val(out), n, np.float64)

@@ -158,7 +158,7 @@ def test_tucker_hooi_parity(key, golden_summary):
         check_summary(a.z[n].cpu().numpy(), gold['layers'][n]['z2'])
 
 
-@pytest.mark.parametrize('C,frac', [(64, 0.25), (128, 0.5), (256, 0.25)])
+@pytest.mark.parametrize('C,frac', [(64, 0.25), (128, 0.5), (256, 0.25), (512, 0.25)])
 def test_tucker_sweep_config(C, frac):
     from admm import ADMM
     weights = workloads.tucker_sweep_weight(C)
@@ -234,3 +234,37 @@ def test_warm_start_after_a_rank_deficient_update():
     assert max(max(v) for v in b.sweeps.values()) <= 4 < cold
     for n in names:
         assert rel_fro(b.z[n].cpu().numpy(), o.z[n]) <= Z_TOL, n
+
+
+def _tucker_sweep_golden():
+    with open(os.path.join(GOLDEN, 'tucker_sweep.json')) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize('case', _tucker_sweep_golden() if os.path.isfile(os.path.join(GOLDEN, 'tucker_sweep.json')) else [],
+                         ids=lambda c: 'C{}-r{}'.format(c['C'], c['ranks'][0]))
+def test_tucker_sweep_large_channels_against_oracle_records(case):
+    """BASELINE config 5 at C = 512 (k = 512: the fp64 tridiagonalisation solver) and C = 1024 (k = 1024: the
+    multi-launch Jacobi solver): same HOOI sweep count and the same Z (norm 2e-5, probe 8e-4 of the rms entry) as the
+    restated-tensorly oracle's committed records (oracle/gen_golden_tucker_sweep.py; parity UNPINNED)."""
+    from admm import ADMM
+    C, frac = case['C'], case['frac']
+    weights = workloads.tucker_sweep_weight(C)
+    hp = hp_tables.tucker_sweep(C, frac)
+    assert [int(r) for r in hp.ranks['weight']] == case['ranks']
+    a = ADMM(workloads.ParamBag(weights, device=DEV), 1e-3, hp, 'tk', DEV)
+    a.update(update_u=False)
+    assert a._plans[0][0].hooi_sweeps['weight'] == case['hooi_sweeps']
+    check_summary(a.z['weight'].cpu().numpy(), case['z'])
+
+
+def test_svd_projection_wider_than_the_cluster_solvers():
+    """A matrix-SVD step with min(m, n) = 640 > tta_symeig_max_k(): the multi-launch Jacobi solver inside a TT plan
+    (its convergence status reaches TTProjectionPlan.collect through the scratch buffer)."""
+    from admm import ADMM
+    g = torch.Generator().manual_seed(9)
+    weights = {'fc.weight': torch.randn(640, 700, generator=g)}
+    hp = hp_tables.HpTable('svd', {'fc.weight': 48})
+    a = ADMM(workloads.ParamBag(weights, device=DEV), 1e-3, hp, 'svd', DEV)
+    a.update()
+    assert rel_fro(a.z['fc.weight'].cpu().numpy(), port.project_linear_svd(weights['fc.weight'].numpy(), 48)) <= Z_TOL

@@ -312,3 +312,75 @@ def test_ten2tt_cores_are_orthonormal_like_the_reference(emulated_backend):
     ttd.ten2tt(x, [8, 6, 10], (1, 5, 7, 1))                      # no clip needed: a tuple is fine
     with pytest.raises(TypeError):
         ttd.ten2tt(x, [8, 6, 10], (1, 9, 7, 1))                  # clip 9 -> 8 must write into the tuple
+
+
+def _orth_reference(model, rho):
+    """orthogonal.py:9-20 restated with torch ops (the oracle of the regulariser)."""
+    total = torch.zeros((), dtype=torch.float64)
+    for name, p in model.named_parameters():
+        if any(k in name for k in ('first_kernel', 'last_kernel', 'first_factor', 'last_factor', 'left_kernel')):
+            m = torch.squeeze(p).double()
+            g = m @ m.t() if m.shape[0] < m.shape[1] else m.t() @ m
+            total = total + 0.5 * rho * torch.norm(g - torch.eye(g.shape[0], dtype=torch.float64), p=2) ** 2
+    return total
+
+
+def test_orthogonal_regulariser_matches_reference_formula(emulated_backend):
+    """`append_double_l2_loss` (orthogonal.py:9-20): value and gradient for wide, tall and 4-D (1x1 kernel) factors,
+    unselected parameters untouched, AMP-style scaled backward."""
+    import orthogonal
+    g = torch.Generator().manual_seed(7)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.first_factor = torch.nn.Parameter(torch.randn(6, 20, generator=g) * 0.3)         # wide: F F^T
+            self.last_factor = torch.nn.Parameter(torch.randn(40, 9, generator=g) * 0.3)          # tall: F^T F
+            self.first_kernel = torch.nn.Parameter(torch.randn(5, 33, 1, 1, generator=g) * 0.3)   # TKConv2dC
+            self.left_kernel = torch.nn.Parameter(torch.randn(37, 37, 1, 1, generator=g) * 0.2)   # square: F^T F
+            self.core_kernel = torch.nn.Parameter(torch.randn(4, 4, 3, 3, generator=g))           # not selected
+
+    net = Net()
+    rho = 0.05
+    base = torch.tensor(0.5, requires_grad=True)
+    loss = orthogonal.append_double_l2_loss(net, base * 2.0, rho, 'cpu')
+    ref = _orth_reference(net, rho)
+    assert abs(float(loss.detach()) - (1.0 + float(ref))) <= 1e-5 * (1.0 + float(ref))
+    (loss * 3.0).backward()
+    assert abs(float(base.grad) - 6.0) < 1e-6
+    grads = torch.autograd.grad(ref, [net.first_factor, net.last_factor, net.first_kernel, net.left_kernel])
+    for p, gr in zip([net.first_factor, net.last_factor, net.first_kernel, net.left_kernel], grads):
+        assert torch.allclose(p.grad.double(), 3.0 * gr.double(), rtol=1e-4, atol=1e-6)
+    assert net.core_kernel.grad is None
+    # a model without factor parameters: the loss is returned unchanged
+    lin = torch.nn.Linear(3, 3)
+    l0 = torch.zeros(())
+    assert orthogonal.append_double_l2_loss(lin, l0, rho, 'cpu') is l0
+
+
+def test_orthogonal_regulariser_against_reference_golden(emulated_backend):
+    """Host-side wiring of `append_double_l2_loss` against the reference's own run (tests/golden/forward_modules.*)."""
+    import json
+    import os
+    import orthogonal
+    from helpers import GOLDEN
+    with open(os.path.join(GOLDEN, 'forward_modules.json')) as f:
+        case = [c for c in json.load(f) if c['kind'] == 'orth'][0]
+    arr = np.load(os.path.join(GOLDEN, 'forward_modules.npz'))
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            for n in case['params']:
+                setattr(self, n, torch.nn.Parameter(torch.from_numpy(arr['orth|' + n]).clone()))
+
+    toy = Toy()
+    loss = orthogonal.append_double_l2_loss(toy, torch.zeros(()), case['rho'], 'cpu')
+    assert abs(float(loss.detach()) - case['loss']) <= 1e-5 * abs(case['loss'])
+    loss.backward()
+    for n, p in toy.named_parameters():
+        key = 'orth|grad|' + n
+        if key in arr.files:
+            assert np.allclose(p.grad.numpy(), arr[key], rtol=1e-4, atol=1e-6), n
+        else:
+            assert p.grad is None
