@@ -99,7 +99,11 @@ def wave_makespan_ms(ks):
     streams carry descending priorities) on the first GPC with enough free SMs; one CTA per SM."""
     if not ks:
         return 0.0
-    pending = sorted(ks, reverse=True)
+    whole = [k for k in ks if eig_ctas(k) > max(_GPC_SMS)]      # whole-GPU solves run one after another
+    pending = sorted((k for k in ks if eig_ctas(k) <= max(_GPC_SMS)), reverse=True)
+    serial = sum(eig_time_ms(k) for k in whole)
+    if not pending:
+        return serial
     free = list(_GPC_SMS)
     running = []                 # (end time, gpc, ctas)
     now, end = 0.0, 0.0
@@ -121,7 +125,7 @@ def wave_makespan_ms(ks):
             t_end, g, need = running.pop(0)
             now = t_end
             free[g] += need
-    return end
+    return end + serial
 
 
 TRD_MIN_K = 33          # k <= 32 stays on the one-CTA Jacobi solver (eig_cluster.cu)
@@ -873,7 +877,19 @@ class TKLayer:
         self.numel = self.O * self.I * self.KK
         if isinstance(ranks, int) or len(ranks) != 2:
             raise ValueError('Tucker-2 needs ranks [r_out, r_in] for {}'.format(name))
-        self.r0, self.r1 = min(int(ranks[0]), self.O), min(int(ranks[1]), self.I)
+        # A truncated SVD returns at most min(shape) vectors (tensorly slices U[:, :rank]): the HOSVD initialisation
+        # clips r_out to min(O, I*KK) and r_in to min(I, O*KK), and every HOOI half-sweep clips the factor it
+        # refreshes to the width of the partially projected unfolding (O x r_in*KK, I x r_out*KK) -- e.g. a linear
+        # layer with ranks [30, 20] ends with factors of 20 columns.  The fixed point is reached statically here.
+        r0 = min(int(ranks[0]), self.O, self.I * self.KK)
+        r1 = min(int(ranks[1]), self.I, self.O * self.KK)
+        while True:
+            n0 = min(r0, r1 * self.KK)
+            n1 = min(r1, n0 * self.KK)
+            if (n0, n1) == (r0, r1):
+                break
+            r0, r1 = n0, n1
+        self.r0, self.r1 = r0, r1
 
 
 class TKProjectionPlan:

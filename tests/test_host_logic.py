@@ -384,3 +384,23 @@ def test_orthogonal_regulariser_against_reference_golden(emulated_backend):
             assert np.allclose(p.grad.numpy(), arr[key], rtol=1e-4, atol=1e-6), n
         else:
             assert p.grad is None
+
+
+@pytest.mark.parametrize('shape,ranks', [((192, 384), [40, 72]), ((192, 384), [72, 40]), ((16, 8, 3, 3), [12, 8]),
+                                         ((8, 64, 1, 1), [8, 40]), ((64, 64, 3, 3), [32, 32]), ((6, 50), [9, 9])])
+def test_tucker_rank_clip_matches_the_oracle_factor_widths(shape, ranks):
+    """A truncated SVD returns at most min(shape) vectors, so HOOI may end with narrower factors than the requested
+    ranks; TKLayer resolves that statically and must agree with the oracle's factors (admm.py:116,124)."""
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal(shape).astype(np.float32)
+    w3 = w.reshape(shape[0], shape[1], -1)
+    _, factors = port.partial_tucker2(w3, list(ranks))
+    layer = projector.TKLayer('w', shape, list(ranks))
+    assert (layer.r0, layer.r1) == (factors[0].shape[1], factors[1].shape[1])
+
+
+def test_wave_makespan_with_whole_gpu_problems():
+    """Eigenproblems wider than the cluster solvers occupy the whole GPU and run after the clustered ones."""
+    t_small = projector.wave_makespan_ms([512, 256])
+    assert projector.wave_makespan_ms([640]) == pytest.approx(projector.eig_time_ms(640))
+    assert projector.wave_makespan_ms([512, 256, 640]) == pytest.approx(t_small + projector.eig_time_ms(640))
