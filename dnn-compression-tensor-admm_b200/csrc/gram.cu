@@ -38,6 +38,21 @@ __device__ __forceinline__ int64_t gram_off(const tta_gram_task& tk, int64_t rho
   return b * tk.sb + (rho - b * tk.nc) * tk.sc;
 }
 
+// operand element: a (+ a2)
+__device__ __forceinline__ float gram_ld(const tta_gram_task& tk, int64_t off) {
+  const float v = __ldg(tk.a + off);
+  return tk.a2 ? v + __ldg(tk.a2 + off) : v;
+}
+
+// tensor-core route (gram_tc.cu)
+__host__ __device__ bool gram_tc_eligible(const tta_gram_task& tk);
+bool gram_tc_enabled();
+int gram_tc_run(const tta_gram_task* host, int cnt, cudaStream_t st);
+
+struct GramFinishFlags {
+  unsigned char tc[kGramMaxTasks];      // 1: `part` holds fp32 partials of 128 x 128 tiles (tensor-core pass)
+};
+
 // TS x TS output tiles, TT x TT outputs per thread: <64, 4> for 32 < k <= 64, <32, 2> for k <= 32 (the
 // first and last TT steps of a k x k convolution have k = r <= 32 and a reduction length of up to
 // 73 728: a 64-wide tile would spend 3/4 .. 15/16 of its DFMAs on padding).
@@ -96,8 +111,8 @@ __global__ void __launch_bounds__(kGramThreads) gram_partial(const tta_gram_task
         const int64_t rho = rr + kk;
         const bool rok = rho < rend;
         const int64_t off = rok ? gram_off(tk, rho) : 0;
-        ra[q] = (rok && (i0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(i0 + row) * tk.si + off) : 0.f;
-        rb[q] = (!diag && rok && (j0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(j0 + row) * tk.si + off) : 0.f;
+        ra[q] = (rok && (i0 + row) < tk.k) ? gram_ld(tk, (int64_t)(i0 + row) * tk.si + off) : 0.f;
+        rb[q] = (!diag && rok && (j0 + row) < tk.k) ? gram_ld(tk, (int64_t)(j0 + row) * tk.si + off) : 0.f;
       }
     };
     fetch(rbeg);
@@ -204,8 +219,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_partial_big(const tta_gr
         const int64_t rho = rr + kk;
         const bool rok = rho < rend;
         const int64_t off = rok ? gram_off(tk, rho) : 0;
-        ra[q] = (rok && (i0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(i0 + row) * tk.si + off) : 0.f;
-        rb[q] = (!diag && rok && (j0 + row) < tk.k) ? __ldg(tk.a + (int64_t)(j0 + row) * tk.si + off) : 0.f;
+        ra[q] = (rok && (i0 + row) < tk.k) ? gram_ld(tk, (int64_t)(i0 + row) * tk.si + off) : 0.f;
+        rb[q] = (!diag && rok && (j0 + row) < tk.k) ? gram_ld(tk, (int64_t)(j0 + row) * tk.si + off) : 0.f;
       }
     };
     auto stash = [&](int buf) {
@@ -266,8 +281,10 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_partial_big(const tta_gr
 }
 
 // x[col*ld + row] = sum_s part[s][max-tile-ordered (row,col)]; zero padding beyond k.
-__global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restrict__ tasks) {
+__global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restrict__ tasks,
+                                                   const __grid_constant__ GramFinishFlags flags) {
   const tta_gram_task tk = tasks[blockIdx.y];
+  const bool tcp = flags.tc[blockIdx.y] != 0;
   const int64_t total = (int64_t)tk.ld * tk.kpad;
   const int64_t kk2 = (int64_t)tk.k * tk.k;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -277,11 +294,18 @@ __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restri
     float v = 0.f;
     if (row < tk.k && col < tk.k) {
       int i = row, j = col;
-      const int tsz = gram_tile(gram_class(tk));
-      if ((i / tsz) < (j / tsz)) { i = col; j = row; }  // stored tiles have ti >= tj
-      const double* p = tk.part + (int64_t)i * tk.k + j;
+      const int tsz = tcp ? 128 : gram_tile(gram_class(tk));
+      // stored tiles have ti >= tj; the tensor-core tiles on the diagonal are not bitwise symmetric (lo*hi and hi*lo
+      // swap roles across the diagonal): the lower triangle is taken
+      if (tcp ? (i < j) : ((i / tsz) < (j / tsz))) { i = col; j = row; }
       double s = 0.0;
-      for (int sidx = 0; sidx < tk.nsplit; ++sidx) s += p[(int64_t)sidx * kk2];
+      if (tcp) {
+        const float* p = reinterpret_cast<const float*>(tk.part) + (int64_t)i * tk.k + j;
+        for (int sidx = 0; sidx < tk.nsplit; ++sidx) s += (double)p[(int64_t)sidx * kk2];
+      } else {
+        const double* p = tk.part + (int64_t)i * tk.k + j;
+        for (int sidx = 0; sidx < tk.nsplit; ++sidx) s += p[(int64_t)sidx * kk2];
+      }
       v = (float)s;
       if (tk.g64) tk.g64[(int64_t)row * tk.k + col] = s;
     }
@@ -320,9 +344,27 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
       const int64_t el = (int64_t)tk.ld * tk.kpad;
       max_elems = el > max_elems ? el : max_elems;
     }
+    // tensor-core route: TMA-addressable tasks are computed by gram_tc_kernel (fp32 partials)
+    GramFinishFlags flags;
+    bool any_cc = false;
+    {
+      tta_gram_task tcs[kGramMaxTasks];
+      int ntc = 0;
+      const bool on = gram_tc_enabled();
+      for (int t = 0; t < cnt; ++t) {
+        const tta_gram_task& tk = tasks_host[first + t];
+        flags.tc[t] = (on && gram_tc_eligible(tk)) ? 1 : 0;
+        if (flags.tc[t]) tcs[ntc++] = tk; else any_cc = true;
+      }
+      for (int t = cnt; t < kGramMaxTasks; ++t) flags.tc[t] = 0;
+      if (ntc) {
+        const int rc = gram_tc_run(tcs, ntc, st);
+        if (rc) return rc;
+      }
+    }
     // pass 0: k <= 32 on 32 x 32 tiles; pass 1: k <= 64 on 64 x 64 tiles; pass 2: larger k on 128 x 128
     // tiles.  A task that does not belong to a pass contributes zero tiles to its table.
-    for (int pass = 0; pass < 3; ++pass) {
+    for (int pass = 0; any_cc && pass < 3; ++pass) {
       GramTable tab;
       tab.n_tasks = cnt;
       int64_t total = 0;
@@ -330,7 +372,7 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
       for (int t = 0; t < cnt; ++t) {
         const tta_gram_task& tk = tasks_host[first + t];
         tab.start[t] = (int)total;
-        if (gram_class(tk) != pass) continue;
+        if (flags.tc[t] || gram_class(tk) != pass) continue;
         const int T = (tk.k + tsz - 1) / tsz;
         total += (int64_t)(T * (T + 1) / 2) * tk.nsplit;
         if (total > 0x7fffffff) {
@@ -356,7 +398,7 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
     int gx = (int)((max_elems + 255) / 256);
     if (gx > kNumSMs * 4) gx = kNumSMs * 4;
     if (gx < 1) gx = 1;
-    gram_finish<<<dim3(gx, cnt), 256, 0, st>>>(tasks_dev + first);
+    gram_finish<<<dim3(gx, cnt), 256, 0, st>>>(tasks_dev + first, flags);
     TTA_CHECK_LAUNCH("gram_finish launch");
   }
   return TTA_OK;

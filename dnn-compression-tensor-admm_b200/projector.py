@@ -484,12 +484,12 @@ class TTProjectionPlan:
                 x = st['X'].ptr if st['X'] is not None else 0
                 g64 = st['g64'].ptr if 'g64' in st else 0
                 if m <= n:   # row Gram A A^T
-                    g[q] = (a, st['part'].ptr, x, g64, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'])
+                    g[q] = (a, st['part'].ptr, x, g64, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'], 0)
                     sel[q] = (x, st['E'].ptr, st['core'].ptr, 0, 0, 0, k, st['ld'], r, 0)
                     # carry' (r x n) = E (r x m) * A (m x n)
                     mm[q] = (st['E'].ptr, a, st['carry'].ptr, 0, m, 1, n, 1, n, r, n, m, 0)
                 else:        # column Gram A^T A
-                    g[q] = (a, st['part'].ptr, x, g64, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'])
+                    g[q] = (a, st['part'].ptr, x, g64, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'], 0)
                     sel[q] = (x, st['E'].ptr, 0, st['carry'].ptr, st['sigma'].ptr, st['isigma'].ptr,
                               k, st['ld'], r, 0)
                     # core (m x r) = A (m x n) * E^T (n x r) * diag(1/sigma)
@@ -763,7 +763,7 @@ class EigBatch:
         g = np.zeros(n, dtype=rt.GRAM_TASK)
         for q, (b, op) in enumerate(problems):
             g[q] = (op['a'], b['part'].ptr, b['X'].ptr if b['X'] is not None else 0, b['g64'].ptr, op['si'], op['sb'],
-                    op['sc'], b['k'], op['nb'], op['nc'], b['nsplit'], b['ld'], b['kpad'])
+                    op['sc'], b['k'], op['nb'], op['nc'], b['nsplit'], b['ld'], b['kpad'], op.get('a2', 0))
         jq = [q for q, (b, _) in enumerate(problems) if not b['trd']]
         tq = sorted((q for q, (b, _) in enumerate(problems) if b['trd']), key=lambda q: -problems[q][0]['k'])
         nj, nt = len(jq), len(tq)

@@ -28,7 +28,7 @@ FOLD_TASK = np.dtype([('w', P), ('u', P), ('t', P), ('z', P), ('O', np.int32), (
                       ('KK', np.int32), ('pad_', np.int32)], align=True)
 GRAM_TASK = np.dtype([('a', P), ('part', P), ('x', P), ('g64', P), ('si', np.int64), ('sb', np.int64), ('sc', np.int64),
                       ('k', np.int32), ('nb', np.int32), ('nc', np.int32), ('nsplit', np.int32),
-                      ('ld', np.int32), ('kpad', np.int32)], align=True)
+                      ('ld', np.int32), ('kpad', np.int32), ('a2', P)], align=True)
 EIG_TASK = np.dtype([('x', P), ('k', np.int32), ('ld', np.int32), ('kpad', np.int32), ('bw', np.int32)],
                     align=True)
 SELECT_TASK = np.dtype([('x', P), ('e', P), ('et', P), ('se', P), ('sigma', P), ('isigma', P),
@@ -57,7 +57,7 @@ STRUCT_SIZES = {'tta_ew_task': EW_TASK.itemsize, 'tta_fold_task': FOLD_TASK.item
 
 EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_device', 'tta_jacobi_profile_enable',
            'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch', 'tta_jacobi_enable_gra',
-           'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_dual_update_multi',
+           'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_gram_enable_tc', 'tta_dual_update_multi',
            'tta_penalty_fwd_multi', 'tta_penalty_bwd_multi', 'tta_unfold_add_batched',
            'tta_fold_store_batched', 'tta_gram_batched', 'tta_jacobi_eigh_batched',
            'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
@@ -431,6 +431,13 @@ def gemm_enable_tc(on):
     K = 480, which the small-gap TT projections amplify past the 1e-4 parity bar on DeiT-small)."""
     if _FAKE is None:
         lib().tta_gemm_enable_tc(int(bool(on)))
+
+
+def gram_enable_tc(on):
+    """False keeps every Gram task on the fp64 CUDA-core kernels (the library default routes TMA-addressable operands
+    to the tcgen05 3xTF32 kernel of csrc/gram_tc.cu)."""
+    if _FAKE is None:
+        lib().tta_gram_enable_tc(int(bool(on)))
 
 
 def jacobi_enable_gra(on):

@@ -125,10 +125,20 @@ typedef struct {
   int64_t si, sb, sc;
   int32_t k, nb, nc, nsplit;
   int32_t ld, kpad;
+  const float* a2; /* nullable: second addend, same indexing -- the operand is a + a2 (V = W + U of admm.py:45 read in
+                    * place: the first TT step / HOSVD mode needs no materialised sum) */
 } tta_gram_task;
 
 int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_task* tasks_host, int n_tasks,
                      void* stream);
+/* Default on: tasks whose operand TMA can address (nb == 1, one of the two indices contiguous, 16-byte aligned base and
+ * pitch, reduction length >= 32) are computed on the tensor cores -- TMA boxes of a (and a2) -> hi / lo TF32 split in
+ * shared memory -> tcgen05.mma kind::tf32 (lo*hi + hi*lo + hi*hi) with a FRESH TMEM accumulator for every 32
+ * reduction indices, drained into fp32 registers (round to nearest) and summed over slices in fp64.  The tensor core's
+ * accumulator truncates: its error grows linearly with the accumulation length (3.5e-6 at 512, measured), 1.3e-7 for
+ * one 32-index block.  The remaining tasks, and all tasks when off, use the fp64 CUDA-core kernels.  `part` is
+ * reinterpreted as float[nsplit][k][k] by the tensor-core path. */
+void tta_gram_enable_tc(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * Symmetric eigensolver: one-sided (Hestenes) block Jacobi on the columns of X = G

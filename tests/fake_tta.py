@@ -114,6 +114,9 @@ class FakeTTA:
             base = _view(tk['a'], span)
             a = np.lib.stride_tricks.as_strided(base, shape=(k, nb, nc), strides=(4 * si, 4 * sb, 4 * sc))
             a = a.reshape(k, nb * nc).astype(np.float64)
+            if tk['a2']:
+                b2 = np.lib.stride_tricks.as_strided(_view(tk['a2'], span), shape=(k, nb, nc), strides=(4 * si, 4 * sb, 4 * sc))
+                a = (a.astype(np.float32) + b2.reshape(k, nb * nc)).astype(np.float64)      # fp32 sum, as on the device
             g = a @ a.T
             ld, kpad = int(tk['ld']), int(tk['kpad'])
             if tk['x']:

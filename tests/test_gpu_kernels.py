@@ -80,9 +80,10 @@ def test_unfold_fold_exact(O, I, KK):
     assert np.array_equal(z.cpu().numpy().reshape(O, I, KK), W + U)
 
 
-def _gram_task(a, x, part, k, si, sb, sc, nb, nc, nsplit, ld, kpad):
+def _gram_task(a, x, part, k, si, sb, sc, nb, nc, nsplit, ld, kpad, a2=None, g64=None):
     tab = np.zeros(1, dtype=rt.GRAM_TASK)
-    tab[0] = (a.data_ptr(), part.data_ptr(), x.data_ptr(), 0, si, sb, sc, k, nb, nc, nsplit, ld, kpad)
+    tab[0] = (a.data_ptr(), part.data_ptr(), x.data_ptr() if x is not None else 0, g64.data_ptr() if g64 is not None else 0,
+              si, sb, sc, k, nb, nc, nsplit, ld, kpad, a2.data_ptr() if a2 is not None else 0)
     return rt.TaskTable(tab, DEV)
 
 
@@ -104,10 +105,72 @@ def test_gram_row_and_col(m, n, nsplit):
         else:
             tab = _gram_task(a, x, part, k, 1, 0, n, 1, m, nsplit, ld, kpad)
             G = A.astype(np.float64).T @ A.astype(np.float64)
-        rt.gram(tab)
+        rt.gram_enable_tc(False)             # the fp64 CUDA-core kernels (operands TMA cannot address use them)
+        try:
+            rt.gram(tab)
+        finally:
+            rt.gram_enable_tc(True)
         X = x.cpu().numpy().reshape(kpad, ld)
         assert np.allclose(X[:k, :k], G.astype(np.float32).T, rtol=2e-7, atol=1e-12 * np.abs(G).max())  # fp64 accumulation
         assert not X[k:].any() and not X[:, k:].any()                 # zero padding
+
+
+@pytest.mark.parametrize('m,n,nsplit', [(8, 4608, 9), (32, 73728, 48), (64, 576, 2), (75, 512, 1), (130, 512, 3),
+                                        (480, 4608, 18), (512, 948, 4), (300, 100, 1), (1680, 32, 3), (96, 36, 1)])
+@pytest.mark.parametrize('with_u', [False, True])
+def test_gram_tensor_core(m, n, nsplit, with_u):
+    """tcgen05 3xTF32 Gram (csrc/gram_tc.cu), TMA-fed, the optional second addend summed in shared memory: row and
+    column Grams against fp64, error relative to sqrt(g_ii g_jj) (the accumulator is flushed every 32 indices, so the
+    error does not grow with the reduction length: 1e-7 grade, tolerance 5e-7)."""
+    rng = np.random.RandomState(m + n)
+    A = rng.randn(m, n).astype(np.float32)
+    U = (0.3 * rng.randn(m, n)).astype(np.float32) if with_u else None
+    a = _t(A)
+    u = _t(U) if with_u else None
+    V = (A + U) if with_u else A
+    V64 = V.astype(np.float64)
+    for mode in ('row', 'col'):
+        k = m if mode == 'row' else n
+        if k > 640 or (k if mode == 'col' else n) % 4:
+            continue
+        ld, kpad = (k + 3) // 4 * 4, (k + 15) // 16 * 16
+        x = torch.full((kpad * ld,), 7.0, device=DEV)
+        g64 = torch.full((k * k,), 7.0, dtype=torch.float64, device=DEV)
+        part = torch.empty(nsplit * k * k, dtype=torch.float64, device=DEV)
+        if mode == 'row':
+            tab = _gram_task(a, x, part, k, n, 0, 1, 1, n, nsplit, ld, kpad, a2=u, g64=g64)
+            G = V64 @ V64.T
+        else:
+            tab = _gram_task(a, x, part, k, 1, 0, n, 1, m, nsplit, ld, kpad, a2=u, g64=g64)
+            G = V64.T @ V64
+        n0 = rt.launch_count()
+        rt.gram(tab)
+        torch.cuda.synchronize()
+        assert rt.launch_count() - n0 == 2            # gram_tc_kernel + gram_finish: no CUDA-core partial pass
+        got = g64.cpu().numpy().reshape(k, k)
+        scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
+        err = np.abs(got - G) / scale
+        assert err.max() <= 5e-7, (mode, err.max())
+        assert np.array_equal(got, got.T)
+        X = x.cpu().numpy().reshape(kpad, ld)
+        assert np.array_equal(X[:k, :k], got.astype(np.float32).T)
+        assert not X[k:].any() and not X[:, k:].any()
+
+
+def test_gram_second_addend_on_cuda_cores():
+    """a2 on the fp64 CUDA-core kernels (operand not TMA-addressable: odd pitch)."""
+    rng = np.random.RandomState(12)
+    m, n = 40, 1001
+    A = rng.randn(m, n).astype(np.float32)
+    U = rng.randn(m, n).astype(np.float32)
+    a, u = _t(A), _t(U)
+    k, ld, kpad = m, 40, 48
+    x = torch.empty(kpad * ld, device=DEV)
+    part = torch.empty(2 * k * k, dtype=torch.float64, device=DEV)
+    rt.gram(_gram_task(a, x, part, k, n, 0, 1, 1, n, 2, ld, kpad, a2=u))
+    V = (A + U).astype(np.float64)
+    G = V @ V.T
+    assert np.allclose(x.cpu().numpy().reshape(kpad, ld)[:k, :k], G.astype(np.float32).T, rtol=2e-7, atol=1e-12 * np.abs(G).max())
 
 
 def test_gram_mode_layout():
