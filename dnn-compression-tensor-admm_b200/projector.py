@@ -158,12 +158,13 @@ def refine_window(k, r):
 
 
 def gram_splits(k, red_len):
-    """Slices of the reduction range per Gram problem: enough tiles x slices to fill the SMs twice,
-    at least 512 reduction indices per slice, at most 48 slices (the finish kernel sums them)."""
-    ts = 32 if k <= 32 else 64 if (k <= 64 or red_len < 1536) else 128   # csrc/gram.cu: gram_class
-    tiles = (k + ts - 1) // ts
+    """Slices of the reduction range per Gram problem (one CTA per 128 x 128 lower-triangular tile and slice on the
+    tensor-core path, csrc/gram_tc.cu): enough tiles x slices for every SM, at least 256 reduction indices (8 k-blocks)
+    per slice, at most 148 slices (the finish kernel sums them in fp64).  The fp64 CUDA-core kernels, which serve
+    the operands TMA cannot address, take the same split (their tiles are 32 / 64 / 128 wide)."""
+    tiles = (k + 127) // 128
     pairs = tiles * (tiles + 1) // 2
-    return max(1, min((red_len + 511) // 512, (296 + pairs - 1) // pairs, 48))
+    return max(1, min((red_len + 255) // 256, (148 + pairs - 1) // pairs, 148))
 
 
 def tt_step_flops(shapes, ranks):
@@ -333,6 +334,7 @@ class TTProjectionPlan:
         # bisection + twisted factorisation (no refinement, no warm start needed), 'jacobi' = round-1 path.  A plan
         # whose trd solve reports inseparable eigenvalues (exactly repeated singular values) switches to 'jacobi'.
         self.solver = default_solver() if refine else 'jacobi'
+        self.gram_in_place = os.environ.get('TTA_GRAM_IN_PLACE', '1') != '0'
         self._last = None
         self._warm_valid = False
         self._warm_used = False      # the update being collected was warm-started
@@ -483,13 +485,23 @@ class TTProjectionPlan:
                 a = st['A'].ptr
                 x = st['X'].ptr if st['X'] is not None else 0
                 g64 = st['g64'].ptr if 'g64' in st else 0
+                # The Gram matrix of the first step is formed from W and U IN PLACE (tta_gram_task.a2): a row Gram does
+                # not depend on the order of the reduction index, so the (O, I, KK) -> (O, KK, I) permute of admm.py:96
+                # is irrelevant to it as long as a row of the unfolding is made of whole output channels; without a
+                # spatial extent (KK == 1) there is no permute at all.  T = unfold(W + U) feeds the projection GEMM only.
+                li, si = members[q]
+                L = self.layers[li]
+                ga, ga2 = a, 0
+                if si == 0 and self.gram_in_place and (L.KK == 1 or (m <= n and n % (L.I * L.KK) == 0)):
+                    ga = w_list[li].data_ptr()
+                    ga2 = u_list[li].data_ptr() if u_list[li] is not None else 0
                 if m <= n:   # row Gram A A^T
-                    g[q] = (a, st['part'].ptr, x, g64, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'], 0)
+                    g[q] = (ga, st['part'].ptr, x, g64, n, 0, 1, k, 1, n, st['nsplit'], st['ld'], st['kpad'], ga2)
                     sel[q] = (x, st['E'].ptr, st['core'].ptr, 0, 0, 0, k, st['ld'], r, 0)
                     # carry' (r x n) = E (r x m) * A (m x n)
                     mm[q] = (st['E'].ptr, a, st['carry'].ptr, 0, m, 1, n, 1, n, r, n, m, 0)
                 else:        # column Gram A^T A
-                    g[q] = (a, st['part'].ptr, x, g64, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'], 0)
+                    g[q] = (ga, st['part'].ptr, x, g64, 1, 0, n, k, 1, m, st['nsplit'], st['ld'], st['kpad'], ga2)
                     sel[q] = (x, st['E'].ptr, 0, st['carry'].ptr, st['sigma'].ptr, st['isigma'].ptr,
                               k, st['ld'], r, 0)
                     # core (m x r) = A (m x n) * E^T (n x r) * diag(1/sigma)
@@ -912,6 +924,7 @@ class TKProjectionPlan:
         self.hooi_sweeps = {}
         self.errors = {}
         self.profile = None
+        self.gram_in_place = os.environ.get('TTA_GRAM_IN_PLACE', '1') != '0'
         self._alloc(None)
 
     def _alloc(self, solver):
@@ -964,7 +977,9 @@ class TKProjectionPlan:
             self.row['nx'][li] = (T, L.numel)
             self.row['nc'][li] = (w['core'].ptr, r0 * KK * r1)
             self.gram_ops.append(dict(
-                init0=dict(a=T, si=KK * I, sb=0, sc=1, nb=1, nc=KK * I),            # unfold_0(X) rows
+                # unfold_0(X) rows: read from W and U in place (the order of the reduction index is irrelevant)
+                init0=(dict(a=w_list[li].data_ptr(), a2=up, si=KK * I, sb=0, sc=1, nb=1, nc=KK * I) if self.gram_in_place
+                       else dict(a=T, si=KK * I, sb=0, sc=1, nb=1, nc=KK * I)),
                 init1=dict(a=T, si=1, sb=0, sc=I, nb=1, nc=O * KK),                  # columns of (O*KK x I)
                 sweep0=dict(a=w['P0'].ptr, si=KK * r1, sb=0, sc=1, nb=1, nc=KK * r1),
                 sweep1=dict(a=w['P1'].ptr, si=1, sb=0, sc=I, nb=1, nc=r0 * KK)))
