@@ -158,7 +158,8 @@ namespace tta {
 // tensor-core path for fp32 tasks (gemm_tf32.cu)
 bool gemm_tf32x3_eligible(const tta_gemm_task& tk);
 int gemm_tf32x3_run(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int cnt, cudaStream_t st);
-static bool g_gemm_tc = false;   // see DESIGN.md: 3xTF32 accumulation error is amplified by the small-gap projections
+void gemm_tf32x3_set_mode(int mode);
+int gemm_tf32x3_mode();
 
 template <typename T>
 static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks, void* stream) {
@@ -179,7 +180,7 @@ static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* task
         return TTA_E_INVALID;
       }
       tab.start[t] = (int)total;
-      if (sizeof(T) == 4 && g_gemm_tc && gemm_tf32x3_eligible(tk)) continue;   // served by the tcgen05 kernel below
+      if (sizeof(T) == 4 && gemm_tf32x3_eligible(tk)) continue;   // served by the tcgen05 kernel below
       total += (int64_t)((tk.M + kGemmBM - 1) / kGemmBM) * ((tk.N + kGemmBN - 1) / kGemmBN);
       if (total > 0x7fffffff) {
         set_error("gemm: too many tiles");
@@ -188,7 +189,7 @@ static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* task
     }
     tab.start[cnt] = (int)total;
     tab.total = (int)total;
-    if (sizeof(T) == 4 && g_gemm_tc) {
+    if (sizeof(T) == 4 && gemm_tf32x3_mode()) {
       const int rc = gemm_tf32x3_run(tasks_dev + first, tasks_host + first, cnt, st);
       if (rc) return rc;
     }
@@ -203,7 +204,7 @@ static int launch_gemm(const tta_gemm_task* tasks_dev, const tta_gemm_task* task
 
 extern "C" {
 
-void tta_gemm_enable_tc(int on) { tta::g_gemm_tc = on != 0; }
+void tta_gemm_enable_tc(int on) { tta::gemm_tf32x3_set_mode(on < 0 ? 0 : on > 2 ? 2 : on); }
 
 int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
                      void* stream) {

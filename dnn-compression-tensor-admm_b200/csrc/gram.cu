@@ -280,36 +280,57 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_partial_big(const tta_gr
   }
 }
 
-// x[col*ld + row] = sum_s part[s][max-tile-ordered (row,col)]; zero padding beyond k.
+// G = sum over slices of the partial tiles (fp64, fixed order), mirrored; stored as the eigensolver's column state
+// x[col*ld + row] (fp32, zero padded to ld x kpad) and / or as the k x k fp64 matrix g64.
+// Eight lanes share one element of the lower triangle (i >= j, consecutive lanes groups take consecutive j: the
+// partial rows are read contiguously) and split the slices between them; both partial kernels store the tiles that
+// hold the lower triangle, and the tensor-core tiles on the diagonal are not bitwise symmetric (lo*hi and hi*lo swap
+// roles across the diagonal), so the lower triangle is the one that is taken.
 __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restrict__ tasks,
                                                    const __grid_constant__ GramFinishFlags flags) {
   const tta_gram_task tk = tasks[blockIdx.y];
   const bool tcp = flags.tc[blockIdx.y] != 0;
-  const int64_t total = (int64_t)tk.ld * tk.kpad;
   const int64_t kk2 = (int64_t)tk.k * tk.k;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int col = (int)(e / tk.ld);
-    const int row = (int)(e - (int64_t)col * tk.ld);
-    float v = 0.f;
-    if (row < tk.k && col < tk.k) {
-      int i = row, j = col;
-      const int tsz = tcp ? 128 : gram_tile(gram_class(tk));
-      // stored tiles have ti >= tj; the tensor-core tiles on the diagonal are not bitwise symmetric (lo*hi and hi*lo
-      // swap roles across the diagonal): the lower triangle is taken
-      if (tcp ? (i < j) : ((i / tsz) < (j / tsz))) { i = col; j = row; }
-      double s = 0.0;
+  const int sub = threadIdx.x & 7;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int grp = (threadIdx.x & 31) >> 3;
+  for (int64_t e0 = (gtid >> 5) * 4; e0 < kk2; e0 += nthr >> 3) {       // warp-uniform trip count (full-mask shuffles)
+    const int64_t e = e0 + grp;
+    const int i = (int)(e / tk.k);
+    const int j = (int)(e - (int64_t)i * tk.k);
+    const bool lower = e < kk2 && j <= i;
+    double s = 0.0;
+    if (lower) {
       if (tcp) {
-        const float* p = reinterpret_cast<const float*>(tk.part) + (int64_t)i * tk.k + j;
-        for (int sidx = 0; sidx < tk.nsplit; ++sidx) s += (double)p[(int64_t)sidx * kk2];
+        const float* p = reinterpret_cast<const float*>(tk.part) + e;
+        for (int sidx = sub; sidx < tk.nsplit; sidx += 8) s += (double)p[(int64_t)sidx * kk2];
       } else {
-        const double* p = tk.part + (int64_t)i * tk.k + j;
-        for (int sidx = 0; sidx < tk.nsplit; ++sidx) s += p[(int64_t)sidx * kk2];
+        const double* p = tk.part + e;
+        for (int sidx = sub; sidx < tk.nsplit; sidx += 8) s += p[(int64_t)sidx * kk2];
       }
-      v = (float)s;
-      if (tk.g64) tk.g64[(int64_t)row * tk.k + col] = s;
     }
-    if (tk.x) tk.x[e] = v;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (lower && sub == 0) {
+      if (tk.g64) {
+        tk.g64[(int64_t)i * tk.k + j] = s;
+        tk.g64[(int64_t)j * tk.k + i] = s;
+      }
+      if (tk.x) {
+        tk.x[(int64_t)j * tk.ld + i] = (float)s;
+        tk.x[(int64_t)i * tk.ld + j] = (float)s;
+      }
+    }
+  }
+  if (tk.x) {   // zero padding of the column state beyond k
+    const int64_t total = (int64_t)tk.ld * tk.kpad;
+    for (int64_t e = gtid; e < total; e += nthr) {
+      const int col = (int)(e / tk.ld);
+      const int row = (int)(e - (int64_t)col * tk.ld);
+      if (row >= tk.k || col >= tk.k) tk.x[e] = 0.f;
+    }
   }
 }
 
@@ -341,7 +362,7 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
                   tk.nc, tk.nsplit, tk.ld, tk.kpad);
         return TTA_E_INVALID;
       }
-      const int64_t el = (int64_t)tk.ld * tk.kpad;
+      const int64_t el = (int64_t)tk.k * tk.k * 8;     // eight lanes per element (gram_finish)
       max_elems = el > max_elems ? el : max_elems;
     }
     // tensor-core route: TMA-addressable tasks are computed by gram_tc_kernel (fp32 partials)
@@ -396,7 +417,7 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
       TTA_CHECK_LAUNCH("gram_partial launch");
     }
     int gx = (int)((max_elems + 255) / 256);
-    if (gx > kNumSMs * 4) gx = kNumSMs * 4;
+    if (gx > kNumSMs * 16) gx = kNumSMs * 16;
     if (gx < 1) gx = 1;
     gram_finish<<<dim3(gx, cnt), 256, 0, st>>>(tasks_dev + first, flags);
     TTA_CHECK_LAUNCH("gram_finish launch");

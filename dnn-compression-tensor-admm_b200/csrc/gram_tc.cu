@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "tc_common.cuh"
+#include "tf32_split.cuh"
 
 namespace tta {
 
@@ -56,86 +57,6 @@ struct GtParams {
   GtTask task[kGtMaxTasks];
   CUtensorMap maps[kGtMaxTasks][2];
 };
-
-__device__ __forceinline__ float gt_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
-
-// instruction descriptor: D = fp32, A = B = tf32, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t gt_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kGtTile >> 4) << 24);
-}
-
-__device__ __forceinline__ void gt_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
-__device__ __forceinline__ void gt_ld16(uint32_t addr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(addr));
-}
-
-// hi / lo split of four consecutive reduction indices of operand row `row`, 16-byte chunk `ch` of its 128-byte row
-__device__ __forceinline__ void gt_store_chunk(uint32_t hi_tile, uint32_t lo_tile, int row, int ch, float4 v) {
-  const float4 h = make_float4(gt_tf32(v.x), gt_tf32(v.y), gt_tf32(v.z), gt_tf32(v.w));
-  const float4 l = make_float4(gt_tf32(v.x - h.x), gt_tf32(v.y - h.y), gt_tf32(v.z - h.z), gt_tf32(v.w - h.w));
-  const uint32_t off = (uint32_t)(row * 128 + ((ch ^ (row & 7)) << 4));
-  tc::sts128(hi_tile + off, __float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w));
-  tc::sts128(lo_tile + off, __float_as_uint(l.x), __float_as_uint(l.y), __float_as_uint(l.z), __float_as_uint(l.w));
-}
-
-__device__ __forceinline__ float gt_lds(uint32_t addr) {
-  float r;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
-  return r;
-}
-
-// one operand tile of one k-block: staging box(es) -> hi / lo tiles.  `sub` = which 32 reduction indices of the box.
-__device__ __forceinline__ void gt_transform(uint32_t src, uint32_t src2, bool has2, uint32_t hi_tile, uint32_t lo_tile,
-                                             int rb, int kcols, int sub, bool colmajor, int tid) {
-  const int items = rb * 8;       // 16-byte chunks of the tile
-  if (!colmajor) {
-    // box = rb rows x kcols reduction indices, row pitch kcols * 4 bytes
-    const uint32_t pitch = (uint32_t)kcols * 4u;
-    for (int it = tid; it < items; it += kGtXformThreads) {
-      const int row = it >> 3, ch = it & 7;
-      const uint32_t o = (uint32_t)row * pitch + (uint32_t)sub * 128u + (uint32_t)ch * 16u;
-      float4 v = tc::lds128(src + o);
-      if (has2) {
-        const float4 w = tc::lds128(src2 + o);
-        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-      }
-      gt_store_chunk(hi_tile, lo_tile, row, ch, v);
-    }
-  } else {
-    // box = kcols reduction rows x rb operand indices, row pitch rb * 4 bytes: transpose while splitting
-    const uint32_t pitch = (uint32_t)rb * 4u;
-    for (int it = tid; it < items; it += kGtXformThreads) {
-      const int row = it % rb, ch = it / rb;
-      const uint32_t o = (uint32_t)(sub * 32 + ch * 4) * pitch + (uint32_t)row * 4u;
-      float4 v = make_float4(gt_lds(src + o), gt_lds(src + o + pitch), gt_lds(src + o + 2 * pitch), gt_lds(src + o + 3 * pitch));
-      if (has2) {
-        v.x += gt_lds(src2 + o);
-        v.y += gt_lds(src2 + o + pitch);
-        v.z += gt_lds(src2 + o + 2 * pitch);
-        v.w += gt_lds(src2 + o + 3 * pitch);
-      }
-      gt_store_chunk(hi_tile, lo_tile, row, ch, v);
-    }
-  }
-}
 
 __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(const __grid_constant__ GtParams P) {
   extern __shared__ __align__(1024) uint8_t gt_smem_raw[];
@@ -252,9 +173,13 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(const __grid_con
       const int s = q / SUB, sub = q - s * SUB, slot = s & 1;
       if (sub == 0) tc::mbar_wait(st_full0 + 8 * slot, (uint32_t)((s >> 1) & 1));
       if (q >= 1) tc::mbar_wait(op_empty, (uint32_t)((q - 1) & 1));
-      const uint32_t base = stage0 + (uint32_t)slot * kGtStageBytes;
-      gt_transform(base, base + kGtBoxBytes, has2, a_hi, a_lo, rb, kcols, sub, colmajor, tid);
-      if (!diag) gt_transform(base + 2 * kGtBoxBytes, base + 3 * kGtBoxBytes, has2, b_hi, b_lo, rb, kcols, sub, colmajor, tid);
+      // box = rb rows x kcols reduction indices (pitch kcols * 4 bytes), or kcols reduction rows x rb operand indices
+      // (pitch rb * 4 bytes, transposed while splitting); `sub` = which 32 reduction indices of the box
+      const uint32_t pitch = (uint32_t)(colmajor ? rb : kcols) * 4u;
+      const uint32_t base = stage0 + (uint32_t)slot * kGtStageBytes + (colmajor ? (uint32_t)(sub * 32) * pitch : (uint32_t)sub * 128u);
+      tf32::transform<kGtXformThreads>(base, base + kGtBoxBytes, has2, a_hi, a_lo, rb, pitch, colmajor, tid);
+      if (!diag)
+        tf32::transform<kGtXformThreads>(base + 2 * kGtBoxBytes, base + 3 * kGtBoxBytes, has2, b_hi, b_lo, rb, pitch, colmajor, tid);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
       __syncwarp();
       if (lane == 0) {
@@ -264,7 +189,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(const __grid_con
     }
   } else if (warp == 7) {
     // ------------------------------ MMA issuer ------------------------------
-    const uint32_t idesc = gt_idesc(N);
+    const uint32_t idesc = tf32::idesc(N);
     const uint64_t da_hi = tc::umma_desc_sw128(a_hi), da_lo = tc::umma_desc_sw128(a_lo);
     const uint64_t db_hi = diag ? da_hi : tc::umma_desc_sw128(b_hi), db_lo = diag ? da_lo : tc::umma_desc_sw128(b_lo);
     for (int q = 0; q < nq; ++q) {
@@ -273,16 +198,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(const __grid_con
       if (q >= 2) tc::mbar_wait(acc_empty0 + 8 * buf, (uint32_t)(((q >> 1) - 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tc::elect_one()) {
-        const uint32_t d = tmem_base + (uint32_t)buf * kGtTile;
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          // small terms first: A_lo B_hi, A_hi B_lo, then A_hi B_hi
-          const uint64_t da = pass == 0 ? da_lo : da_hi;
-          const uint64_t db = pass == 1 ? db_lo : db_hi;
-#pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)      // 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-            gt_mma(d, da + (uint64_t)(2 * k8), db + (uint64_t)(2 * k8), idesc, (pass | k8) ? 1u : 0u);
-        }
+        tf32::mma_kblock(tmem_base + (uint32_t)buf * kGtTile, da_hi, da_lo, db_hi, db_lo, idesc);
         tc::umma_commit(op_empty);
         tc::umma_commit(acc_full0 + 8 * buf);
       }
@@ -300,20 +216,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(const __grid_con
       tc::mbar_wait(acc_full0 + 8 * buf, (uint32_t)((q >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kGtTile + cbase);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[2][16];
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (cbase + (h * 2 + c) * 16 < N) gt_ld16(taddr + (uint32_t)((h * 2 + c) * 16), v[c]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (cbase + (h * 2 + c) * 16 < N) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[(h * 2 + c) * 16 + j] += __uint_as_float(v[c][j]);
-          }
-      }
+      tf32::drain64(taddr, cbase, N, acc);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(acc_empty0 + 8 * buf);

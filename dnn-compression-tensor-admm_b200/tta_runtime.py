@@ -112,6 +112,8 @@ def _load():
     lib.tta_jacobi_set_stop_rel.restype = None
     lib.tta_gemm_enable_tc.argtypes = [ci]
     lib.tta_gemm_enable_tc.restype = None
+    lib.tta_gram_enable_tc.argtypes = [ci]
+    lib.tta_gram_enable_tc.restype = None
     lib.tta_jacobi_profile_read.argtypes = [vp, vp]
     lib.tta_jacobi_profile_read.restype = None
     lib.tta_check_device.argtypes = [ci]
@@ -153,7 +155,7 @@ def _load():
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count', 'tta_symeig_work_doubles',
                         'tta_symeig_profile_enable', 'tta_symeig_profile_read',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
-                        'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc'):
+                        'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_gram_enable_tc'):
             getattr(lib, name).restype = ci
     _LIB = lib
     return lib
@@ -425,12 +427,11 @@ def jacobi_force_multilaunch(on):
         lib().tta_jacobi_force_multilaunch(int(bool(on)))
 
 
-def gemm_enable_tc(on):
-    """True routes fp32 GEMM tasks with M >= 48, N >= 24 to the tcgen05 3xTF32 kernel; the library default is
-    the CUDA-core kernel (the tensor core's truncating fp32 accumulation costs ~3e-6 relative error at
-    K = 480, which the small-gap TT projections amplify past the 1e-4 parity bar on DeiT-small)."""
+def gemm_enable_tc(mode):
+    """0 / False: every fp32 GEMM task on the CUDA-core kernel; 1 / True (library default): tasks of >= 0.6 GFLOP on the
+    tcgen05 3xTF32 kernel (csrc/gemm_tf32.cu: fresh TMEM accumulator every 32 reduction indices); 2: every task (tests)."""
     if _FAKE is None:
-        lib().tta_gemm_enable_tc(int(bool(on)))
+        lib().tta_gemm_enable_tc(int(mode))
 
 
 def gram_enable_tc(on):

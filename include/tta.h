@@ -227,11 +227,14 @@ typedef struct {
 
 int tta_gemm_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,
                      void* stream);
-/* on != 0: tasks with M >= 48, N >= 24, K >= 8 run on the tensor cores (tcgen05, 3xTF32 split: A_hi B_hi +
- * A_lo B_hi + A_hi B_lo, fp32 TMEM accumulation); the rest, and by default all tasks, on CUDA cores.  Measured
- * on B200: the tensor core's truncating accumulation gives 3.3e-6 relative error at K = 480 (CUDA cores:
- * 3e-7); fed into the next small-gap SVD of a TT chain this is amplified past the 1e-4 parity bar
- * (DeiT-small, 1.3e-4), so the projection path keeps the CUDA-core kernel. */
+/* Mode 1 (default): fp32 tasks of at least 0.6 GFLOP (max(M, N) >= 128, min(M, N) >= 16, K >= 64) run on the tensor
+ * cores (tcgen05, 3xTF32 split: A_lo B_hi + A_hi B_lo + A_hi B_hi into a ZEROED TMEM accumulator for every 32 reduction
+ * indices, running sum in fp32 registers); smaller tasks on CUDA cores, where they are faster (crossover measured in
+ * scripts/bench_gemm_shapes.py: 85 against 31 TFLOP/s at 18432 x 1024 x 2048, 41 against 33 us at 105 x 4608 x 480).
+ * Mode 0: CUDA cores only.  Mode 2 (tests): every task on the tensor cores.
+ * Accuracy, measured on B200 (scripts/ubench/tf32_accum_error.py): the tensor core's truncating accumulation costs
+ * 3.5e-6 relative error at K = 512 when the sum stays in TMEM (amplified past the 1e-4 parity bar by the next small-gap
+ * SVD of a TT chain), 1.3e-7 per 32-index block -- the same grade as the CUDA-core fp32 kernel. */
 void tta_gemm_enable_tc(int on);
 /* Same operator in fp64: a, b, c, colscale address doubles (used by the refinement step below). */
 int tta_gemm_f64_batched(const tta_gemm_task* tasks_dev, const tta_gemm_task* tasks_host, int n_tasks,

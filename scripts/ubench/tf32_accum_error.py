@@ -20,12 +20,12 @@ def run(A, B, tc):
     c = torch.zeros(M, N, device=DEV)
     tab = np.zeros(1, dtype=rt.GEMM_TASK)
     tab[0] = (a.data_ptr(), b.data_ptr(), c.data_ptr(), 0, K, 1, N, 1, N, M, N, K, 0)
-    rt.gemm_enable_tc(tc)
+    rt.gemm_enable_tc(2 if tc else 0)
     try:
         rt.gemm(rt.TaskTable(tab, DEV))
         torch.cuda.synchronize()
     finally:
-        rt.gemm_enable_tc(False)
+        rt.gemm_enable_tc(1)
     return c.cpu().numpy().astype(np.float64)
 
 
