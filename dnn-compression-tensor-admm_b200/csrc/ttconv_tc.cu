@@ -1,0 +1,388 @@
+// Fused forward of the factorised 3x3 convolutions on the 5th-generation tensor cores (bf16 tcgen05, fp32 TMEM
+// accumulators):  1x1 (C_in -> r_a)  ->  3x3 (r_a -> r_b, stride 1, zero padding 1)  ->  1x1 (r_b -> C_out) + bias,
+// ONE kernel, both intermediates stay in shared memory as bf16.
+//
+// This is the contraction of TTConv2dM.forward (TTConv.py:130-153: in-core chain, F.conv2d with core_kernel, out-core
+// chain; the host folds the in / out chains into one matrix each) and of TKConv2dC/M.forward (TKConv.py:93-98, 205-222:
+// first factor, core, last factor).  csrc/ttconv_fused.cu is the fp32 CUDA-core version of the same contraction (and
+// still serves strides, kernel sizes and paddings this kernel does not).
+//
+// Pixel-major implicit GEMM without im2col.  The batch is laid out as one flat sequence of zero-PADDED grids,
+// position g = b * Hp * Wp + (y + 1) * Wp + (x + 1) with Hp = H + 2, Wp = W + 2.  In that space the tap (ky, kx) of the
+// 3x3 stage is a constant offset (ky - 1) * Wp + (kx - 1), and the pad positions -- whose stage-1 output is exactly
+// zero because stage 1 has no bias and reads zero -- isolate rows and images from each other.  A CTA takes a chunk of
+// T x 128 positions plus a halo of Wp + 1 positions on either side:
+//   load    x (NCHW fp32) -> bf16, eight channels = 16 bytes per position and channel group, "planes" [group][position]
+//   stage 1 Z1[pos, ra] = X[pos, :] . A_in[ra, :]          tcgen05.mma M = 128 positions, N = r_a, K = C_in
+//   stage 2 Z2[pos, rb] = sum_taps Z1[pos + tap, :] . K_tap[rb, :]     nine MMAs groups on ROW-SHIFTED views of Z1
+//   stage 3 Y[pos, co]  = Z2[pos, :] . A_out[co, :] + bias  -> NCHW fp32, pad positions dropped
+// The operands use the un-swizzled K-major canonical layout (8 rows x 16 bytes core matrices stored contiguously,
+// SBO = 128 bytes): rows are 16 bytes apart inside a plane, so a view shifted by any number of positions is just a
+// different descriptor start address -- this is what makes the shifted-window trick possible without copies.
+// HBM traffic = x (+ halo) + y; every weight is read from L2 once per CTA.
+#include "tc_common.cuh"
+
+namespace tta {
+
+constexpr int kTcThreads = 256;
+
+struct TcConvDesc {
+  int B, Cin, H, W, Ra, Rb, Cout;
+  int Cinp, Rap, Rbp, Coutp;      // padded to multiples of 16 (MMA K step / N granularity)
+  int Wp, Gp, halo;               // padded row, padded grid size, Wp + 1
+  int T, TE;                      // output tiles per chunk, stage-1 tiles per chunk (chunk + both halos)
+  long long total;                // B * Gp
+  // shared-memory byte offsets
+  int o_wa, o_wk, o_wo, o_bias, o_x, o_z1, smem;
+};
+
+// un-swizzled K-major operand: core matrices (8 rows x 16 B) contiguous, `lbo` bytes between the two 16-byte K chunks
+// of one MMA, 128 bytes between 8-row groups
+__device__ __forceinline__ uint64_t tcv_desc(uint32_t addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t tcv_pack(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void tcv_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// weight matrix w[n][k] (n < N, k < K, element at w + n*sn + k*sk) -> planes [k / 8][Np rows][16 bytes], zero padded
+__device__ __forceinline__ void tcv_stage_weight(uint32_t dst, const float* __restrict__ w, int N, int K, int Np, int Kp,
+                                                 int64_t sn, int64_t sk, int tid) {
+  const int groups = Kp >> 3;
+  for (int it = tid; it < groups * Np; it += kTcThreads) {
+    const int n = it % Np, kg = it / Np;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kg * 8 + e;
+      v[e] = (n < N && k < K) ? __ldg(w + (int64_t)n * sn + (int64_t)k * sk) : 0.f;
+    }
+    tc::sts128(dst + (uint32_t)(kg * Np + n) * 16u, tcv_pack(v[0], v[1]), tcv_pack(v[2], v[3]), tcv_pack(v[4], v[5]),
+               tcv_pack(v[6], v[7]));
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __restrict__ x, const float* __restrict__ a_in,
+                                                              const float* __restrict__ kern,
+                                                              const float* __restrict__ a_out,
+                                                              const float* __restrict__ bias, float* __restrict__ y,
+                                                              const __grid_constant__ TcConvDesc d) {
+  extern __shared__ __align__(128) uint8_t tcv_smem_raw[];
+  const uint32_t smem = (tc::smem_u32(tcv_smem_raw) + 127u) & ~127u;
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t full0 = tc::smem_u32(bars), empty0 = full0 + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    tc::mbar_init(full0, 1);
+    tc::mbar_init(full0 + 8, 1);
+    tc::mbar_init(empty0, 4);
+    tc::mbar_init(empty0 + 8, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base_smem)),
+                 "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  const uint32_t wa = smem + d.o_wa, wk = smem + d.o_wk, wo = smem + d.o_wo, xs = smem + d.o_x, z1 = smem + d.o_z1;
+  const uint32_t z2 = xs;                                    // X is dead once stage 1 is over
+  float* bias_s = reinterpret_cast<float*>(tcv_smem_raw + ((smem - tc::smem_u32(tcv_smem_raw)) + d.o_bias));
+  const int NP = d.TE * 128;                                 // rows of the X and Z1 planes
+  const uint32_t plx = (uint32_t)NP * 16u, plz2 = (uint32_t)d.T * 128u * 16u;
+
+  // ---- weights: A_in [ra][c], K_tap [rb][ra] for the nine taps, A_out [co][rb]; bias ----
+  tcv_stage_weight(wa, a_in, d.Ra, d.Cin, d.Rap, d.Cinp, d.Cin, 1, tid);
+  for (int tap = 0; tap < 9; ++tap)
+    tcv_stage_weight(wk + (uint32_t)tap * (uint32_t)(d.Rap * d.Rbp * 2), kern + tap, d.Rb, d.Ra, d.Rbp, d.Rap, (int64_t)d.Ra * 9, 9,
+                     tid);
+  tcv_stage_weight(wo, a_out, d.Cout, d.Rb, d.Coutp, d.Rbp, d.Rb, 1, tid);
+  for (int c = tid; c < d.Coutp; c += kTcThreads) bias_s[c] = (bias && c < d.Cout) ? __ldg(bias + c) : 0.f;
+
+  // ---- input chunk + halos: x (NCHW fp32) -> bf16 planes; zero at pad positions and outside the batch ----
+  const long long c0 = (long long)blockIdx.x * d.T * 128;    // first output position of the chunk
+  const long long e0 = c0 - d.halo;                          // position of row 0 of the X / Z1 planes
+  {
+    const int groups = d.Cinp >> 3;
+    const int64_t hw = (int64_t)d.H * d.W;
+    for (int it = tid; it < groups * NP; it += kTcThreads) {
+      const int row = it % NP, kg = it / NP;
+      const long long g = e0 + row;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (g >= 0 && g < d.total) {
+        const int b = (int)(g / d.Gp);
+        const int rem = (int)(g - (long long)b * d.Gp);
+        const int py = rem / d.Wp, px = rem - py * d.Wp;
+        if (py >= 1 && py <= d.H && px >= 1 && px <= d.W) {
+          const float* p = x + ((int64_t)b * d.Cin + kg * 8) * hw + (int64_t)(py - 1) * d.W + (px - 1);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (kg * 8 + e < d.Cin) v[e] = __ldg(p + e * hw);
+        }
+      }
+      tc::sts128(xs + (uint32_t)kg * plx + (uint32_t)row * 16u, tcv_pack(v[0], v[1]), tcv_pack(v[2], v[3]),
+                 tcv_pack(v[4], v[5]), tcv_pack(v[6], v[7]));
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  int tile_ctr = 0;          // accumulator tiles issued / drained so far (same sequence in the issuer and the drainers)
+
+  // =============================== stage 1: Z1 = X . A_in^T over the chunk and its halos ===============================
+  if (warp == 4) {
+    const uint32_t idesc = tc::umma_idesc_bf16(d.Rap);
+    for (int e = 0; e < d.TE; ++e, ++tile_ctr) {
+      const int buf = tile_ctr & 1;
+      if (tile_ctr >= 2) tc::mbar_wait(empty0 + 8 * buf, (uint32_t)(((tile_ctr >> 1) - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tc::elect_one()) {
+        for (int k2 = 0; k2 < (d.Cinp >> 4); ++k2)
+          tc::umma_bf16(tmem_base + (uint32_t)buf * 64u, tcv_desc(xs + (uint32_t)(2 * k2) * plx + (uint32_t)e * 2048u, plx),
+                        tcv_desc(wa + (uint32_t)(2 * k2) * (uint32_t)d.Rap * 16u, (uint32_t)d.Rap * 16u), idesc, k2 ? 1u : 0u);
+        tc::umma_commit(full0 + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    for (int e = 0; e < d.TE; ++e, ++tile_ctr) {
+      const int buf = tile_ctr & 1;
+      tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
+      const int row = e * 128 + warp * 32 + lane;
+      for (int cg = 0; cg < (d.Rap >> 4); ++cg) {
+        uint32_t v[16];
+        tcv_ld16(taddr + (uint32_t)cg * 16u, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tc::sts128(z1 + (uint32_t)(2 * cg + h) * plx + (uint32_t)row * 16u,
+                     tcv_pack(__uint_as_float(v[8 * h]), __uint_as_float(v[8 * h + 1])),
+                     tcv_pack(__uint_as_float(v[8 * h + 2]), __uint_as_float(v[8 * h + 3])),
+                     tcv_pack(__uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5])),
+                     tcv_pack(__uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7])));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty0 + 8 * buf);
+    }
+  }
+  if (warp > 4) tile_ctr += d.TE;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // =============================== stage 2: Z2 = sum over taps of shifted Z1 . K_tap^T ===============================
+  if (warp == 4) {
+    const uint32_t idesc = tc::umma_idesc_bf16(d.Rbp);
+    const uint32_t plk = (uint32_t)d.Rbp * 16u, tapb = (uint32_t)(d.Rap * d.Rbp * 2);
+    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
+      const int buf = tile_ctr & 1;
+      if (tile_ctr >= 2) tc::mbar_wait(empty0 + 8 * buf, (uint32_t)(((tile_ctr >> 1) - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tc::elect_one()) {
+        uint32_t acc = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = (tap / 3 - 1) * d.Wp + (tap % 3 - 1);
+          const uint32_t arow = (uint32_t)(t * 128 + d.halo + shift) * 16u;
+          for (int k2 = 0; k2 < (d.Rap >> 4); ++k2) {
+            tc::umma_bf16(tmem_base + (uint32_t)buf * 64u, tcv_desc(z1 + (uint32_t)(2 * k2) * plx + arow, plx),
+                          tcv_desc(wk + (uint32_t)tap * tapb + (uint32_t)(2 * k2) * plk, plk), idesc, acc);
+            acc = 1;
+          }
+        }
+        tc::umma_commit(full0 + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
+      const int buf = tile_ctr & 1;
+      tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
+      const int row = t * 128 + warp * 32 + lane;
+      for (int cg = 0; cg < (d.Rbp >> 4); ++cg) {
+        uint32_t v[16];
+        tcv_ld16(taddr + (uint32_t)cg * 16u, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tc::sts128(z2 + (uint32_t)(2 * cg + h) * plz2 + (uint32_t)row * 16u,
+                     tcv_pack(__uint_as_float(v[8 * h]), __uint_as_float(v[8 * h + 1])),
+                     tcv_pack(__uint_as_float(v[8 * h + 2]), __uint_as_float(v[8 * h + 3])),
+                     tcv_pack(__uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5])),
+                     tcv_pack(__uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7])));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty0 + 8 * buf);
+    }
+  }
+  if (warp > 4) tile_ctr += d.T;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // =============================== stage 3: Y = Z2 . A_out^T + bias -> NCHW ===============================
+  if (warp == 4) {
+    const uint32_t idesc = tc::umma_idesc_bf16(d.Coutp);
+    const uint32_t plo = (uint32_t)d.Coutp * 16u;
+    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
+      const int buf = tile_ctr & 1;
+      if (tile_ctr >= 2) tc::mbar_wait(empty0 + 8 * buf, (uint32_t)(((tile_ctr >> 1) - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tc::elect_one()) {
+        for (int k2 = 0; k2 < (d.Rbp >> 4); ++k2)
+          tc::umma_bf16(tmem_base + (uint32_t)buf * 64u, tcv_desc(z2 + (uint32_t)(2 * k2) * plz2 + (uint32_t)t * 2048u, plz2),
+                        tcv_desc(wo + (uint32_t)(2 * k2) * plo, plo), idesc, k2 ? 1u : 0u);
+        tc::umma_commit(full0 + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    const int64_t hw = (int64_t)d.H * d.W;
+    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
+      const int buf = tile_ctr & 1;
+      tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
+      const long long g = c0 + t * 128 + warp * 32 + lane;
+      bool valid = g < d.total;
+      float* yp = y;
+      if (valid) {
+        const int b = (int)(g / d.Gp);
+        const int rem = (int)(g - (long long)b * d.Gp);
+        const int py = rem / d.Wp, px = rem - py * d.Wp;
+        valid = py >= 1 && py <= d.H && px >= 1 && px <= d.W;
+        yp = y + (int64_t)b * d.Cout * hw + (int64_t)(py - 1) * d.W + (px - 1);
+      }
+      for (int cg = 0; cg < (d.Coutp >> 4); ++cg) {
+        uint32_t v[16];
+        tcv_ld16(taddr + (uint32_t)cg * 16u, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = cg * 16 + j;
+            if (co < d.Cout) yp[(int64_t)co * hw] = __uint_as_float(v[j]) + bias_s[co];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty0 + 8 * buf);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+static int tcv_round16(int v) { return (v + 15) & ~15; }
+
+// geometry this kernel serves: 3x3, stride 1, padding 1, channel counts and ranks <= 64
+bool ttconv_tc_supported(int Cin, int Ra, int Rb, int Cout, int KS, int stride, int pad) {
+  return KS == 3 && stride == 1 && pad == 1 && Cin <= 64 && Ra <= 64 && Rb <= 64 && Cout <= 64;
+}
+
+static void tcv_layout(TcConvDesc& d, int T) {
+  d.T = T;
+  d.TE = (T * 128 + 2 * d.halo + 127) / 128;
+  int o = 0;
+  d.o_wa = o; o += d.Cinp * d.Rap * 2;
+  d.o_wk = o; o += 9 * d.Rap * d.Rbp * 2;
+  d.o_wo = o; o += d.Rbp * d.Coutp * 2;
+  d.o_bias = o; o += d.Coutp * 4;
+  o = (o + 127) & ~127;
+  const int xb = d.Cinp * d.TE * 128 * 2, z2b = d.Rbp * T * 128 * 2;
+  d.o_x = o; o += xb > z2b ? xb : z2b;
+  d.o_z1 = o; o += d.Rap * d.TE * 128 * 2;
+  d.smem = o + 128;
+}
+
+}  // namespace tta
+
+extern "C" int tta_ttconv_tc_fwd(const float* x, const float* a_in, const float* kern, const float* a_out, const float* bias,
+                                 float* y, int B, int Cin, int H, int W, int Ra, int Rb, int Cout, int KS, int stride, int pad,
+                                 void* stream) {
+  using namespace tta;
+  if (!x || !a_in || !kern || !a_out || !y || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Ra <= 0 || Rb <= 0 || Cout <= 0) {
+    set_error("ttconv_tc: bad argument");
+    return TTA_E_INVALID;
+  }
+  if (!ttconv_tc_supported(Cin, Ra, Rb, Cout, KS, stride, pad)) {
+    set_error("ttconv_tc: unsupported geometry (kernel %d, stride %d, pad %d, channels %d/%d/%d/%d): use tta_ttconv_fused_fwd",
+              KS, stride, pad, Cin, Ra, Rb, Cout);
+    return TTA_E_INVALID;
+  }
+  TcConvDesc d;
+  d.B = B; d.Cin = Cin; d.H = H; d.W = W; d.Ra = Ra; d.Rb = Rb; d.Cout = Cout;
+  d.Cinp = tcv_round16(Cin); d.Rap = tcv_round16(Ra); d.Rbp = tcv_round16(Rb); d.Coutp = tcv_round16(Cout);
+  d.Wp = W + 2;
+  d.Gp = (H + 2) * d.Wp;
+  d.halo = d.Wp + 1;
+  d.total = (long long)B * d.Gp;
+  // chunk size: as many 128-position tiles per CTA as fit in shared memory (fewer halo positions are recomputed), but
+  // not so many that the grid leaves SMs without a chunk
+  int T = 0;
+  for (int pass = 0; pass < 3 && !T; ++pass)
+    for (int cand = 8; cand >= 1; cand >>= 1) {
+      tcv_layout(d, cand);
+      const long long chunks = (d.total + (long long)cand * 128 - 1) / ((long long)cand * 128);
+      const bool fits = d.smem <= 220 * 1024;
+      if (fits && (pass == 2 || chunks >= (pass == 0 ? 2 : 1) * (long long)kNumSMs)) {
+        T = cand;
+        break;
+      }
+    }
+  if (!T) T = 1;
+  tcv_layout(d, T);
+  if (d.smem > 227 * 1024) {
+    set_error("ttconv_tc: working set %d B does not fit shared memory", d.smem);
+    return TTA_E_INVALID;
+  }
+  const long long chunks = (d.total + (long long)T * 128 - 1) / ((long long)T * 128);
+  static int smem_set = 0;
+  if (d.smem > 48 * 1024 && d.smem > smem_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(ttconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem),
+                        "ttconv_tc smem attribute");
+    if (rc) return rc;
+    smem_set = d.smem;
+  }
+  ttconv_tc_kernel<<<(unsigned)chunks, kTcThreads, d.smem, (cudaStream_t)stream>>>(x, a_in, kern, a_out, bias, y, d);
+  TTA_CHECK_LAUNCH("ttconv_tc launch");
+  return TTA_OK;
+}
+
+extern "C" int tta_ttconv_tc_supported(int Cin, int Ra, int Rb, int Cout, int KS, int stride, int pad) {
+  return tta::ttconv_tc_supported(Cin, Ra, Rb, Cout, KS, stride, pad) ? 1 : 0;
+}

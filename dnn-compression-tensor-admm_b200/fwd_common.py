@@ -16,6 +16,8 @@ with torch ops -- the fused backward is SURVEY 8(f) "next".
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 import tta_runtime as rt
@@ -73,6 +75,9 @@ class PackedWeight:
         return self
 
 
+_TTCONV_TC = os.environ.get('TTA_TTCONV_TC', '1') != '0'
+
+
 class FoldedConv:
     """Cached fp32 operands of the fused factorised-convolution kernel (`tta_ttconv_fused_fwd`):
     a_in (r_a x C_in), kern (r_b, r_a, k, k), a_out (C_out x r_b); rebuilt when a parameter changes."""
@@ -82,6 +87,7 @@ class FoldedConv:
         self.params = [p for p in params if p is not None]
         self.key = None
         self.ops = None
+        self.tc_ok = {}
 
     def get(self):
         key = tuple((p.data_ptr(), p._version) for p in self.params)
@@ -110,9 +116,15 @@ def fused_conv(x, folded, bias, kernel_size, stride, padding):
     y = torch.empty((B, cout, (H + 2 * p - ks) // s + 1, (W + 2 * p - ks) // s + 1), dtype=torch.float32, device=x.device)
     if bias is not None and (bias.dtype is not torch.float32 or not bias.is_contiguous()):
         bias = bias.detach().to(torch.float32).contiguous()
-    rt.ttconv_fused_fwd_raw(x.data_ptr(), a_in.data_ptr(), kern.data_ptr(), a_out.data_ptr(),
-                            bias.data_ptr() if bias is not None else None, y.data_ptr(), B, C, H, W, a_in.shape[0],
-                            kern.shape[0], cout, ks, s, p)
+    # bf16 tcgen05 kernel for the geometry of the reference's tables (3 x 3, stride 1, pad 1, <= 64 channels / ranks);
+    # the fp32 CUDA-core kernel otherwise (and with TTA_TTCONV_TC=0)
+    tc_ok = folded.tc_ok.get((C, ks, s, p))
+    if tc_ok is None:
+        tc_ok = _TTCONV_TC and rt.ttconv_tc_supported(C, a_in.shape[0], kern.shape[0], cout, ks, s, p)
+        folded.tc_ok[(C, ks, s, p)] = tc_ok
+    call = rt.ttconv_tc_fwd_raw if tc_ok else rt.ttconv_fused_fwd_raw
+    call(x.data_ptr(), a_in.data_ptr(), kern.data_ptr(), a_out.data_ptr(), bias.data_ptr() if bias is not None else None,
+         y.data_ptr(), B, C, H, W, a_in.shape[0], kern.shape[0], cout, ks, s, p)
     return y
 
 

@@ -63,7 +63,7 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
-           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd',
+           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd', 'tta_ttconv_tc_fwd', 'tta_ttconv_tc_supported',
            'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k',
            'tta_symeig_profile_enable', 'tta_symeig_profile_read', 'tta_orth_penalty_fwd_batched',
            'tta_orth_penalty_bwd_batched']
@@ -150,6 +150,8 @@ def _load():
     lib.tta_nhwc_to_nchw_f32.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp]
     lib.tta_im2col_bf16.argtypes = [vp, vp] + [ci] * 16 + [vp]
     lib.tta_ttconv_fused_fwd.argtypes = [vp] * 6 + [ci] * 10 + [vp]
+    lib.tta_ttconv_tc_fwd.argtypes = [vp] * 6 + [ci] * 10 + [vp]
+    lib.tta_ttconv_tc_supported.argtypes = [ci] * 7
     lib.tta_lowrank2_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, ci, i64, ci, ci, ci, vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count', 'tta_symeig_work_doubles',
@@ -408,6 +410,26 @@ def ttconv_fused_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, 
     _check(lib().tta_ttconv_fused_fwd(_p(x), _p(a_in), _p(kern), _p(a_out), _p(bias), _p(y), int(B), int(Cin), int(H),
                                       int(W), int(Ra), int(Rb), int(Cout), int(KS), int(stride), int(pad),
                                       stream_handle()), 'tta_ttconv_fused_fwd')
+
+
+def ttconv_tc_supported(Cin, Ra, Rb, Cout, KS, stride, pad):
+    """True when the bf16 tcgen05 kernel (csrc/ttconv_tc.cu) serves this geometry."""
+    if _FAKE is not None:
+        return False
+    return bool(lib().tta_ttconv_tc_supported(int(Cin), int(Ra), int(Rb), int(Cout), int(KS), int(stride), int(pad)))
+
+
+def ttconv_tc_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
+    _check(lib().tta_ttconv_tc_fwd(_p(x), _p(a_in), _p(kern), _p(a_out), _p(bias), _p(y), int(B), int(Cin), int(H),
+                                   int(W), int(Ra), int(Rb), int(Cout), int(KS), int(stride), int(pad),
+                                   stream_handle()), 'tta_ttconv_tc_fwd')
+
+
+def ttconv_tc_fwd_raw(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
+    rc = lib().tta_ttconv_tc_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad,
+                                 torch.cuda.current_stream().cuda_stream)
+    if rc:
+        _check(rc, 'tta_ttconv_tc_fwd')
 
 
 def ttconv_fused_fwd_raw(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):

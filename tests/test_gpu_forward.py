@@ -254,6 +254,44 @@ def test_ttconv_fused_kernel_matches_conv_chain(B, Cin, H, W, Ra, Rb, Cout, KS, 
         assert _rel(y, ref) <= 2e-6, _rel(y, ref)
 
 
+@pytest.mark.parametrize('B,Cin,H,W,Ra,Rb,Cout', [
+    (3, 16, 32, 32, 16, 16, 16),       # ttm_resnet32 layer1
+    (5, 32, 16, 16, 20, 24, 32),       # layer2, ranks not multiples of 16
+    (4, 64, 8, 8, 27, 29, 64),         # layer3 ranks
+    (2, 7, 13, 9, 5, 6, 11),           # ragged everything
+    (1, 64, 56, 56, 40, 40, 64),       # bigger image: the taps reach across several 128-position tiles
+    (1, 16, 3, 3, 16, 16, 16),         # one chunk, mostly padding
+    (130, 16, 32, 32, 16, 16, 16),     # chunks of several tiles, many images
+])
+def test_ttconv_tensor_core_kernel_matches_conv_chain(B, Cin, H, W, Ra, Rb, Cout):
+    """tta_ttconv_tc_fwd (bf16 tcgen05, intermediates in shared memory) == conv1x1 -> conv3x3 -> conv1x1 (+bias) of torch
+    in fp64, within the 1e-2 bar of the decomposed-layer forwards (three bf16 roundings: ~4e-3)."""
+    import torch.nn.functional as F
+    assert rt.ttconv_tc_supported(Cin, Ra, Rb, Cout, 3, 1, 1)
+    assert not rt.ttconv_tc_supported(Cin, Ra, Rb, Cout, 3, 2, 1) and not rt.ttconv_tc_supported(128, Ra, Rb, Cout, 3, 1, 1)
+    g = torch.Generator(device='cpu').manual_seed(B * 131 + Cin * 17 + H)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+    a_in = (torch.randn(Ra, Cin, generator=g) / Cin ** 0.5).to(DEV)
+    kern = (torch.randn(Rb, Ra, 3, 3, generator=g) / (Ra * 9) ** 0.5).to(DEV)
+    a_out = (torch.randn(Cout, Rb, generator=g) / Rb ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    for b in (bias, None):
+        y = torch.full((B, Cout, H, W), float('nan'), device=DEV)
+        rt.ttconv_tc_fwd(x, a_in, kern, a_out, b, y, B, Cin, H, W, Ra, Rb, Cout, 3, 1, 1)
+        torch.cuda.synchronize()
+        ref = F.conv2d(F.conv2d(F.conv2d(x.double(), a_in.double()[:, :, None, None]), kern.double(), None, 1, 1),
+                       a_out.double()[:, :, None, None], b.double() if b is not None else None)
+        assert torch.isfinite(y).all()
+        assert _rel(y, ref) <= 1e-2, _rel(y, ref)
+        # every image and every border pixel individually (a wrong tap offset or a leak across the padding shows here)
+        err = (y.double() - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)
+        assert float(err.max()) <= 1.5e-2, float(err.max())
+        edge = torch.cat([(y.double() - ref)[..., 0, :].flatten(), (y.double() - ref)[..., -1, :].flatten(),
+                          (y.double() - ref)[..., :, 0].flatten(), (y.double() - ref)[..., :, -1].flatten()])
+        edge_ref = torch.cat([ref[..., 0, :].flatten(), ref[..., -1, :].flatten(), ref[..., :, 0].flatten(), ref[..., :, -1].flatten()])
+        assert float(edge.norm() / edge_ref.norm()) <= 1.5e-2
+
+
 @pytest.mark.parametrize('M,K1,N1,N2', [(128, 64, 64, 64), (256, 384, 320, 1152), (1000, 384, 256, 384),
                                         (300, 1536, 320, 384), (77, 72, 40, 50), (4096, 384, 320, 1536),
                                         (513, 200, 23, 1000), (129, 384, 384, 96), (20000, 384, 256, 1152),
