@@ -20,6 +20,8 @@
 // SBO = 128 bytes): rows are 16 bytes apart inside a plane, so a view shifted by any number of positions is just a
 // different descriptor start address -- this is what makes the shifted-window trick possible without copies.
 // HBM traffic = x (+ halo) + y; every weight is read from L2 once per CTA.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace tta {
@@ -34,6 +36,8 @@ struct TcConvDesc {
   long long total;                // B * Gp
   // shared-memory byte offsets
   int o_wa, o_wk, o_wo, o_bias, o_x, o_z1, smem;
+  int wbytes;                     // size of the weight image (= offset of the activation planes)
+  int nb;                         // columns of one TMEM accumulator: 32 or 64 (two are allocated)
 };
 
 // un-swizzled K-major operand: core matrices (8 rows x 16 B) contiguous, `lbo` bytes between the two 16-byte K chunks
@@ -62,8 +66,8 @@ __device__ __forceinline__ void tcv_ld16(uint32_t addr, uint32_t (&v)[16]) {
 }
 
 // weight matrix w[n][k] (n < N, k < K, element at w + n*sn + k*sk) -> planes [k / 8][Np rows][16 bytes], zero padded
-__device__ __forceinline__ void tcv_stage_weight(uint32_t dst, const float* __restrict__ w, int N, int K, int Np, int Kp,
-                                                 int64_t sn, int64_t sk, int tid) {
+__device__ __forceinline__ void tcv_pack_weight(uint8_t* dst, const float* __restrict__ w, int N, int K, int Np, int Kp,
+                                                int64_t sn, int64_t sk, int tid) {
   const int groups = Kp >> 3;
   for (int it = tid; it < groups * Np; it += kTcThreads) {
     const int n = it % Np, kg = it / Np;
@@ -73,21 +77,34 @@ __device__ __forceinline__ void tcv_stage_weight(uint32_t dst, const float* __re
       const int k = kg * 8 + e;
       v[e] = (n < N && k < K) ? __ldg(w + (int64_t)n * sn + (int64_t)k * sk) : 0.f;
     }
-    tc::sts128(dst + (uint32_t)(kg * Np + n) * 16u, tcv_pack(v[0], v[1]), tcv_pack(v[2], v[3]), tcv_pack(v[4], v[5]),
-               tcv_pack(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst + (size_t)(kg * Np + n) * 16) =
+        make_uint4(tcv_pack(v[0], v[1]), tcv_pack(v[2], v[3]), tcv_pack(v[4], v[5]), tcv_pack(v[6], v[7]));
   }
 }
 
-__global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __restrict__ x, const float* __restrict__ a_in,
-                                                              const float* __restrict__ kern,
-                                                              const float* __restrict__ a_out,
-                                                              const float* __restrict__ bias, float* __restrict__ y,
-                                                              const __grid_constant__ TcConvDesc d) {
+// Weights -> the shared-memory image of the forward kernel (bf16 planes of A_in, the nine K_tap, A_out; fp32 bias): done
+// once per weight change by the host (fwd_common.FoldedConv), so that a CTA fetches its weights with ONE bulk copy.
+__global__ void __launch_bounds__(kTcThreads) ttconv_tc_pack_kernel(const float* __restrict__ a_in, const float* __restrict__ kern,
+                                                                   const float* __restrict__ a_out,
+                                                                   const float* __restrict__ bias, uint8_t* __restrict__ blob,
+                                                                   const __grid_constant__ TcConvDesc d) {
+  const int tid = threadIdx.x;
+  tcv_pack_weight(blob + d.o_wa, a_in, d.Ra, d.Cin, d.Rap, d.Cinp, d.Cin, 1, tid);
+  for (int tap = 0; tap < 9; ++tap)
+    tcv_pack_weight(blob + d.o_wk + (size_t)tap * (size_t)(d.Rap * d.Rbp * 2), kern + tap, d.Rb, d.Ra, d.Rbp, d.Rap,
+                    (int64_t)d.Ra * 9, 9, tid);
+  tcv_pack_weight(blob + d.o_wo, a_out, d.Cout, d.Rb, d.Coutp, d.Rbp, d.Rb, 1, tid);
+  float* bias_b = reinterpret_cast<float*>(blob + d.o_bias);
+  for (int c = tid; c < d.Coutp; c += kTcThreads) bias_b[c] = (bias && c < d.Cout) ? __ldg(bias + c) : 0.f;
+}
+
+__global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ blob,
+                                                              float* __restrict__ y, const __grid_constant__ TcConvDesc d) {
   extern __shared__ __align__(128) uint8_t tcv_smem_raw[];
   const uint32_t smem = (tc::smem_u32(tcv_smem_raw) + 127u) & ~127u;
-  __shared__ uint64_t bars[4];
+  __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_base_smem;
-  const uint32_t full0 = tc::smem_u32(bars), empty0 = full0 + 16;
+  const uint32_t full0 = tc::smem_u32(bars), empty0 = full0 + 16, wbar = full0 + 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -95,11 +112,18 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
     tc::mbar_init(full0 + 8, 1);
     tc::mbar_init(empty0, 4);
     tc::mbar_init(empty0 + 8, 4);
+    tc::mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the weight image: one bulk copy, lands while the activations are being converted
+    tc::mbar_expect_tx(wbar, (uint32_t)d.wbytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (tc::smem_u32(tcv_smem_raw) + 127u) & ~127u),
+                 "l"(blob), "r"((uint32_t)d.wbytes), "r"(wbar)
+                 : "memory");
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base_smem)),
-                 "r"(128u)
+                 "r"((uint32_t)(2 * d.nb))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -110,41 +134,48 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
   const int NP = d.TE * 128;                                 // rows of the X and Z1 planes
   const uint32_t plx = (uint32_t)NP * 16u, plz2 = (uint32_t)d.T * 128u * 16u;
 
-  // ---- weights: A_in [ra][c], K_tap [rb][ra] for the nine taps, A_out [co][rb]; bias ----
-  tcv_stage_weight(wa, a_in, d.Ra, d.Cin, d.Rap, d.Cinp, d.Cin, 1, tid);
-  for (int tap = 0; tap < 9; ++tap)
-    tcv_stage_weight(wk + (uint32_t)tap * (uint32_t)(d.Rap * d.Rbp * 2), kern + tap, d.Rb, d.Ra, d.Rbp, d.Rap, (int64_t)d.Ra * 9, 9,
-                     tid);
-  tcv_stage_weight(wo, a_out, d.Cout, d.Rb, d.Coutp, d.Rbp, d.Rb, 1, tid);
-  for (int c = tid; c < d.Coutp; c += kTcThreads) bias_s[c] = (bias && c < d.Cout) ? __ldg(bias + c) : 0.f;
-
   // ---- input chunk + halos: x (NCHW fp32) -> bf16 planes; zero at pad positions and outside the batch ----
   const long long c0 = (long long)blockIdx.x * d.T * 128;    // first output position of the chunk
   const long long e0 = c0 - d.halo;                          // position of row 0 of the X / Z1 planes
   {
     const int groups = d.Cinp >> 3;
     const int64_t hw = (int64_t)d.H * d.W;
-    for (int it = tid; it < groups * NP; it += kTcThreads) {
-      const int row = it % NP, kg = it / NP;
-      const long long g = e0 + row;
-      float v[8];
+    // four (position, channel group) items per thread in flight: 32 independent loads before the first conversion
+    for (int it0 = tid; it0 < groups * NP; it0 += 4 * kTcThreads) {
+      float v[4][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (g >= 0 && g < d.total) {
-        const int b = (int)(g / d.Gp);
-        const int rem = (int)(g - (long long)b * d.Gp);
-        const int py = rem / d.Wp, px = rem - py * d.Wp;
-        if (py >= 1 && py <= d.H && px >= 1 && px <= d.W) {
-          const float* p = x + ((int64_t)b * d.Cin + kg * 8) * hw + (int64_t)(py - 1) * d.W + (px - 1);
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (kg * 8 + e < d.Cin) v[e] = __ldg(p + e * hw);
+        for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+        const int it = it0 + u * kTcThreads;
+        if (it < groups * NP) {
+          const int row = it % NP, kg = it / NP;
+          const long long g = e0 + row;
+          if (g >= 0 && g < d.total) {
+            const int b = (int)(g / d.Gp);
+            const int rem = (int)(g - (long long)b * d.Gp);
+            const int py = rem / d.Wp, px = rem - py * d.Wp;
+            if (py >= 1 && py <= d.H && px >= 1 && px <= d.W) {
+              const float* p = x + ((int64_t)b * d.Cin + kg * 8) * hw + (int64_t)(py - 1) * d.W + (px - 1);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (kg * 8 + e < d.Cin) v[u][e] = __ldg(p + e * hw);
+            }
+          }
         }
       }
-      tc::sts128(xs + (uint32_t)kg * plx + (uint32_t)row * 16u, tcv_pack(v[0], v[1]), tcv_pack(v[2], v[3]),
-                 tcv_pack(v[4], v[5]), tcv_pack(v[6], v[7]));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * kTcThreads;
+        if (it < groups * NP) {
+          const int row = it % NP, kg = it / NP;
+          tc::sts128(xs + (uint32_t)kg * plx + (uint32_t)row * 16u, tcv_pack(v[u][0], v[u][1]), tcv_pack(v[u][2], v[u][3]),
+                     tcv_pack(v[u][4], v[u][5]), tcv_pack(v[u][6], v[u][7]));
+        }
+      }
     }
   }
+  tc::mbar_wait(wbar, 0);                                              // the weight image has landed
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -162,7 +193,7 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tc::elect_one()) {
         for (int k2 = 0; k2 < (d.Cinp >> 4); ++k2)
-          tc::umma_bf16(tmem_base + (uint32_t)buf * 64u, tcv_desc(xs + (uint32_t)(2 * k2) * plx + (uint32_t)e * 2048u, plx),
+          tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(xs + (uint32_t)(2 * k2) * plx + (uint32_t)e * 2048u, plx),
                         tcv_desc(wa + (uint32_t)(2 * k2) * (uint32_t)d.Rap * 16u, (uint32_t)d.Rap * 16u), idesc, k2 ? 1u : 0u);
         tc::umma_commit(full0 + 8 * buf);
       }
@@ -173,7 +204,7 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
       const int buf = tile_ctr & 1;
       tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * d.nb);
       const int row = e * 128 + warp * 32 + lane;
       for (int cg = 0; cg < (d.Rap >> 4); ++cg) {
         uint32_t v[16];
@@ -211,7 +242,7 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
           const int shift = (tap / 3 - 1) * d.Wp + (tap % 3 - 1);
           const uint32_t arow = (uint32_t)(t * 128 + d.halo + shift) * 16u;
           for (int k2 = 0; k2 < (d.Rap >> 4); ++k2) {
-            tc::umma_bf16(tmem_base + (uint32_t)buf * 64u, tcv_desc(z1 + (uint32_t)(2 * k2) * plx + arow, plx),
+            tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(z1 + (uint32_t)(2 * k2) * plx + arow, plx),
                           tcv_desc(wk + (uint32_t)tap * tapb + (uint32_t)(2 * k2) * plk, plk), idesc, acc);
             acc = 1;
           }
@@ -225,7 +256,7 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
       const int buf = tile_ctr & 1;
       tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * d.nb);
       const int row = t * 128 + warp * 32 + lane;
       for (int cg = 0; cg < (d.Rbp >> 4); ++cg) {
         uint32_t v[16];
@@ -259,7 +290,7 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tc::elect_one()) {
         for (int k2 = 0; k2 < (d.Rbp >> 4); ++k2)
-          tc::umma_bf16(tmem_base + (uint32_t)buf * 64u, tcv_desc(z2 + (uint32_t)(2 * k2) * plz2 + (uint32_t)t * 2048u, plz2),
+          tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(z2 + (uint32_t)(2 * k2) * plz2 + (uint32_t)t * 2048u, plz2),
                         tcv_desc(wo + (uint32_t)(2 * k2) * plo, plo), idesc, k2 ? 1u : 0u);
         tc::umma_commit(full0 + 8 * buf);
       }
@@ -271,7 +302,7 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
       const int buf = tile_ctr & 1;
       tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * d.nb);
       const long long g = c0 + t * 128 + warp * 32 + lane;
       bool valid = g < d.total;
       float* yp = y;
@@ -303,7 +334,7 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __re
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * d.nb)) : "memory");
   }
 }
 
@@ -323,6 +354,7 @@ static void tcv_layout(TcConvDesc& d, int T) {
   d.o_wo = o; o += d.Rbp * d.Coutp * 2;
   d.o_bias = o; o += d.Coutp * 4;
   o = (o + 127) & ~127;
+  d.wbytes = o;
   const int xb = d.Cinp * d.TE * 128 * 2, z2b = d.Rbp * T * 128 * 2;
   d.o_x = o; o += xb > z2b ? xb : z2b;
   d.o_z1 = o; o += d.Rap * d.TE * 128 * 2;
@@ -331,11 +363,60 @@ static void tcv_layout(TcConvDesc& d, int T) {
 
 }  // namespace tta
 
-extern "C" int tta_ttconv_tc_fwd(const float* x, const float* a_in, const float* kern, const float* a_out, const float* bias,
-                                 float* y, int B, int Cin, int H, int W, int Ra, int Rb, int Cout, int KS, int stride, int pad,
-                                 void* stream) {
+namespace tta {
+static int tcv_prepare(TcConvDesc& d, int B, int Cin, int H, int W, int Ra, int Rb, int Cout) {
+  d.B = B; d.Cin = Cin; d.H = H; d.W = W; d.Ra = Ra; d.Rb = Rb; d.Cout = Cout;
+  d.Cinp = tcv_round16(Cin); d.Rap = tcv_round16(Ra); d.Rbp = tcv_round16(Rb); d.Coutp = tcv_round16(Cout);
+  d.Wp = W + 2;
+  d.Gp = (H + 2) * d.Wp;
+  d.halo = d.Wp + 1;
+  d.total = (long long)B * d.Gp;
+  d.nb = (d.Rap > 32 || d.Rbp > 32 || d.Coutp > 32) ? 64 : 32;
+  // chunk size: as many 128-position tiles per CTA as fit in shared memory (fewer halo positions are recomputed), as long
+  // as every SM still gets a chunk
+  int T = 1;
+  static const int forced = [] { const char* e = getenv("TTA_TTCONV_T"); return e ? atoi(e) : 0; }();
+  for (int cand = forced > 0 ? forced : 8; cand >= 1; cand >>= 1) {
+    tcv_layout(d, cand);
+    const long long chunks = (d.total + (long long)cand * 128 - 1) / ((long long)cand * 128);
+    if (d.smem <= 220 * 1024 && (chunks >= kNumSMs || cand == 1 || forced > 0)) {
+      T = cand;
+      break;
+    }
+  }
+  tcv_layout(d, T);
+  return d.smem <= 227 * 1024 ? TTA_OK : TTA_E_INVALID;
+}
+}  // namespace tta
+
+extern "C" int tta_ttconv_tc_supported(int Cin, int Ra, int Rb, int Cout, int KS, int stride, int pad) {
+  return tta::ttconv_tc_supported(Cin, Ra, Rb, Cout, KS, stride, pad) ? 1 : 0;
+}
+
+extern "C" int64_t tta_ttconv_tc_blob_bytes(int Cin, int Ra, int Rb, int Cout) {
+  tta::TcConvDesc d;
+  tta::tcv_prepare(d, 1, Cin, 8, 8, Ra, Rb, Cout);
+  return d.wbytes;
+}
+
+extern "C" int tta_ttconv_tc_pack(const float* a_in, const float* kern, const float* a_out, const float* bias, void* blob,
+                                  int Cin, int Ra, int Rb, int Cout, void* stream) {
   using namespace tta;
-  if (!x || !a_in || !kern || !a_out || !y || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Ra <= 0 || Rb <= 0 || Cout <= 0) {
+  if (!a_in || !kern || !a_out || !blob || !ttconv_tc_supported(Cin, Ra, Rb, Cout, 3, 1, 1)) {
+    set_error("ttconv_tc_pack: bad argument");
+    return TTA_E_INVALID;
+  }
+  TcConvDesc d;
+  tcv_prepare(d, 1, Cin, 8, 8, Ra, Rb, Cout);
+  ttconv_tc_pack_kernel<<<1, kTcThreads, 0, (cudaStream_t)stream>>>(a_in, kern, a_out, bias, reinterpret_cast<uint8_t*>(blob), d);
+  TTA_CHECK_LAUNCH("ttconv_tc_pack launch");
+  return TTA_OK;
+}
+
+extern "C" int tta_ttconv_tc_fwd(const float* x, const void* blob, float* y, int B, int Cin, int H, int W, int Ra, int Rb,
+                                 int Cout, int KS, int stride, int pad, void* stream) {
+  using namespace tta;
+  if (!x || !blob || !y || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Ra <= 0 || Rb <= 0 || Cout <= 0) {
     set_error("ttconv_tc: bad argument");
     return TTA_E_INVALID;
   }
@@ -345,32 +426,11 @@ extern "C" int tta_ttconv_tc_fwd(const float* x, const float* a_in, const float*
     return TTA_E_INVALID;
   }
   TcConvDesc d;
-  d.B = B; d.Cin = Cin; d.H = H; d.W = W; d.Ra = Ra; d.Rb = Rb; d.Cout = Cout;
-  d.Cinp = tcv_round16(Cin); d.Rap = tcv_round16(Ra); d.Rbp = tcv_round16(Rb); d.Coutp = tcv_round16(Cout);
-  d.Wp = W + 2;
-  d.Gp = (H + 2) * d.Wp;
-  d.halo = d.Wp + 1;
-  d.total = (long long)B * d.Gp;
-  // chunk size: as many 128-position tiles per CTA as fit in shared memory (fewer halo positions are recomputed), but
-  // not so many that the grid leaves SMs without a chunk
-  int T = 0;
-  for (int pass = 0; pass < 3 && !T; ++pass)
-    for (int cand = 8; cand >= 1; cand >>= 1) {
-      tcv_layout(d, cand);
-      const long long chunks = (d.total + (long long)cand * 128 - 1) / ((long long)cand * 128);
-      const bool fits = d.smem <= 220 * 1024;
-      if (fits && (pass == 2 || chunks >= (pass == 0 ? 2 : 1) * (long long)kNumSMs)) {
-        T = cand;
-        break;
-      }
-    }
-  if (!T) T = 1;
-  tcv_layout(d, T);
-  if (d.smem > 227 * 1024) {
+  if (tcv_prepare(d, B, Cin, H, W, Ra, Rb, Cout) != TTA_OK) {
     set_error("ttconv_tc: working set %d B does not fit shared memory", d.smem);
     return TTA_E_INVALID;
   }
-  const long long chunks = (d.total + (long long)T * 128 - 1) / ((long long)T * 128);
+  const long long chunks = (d.total + (long long)d.T * 128 - 1) / ((long long)d.T * 128);
   static int smem_set = 0;
   if (d.smem > 48 * 1024 && d.smem > smem_set) {
     int rc = check_cuda(cudaFuncSetAttribute(ttconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem),
@@ -378,11 +438,7 @@ extern "C" int tta_ttconv_tc_fwd(const float* x, const float* a_in, const float*
     if (rc) return rc;
     smem_set = d.smem;
   }
-  ttconv_tc_kernel<<<(unsigned)chunks, kTcThreads, d.smem, (cudaStream_t)stream>>>(x, a_in, kern, a_out, bias, y, d);
+  ttconv_tc_kernel<<<(unsigned)chunks, kTcThreads, d.smem, (cudaStream_t)stream>>>(x, reinterpret_cast<const uint8_t*>(blob), y, d);
   TTA_CHECK_LAUNCH("ttconv_tc launch");
   return TTA_OK;
-}
-
-extern "C" int tta_ttconv_tc_supported(int Cin, int Ra, int Rb, int Cout, int KS, int stride, int pad) {
-  return tta::ttconv_tc_supported(Cin, Ra, Rb, Cout, KS, stride, pad) ? 1 : 0;
 }

@@ -88,6 +88,17 @@ class FoldedConv:
         self.key = None
         self.ops = None
         self.tc_ok = {}
+        self._blob = None
+        self._blob_key = None
+
+    def blob(self, bias):
+        """Weight image of the tensor-core kernel (tta_ttconv_tc_pack), rebuilt when a weight or the bias changes."""
+        key = (self.key, (bias.data_ptr(), bias._version) if bias is not None else None)
+        if key != self._blob_key:
+            a_in, kern, a_out = self.ops
+            self._blob = rt.ttconv_tc_pack(a_in, kern, a_out, bias)
+            self._blob_key = key
+        return self._blob
 
     def get(self):
         key = tuple((p.data_ptr(), p._version) for p in self.params)
@@ -122,9 +133,13 @@ def fused_conv(x, folded, bias, kernel_size, stride, padding):
     if tc_ok is None:
         tc_ok = _TTCONV_TC and rt.ttconv_tc_supported(C, a_in.shape[0], kern.shape[0], cout, ks, s, p)
         folded.tc_ok[(C, ks, s, p)] = tc_ok
-    call = rt.ttconv_tc_fwd_raw if tc_ok else rt.ttconv_fused_fwd_raw
-    call(x.data_ptr(), a_in.data_ptr(), kern.data_ptr(), a_out.data_ptr(), bias.data_ptr() if bias is not None else None,
-         y.data_ptr(), B, C, H, W, a_in.shape[0], kern.shape[0], cout, ks, s, p)
+    if tc_ok:
+        rt.ttconv_tc_fwd_raw(x.data_ptr(), folded.blob(bias).data_ptr(), y.data_ptr(), B, C, H, W, a_in.shape[0],
+                             kern.shape[0], cout, ks, s, p)
+    else:
+        rt.ttconv_fused_fwd_raw(x.data_ptr(), a_in.data_ptr(), kern.data_ptr(), a_out.data_ptr(),
+                                bias.data_ptr() if bias is not None else None, y.data_ptr(), B, C, H, W, a_in.shape[0],
+                                kern.shape[0], cout, ks, s, p)
     return y
 
 

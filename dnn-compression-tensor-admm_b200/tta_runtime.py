@@ -63,7 +63,7 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
-           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd', 'tta_ttconv_tc_fwd', 'tta_ttconv_tc_supported',
+           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd', 'tta_ttconv_tc_fwd', 'tta_ttconv_tc_supported', 'tta_ttconv_tc_pack', 'tta_ttconv_tc_blob_bytes',
            'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k',
            'tta_symeig_profile_enable', 'tta_symeig_profile_read', 'tta_orth_penalty_fwd_batched',
            'tta_orth_penalty_bwd_batched']
@@ -150,14 +150,18 @@ def _load():
     lib.tta_nhwc_to_nchw_f32.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp]
     lib.tta_im2col_bf16.argtypes = [vp, vp] + [ci] * 16 + [vp]
     lib.tta_ttconv_fused_fwd.argtypes = [vp] * 6 + [ci] * 10 + [vp]
-    lib.tta_ttconv_tc_fwd.argtypes = [vp] * 6 + [ci] * 10 + [vp]
+    lib.tta_ttconv_tc_fwd.argtypes = [vp] * 3 + [ci] * 10 + [vp]
     lib.tta_ttconv_tc_supported.argtypes = [ci] * 7
+    lib.tta_ttconv_tc_pack.argtypes = [vp] * 5 + [ci] * 4 + [vp]
+    lib.tta_ttconv_tc_blob_bytes.argtypes = [ci] * 4
+    lib.tta_ttconv_tc_blob_bytes.restype = ctypes.c_int64
     lib.tta_lowrank2_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, ci, i64, ci, ci, ci, vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count', 'tta_symeig_work_doubles',
                         'tta_symeig_profile_enable', 'tta_symeig_profile_read',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
-                        'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_gram_enable_tc'):
+                        'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_gram_enable_tc',
+                        'tta_ttconv_tc_blob_bytes'):
             getattr(lib, name).restype = ci
     _LIB = lib
     return lib
@@ -419,14 +423,24 @@ def ttconv_tc_supported(Cin, Ra, Rb, Cout, KS, stride, pad):
     return bool(lib().tta_ttconv_tc_supported(int(Cin), int(Ra), int(Rb), int(Cout), int(KS), int(stride), int(pad)))
 
 
-def ttconv_tc_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
-    _check(lib().tta_ttconv_tc_fwd(_p(x), _p(a_in), _p(kern), _p(a_out), _p(bias), _p(y), int(B), int(Cin), int(H),
-                                   int(W), int(Ra), int(Rb), int(Cout), int(KS), int(stride), int(pad),
-                                   stream_handle()), 'tta_ttconv_tc_fwd')
+def ttconv_tc_pack(a_in, kern, a_out, bias):
+    """Weight image of the tensor-core fused convolution (bf16 planes + fp32 bias) as a uint8 device tensor."""
+    ra, cin = a_in.shape
+    rb, cout = kern.shape[0], a_out.shape[0]
+    blob = torch.empty(int(lib().tta_ttconv_tc_blob_bytes(int(cin), int(ra), int(rb), int(cout))), dtype=torch.uint8,
+                       device=a_in.device)
+    _check(lib().tta_ttconv_tc_pack(_p(a_in), _p(kern), _p(a_out), _p(bias), _p(blob), int(cin), int(ra), int(rb), int(cout),
+                                    stream_handle()), 'tta_ttconv_tc_pack')
+    return blob
 
 
-def ttconv_tc_fwd_raw(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
-    rc = lib().tta_ttconv_tc_fwd(x, a_in, kern, a_out, bias, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad,
+def ttconv_tc_fwd(x, blob, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
+    _check(lib().tta_ttconv_tc_fwd(_p(x), _p(blob), _p(y), int(B), int(Cin), int(H), int(W), int(Ra), int(Rb), int(Cout),
+                                   int(KS), int(stride), int(pad), stream_handle()), 'tta_ttconv_tc_fwd')
+
+
+def ttconv_tc_fwd_raw(x, blob, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad):
+    rc = lib().tta_ttconv_tc_fwd(x, blob, y, B, Cin, H, W, Ra, Rb, Cout, KS, stride, pad,
                                  torch.cuda.current_stream().cuda_stream)
     if rc:
         _check(rc, 'tta_ttconv_tc_fwd')

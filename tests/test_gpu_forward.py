@@ -277,7 +277,8 @@ def test_ttconv_tensor_core_kernel_matches_conv_chain(B, Cin, H, W, Ra, Rb, Cout
     bias = torch.randn(Cout, generator=g).to(DEV)
     for b in (bias, None):
         y = torch.full((B, Cout, H, W), float('nan'), device=DEV)
-        rt.ttconv_tc_fwd(x, a_in, kern, a_out, b, y, B, Cin, H, W, Ra, Rb, Cout, 3, 1, 1)
+        blob = rt.ttconv_tc_pack(a_in, kern, a_out, b)
+        rt.ttconv_tc_fwd(x, blob, y, B, Cin, H, W, Ra, Rb, Cout, 3, 1, 1)
         torch.cuda.synchronize()
         ref = F.conv2d(F.conv2d(F.conv2d(x.double(), a_in.double()[:, :, None, None]), kern.double(), None, 1, 1),
                        a_out.double()[:, :, None, None], b.double() if b is not None else None)
