@@ -26,7 +26,7 @@
 
 namespace tta {
 
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 256;      // pack kernel
 
 struct TcConvDesc {
   int B, Cin, H, W, Ra, Rb, Cout;
@@ -37,6 +37,7 @@ struct TcConvDesc {
   // shared-memory byte offsets
   int o_wa, o_wk, o_wo, o_bias, o_x, o_z1, smem;
   int wbytes;                     // size of the weight image (= offset of the activation planes)
+  int xbytes;                     // one X buffer (two are laid out)
   int nb;                         // columns of one TMEM accumulator: 32 or 64 (two are allocated)
 };
 
@@ -98,241 +99,255 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_pack_kernel(const float*
   for (int c = tid; c < d.Coutp; c += kTcThreads) bias_b[c] = (bias && c < d.Cout) ? __ldg(bias + c) : 0.f;
 }
 
-__global__ void __launch_bounds__(kTcThreads) ttconv_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ blob,
-                                                              float* __restrict__ y, const __grid_constant__ TcConvDesc d) {
+// Persistent, warp-specialised: a CTA fetches the weight image once and walks over chunks blockIdx.x, blockIdx.x + gridDim.x, ...
+//   warps 0-7   loaders: x of chunk i + 1 -> bf16 planes in the other X buffer while chunk i is being multiplied
+//   warp 8      tcgen05.mma issuer (stage 1 -> stage 2 -> stage 3 of a chunk, two TMEM accumulators used alternately)
+//   warps 9-12  drain: TMEM -> bf16 -> Z1 / Z2 planes, and TMEM + bias -> y (warp & 3 selects the TMEM lane quadrant)
+constexpr int kTcvLoaders = 256;
+constexpr int kTcvThreads = kTcvLoaders + 32 + 128;
+
+__global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ blob,
+                                                                  float* __restrict__ y, const __grid_constant__ TcConvDesc d) {
   extern __shared__ __align__(128) uint8_t tcv_smem_raw[];
   const uint32_t smem = (tc::smem_u32(tcv_smem_raw) + 127u) & ~127u;
-  __shared__ uint64_t bars[5];
+  __shared__ uint64_t bars[11];
   __shared__ uint32_t tmem_base_smem;
-  const uint32_t full0 = tc::smem_u32(bars), empty0 = full0 + 16, wbar = full0 + 32;
+  const uint32_t bar0 = tc::smem_u32(bars);
+  const uint32_t afull0 = bar0, aempty0 = bar0 + 16, xfull0 = bar0 + 32, xempty0 = bar0 + 48, z1done = bar0 + 64, z2done = bar0 + 72,
+                 wbar = bar0 + 80;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    tc::mbar_init(full0, 1);
-    tc::mbar_init(full0 + 8, 1);
-    tc::mbar_init(empty0, 4);
-    tc::mbar_init(empty0 + 8, 4);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      tc::mbar_init(afull0 + 8 * s2, 1);
+      tc::mbar_init(aempty0 + 8 * s2, 4);
+      tc::mbar_init(xfull0 + 8 * s2, kTcvLoaders / 32);
+      tc::mbar_init(xempty0 + 8 * s2, 1);
+    }
+    tc::mbar_init(z1done, 4);
+    tc::mbar_init(z2done, 4);
     tc::mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // the weight image: one bulk copy, lands while the activations are being converted
+    // the weight image: one bulk copy per CTA, lands while the first chunk of activations is being converted
     tc::mbar_expect_tx(wbar, (uint32_t)d.wbytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (tc::smem_u32(tcv_smem_raw) + 127u) & ~127u),
-                 "l"(blob), "r"((uint32_t)d.wbytes), "r"(wbar)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem), "l"(blob),
+                 "r"((uint32_t)d.wbytes), "r"(wbar)
                  : "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base_smem)),
                  "r"((uint32_t)(2 * d.nb))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-
-  const uint32_t wa = smem + d.o_wa, wk = smem + d.o_wk, wo = smem + d.o_wo, xs = smem + d.o_x, z1 = smem + d.o_z1;
-  const uint32_t z2 = xs;                                    // X is dead once stage 1 is over
-  float* bias_s = reinterpret_cast<float*>(tcv_smem_raw + ((smem - tc::smem_u32(tcv_smem_raw)) + d.o_bias));
-  const int NP = d.TE * 128;                                 // rows of the X and Z1 planes
-  const uint32_t plx = (uint32_t)NP * 16u, plz2 = (uint32_t)d.T * 128u * 16u;
-
-  // ---- input chunk + halos: x (NCHW fp32) -> bf16 planes; zero at pad positions and outside the batch ----
-  const long long c0 = (long long)blockIdx.x * d.T * 128;    // first output position of the chunk
-  const long long e0 = c0 - d.halo;                          // position of row 0 of the X / Z1 planes
-  {
-    const int groups = d.Cinp >> 3;
-    const int64_t hw = (int64_t)d.H * d.W;
-    // four (position, channel group) items per thread in flight: 32 independent loads before the first conversion
-    for (int it0 = tid; it0 < groups * NP; it0 += 4 * kTcThreads) {
-      float v[4][8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
-        const int it = it0 + u * kTcThreads;
-        if (it < groups * NP) {
-          const int row = it % NP, kg = it / NP;
-          const long long g = e0 + row;
-          if (g >= 0 && g < d.total) {
-            const int b = (int)(g / d.Gp);
-            const int rem = (int)(g - (long long)b * d.Gp);
-            const int py = rem / d.Wp, px = rem - py * d.Wp;
-            if (py >= 1 && py <= d.H && px >= 1 && px <= d.W) {
-              const float* p = x + ((int64_t)b * d.Cin + kg * 8) * hw + (int64_t)(py - 1) * d.W + (px - 1);
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (kg * 8 + e < d.Cin) v[u][e] = __ldg(p + e * hw);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int it = it0 + u * kTcThreads;
-        if (it < groups * NP) {
-          const int row = it % NP, kg = it / NP;
-          tc::sts128(xs + (uint32_t)kg * plx + (uint32_t)row * 16u, tcv_pack(v[u][0], v[u][1]), tcv_pack(v[u][2], v[u][3]),
-                     tcv_pack(v[u][4], v[u][5]), tcv_pack(v[u][6], v[u][7]));
-        }
-      }
-    }
-  }
-  tc::mbar_wait(wbar, 0);                                              // the weight image has landed
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
-  int tile_ctr = 0;          // accumulator tiles issued / drained so far (same sequence in the issuer and the drainers)
+  const uint32_t wa = smem + d.o_wa, wk = smem + d.o_wk, wo = smem + d.o_wo, z1 = smem + d.o_z1;
+  const float* bias_s = reinterpret_cast<const float*>(tcv_smem_raw + ((smem - tc::smem_u32(tcv_smem_raw)) + d.o_bias));
+  const int NP = d.TE * 128;                                 // rows of the X and Z1 planes
+  const int PE = d.T * 128 + 2 * d.halo;                     // rows of them that are ever read by stage 2
+  const uint32_t plx = (uint32_t)NP * 16u, plz2 = (uint32_t)d.T * 128u * 16u;
+  const uint32_t xbytes = (uint32_t)d.xbytes;                // one X buffer (Z2 of the same chunk aliases it)
+  const long long nchunks = (d.total + (long long)d.T * 128 - 1) / ((long long)d.T * 128);
 
-  // =============================== stage 1: Z1 = X . A_in^T over the chunk and its halos ===============================
-  if (warp == 4) {
-    const uint32_t idesc = tc::umma_idesc_bf16(d.Rap);
-    for (int e = 0; e < d.TE; ++e, ++tile_ctr) {
-      const int buf = tile_ctr & 1;
-      if (tile_ctr >= 2) tc::mbar_wait(empty0 + 8 * buf, (uint32_t)(((tile_ctr >> 1) - 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tc::elect_one()) {
-        for (int k2 = 0; k2 < (d.Cinp >> 4); ++k2)
-          tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(xs + (uint32_t)(2 * k2) * plx + (uint32_t)e * 2048u, plx),
-                        tcv_desc(wa + (uint32_t)(2 * k2) * (uint32_t)d.Rap * 16u, (uint32_t)d.Rap * 16u), idesc, k2 ? 1u : 0u);
-        tc::umma_commit(full0 + 8 * buf);
-      }
-      __syncwarp();
-    }
-  } else if (warp < 4) {
-    for (int e = 0; e < d.TE; ++e, ++tile_ctr) {
-      const int buf = tile_ctr & 1;
-      tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * d.nb);
-      const int row = e * 128 + warp * 32 + lane;
-      for (int cg = 0; cg < (d.Rap >> 4); ++cg) {
-        uint32_t v[16];
-        tcv_ld16(taddr + (uint32_t)cg * 16u, v);
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tc::sts128(z1 + (uint32_t)(2 * cg + h) * plx + (uint32_t)row * 16u,
-                     tcv_pack(__uint_as_float(v[8 * h]), __uint_as_float(v[8 * h + 1])),
-                     tcv_pack(__uint_as_float(v[8 * h + 2]), __uint_as_float(v[8 * h + 3])),
-                     tcv_pack(__uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5])),
-                     tcv_pack(__uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7])));
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(empty0 + 8 * buf);
-    }
-  }
-  if (warp > 4) tile_ctr += d.TE;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // =============================== stage 2: Z2 = sum over taps of shifted Z1 . K_tap^T ===============================
-  if (warp == 4) {
-    const uint32_t idesc = tc::umma_idesc_bf16(d.Rbp);
-    const uint32_t plk = (uint32_t)d.Rbp * 16u, tapb = (uint32_t)(d.Rap * d.Rbp * 2);
-    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
-      const int buf = tile_ctr & 1;
-      if (tile_ctr >= 2) tc::mbar_wait(empty0 + 8 * buf, (uint32_t)(((tile_ctr >> 1) - 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tc::elect_one()) {
-        uint32_t acc = 0;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int shift = (tap / 3 - 1) * d.Wp + (tap % 3 - 1);
-          const uint32_t arow = (uint32_t)(t * 128 + d.halo + shift) * 16u;
-          for (int k2 = 0; k2 < (d.Rap >> 4); ++k2) {
-            tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(z1 + (uint32_t)(2 * k2) * plx + arow, plx),
-                          tcv_desc(wk + (uint32_t)tap * tapb + (uint32_t)(2 * k2) * plk, plk), idesc, acc);
-            acc = 1;
-          }
-        }
-        tc::umma_commit(full0 + 8 * buf);
-      }
-      __syncwarp();
-    }
-  } else if (warp < 4) {
-    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
-      const int buf = tile_ctr & 1;
-      tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * d.nb);
-      const int row = t * 128 + warp * 32 + lane;
-      for (int cg = 0; cg < (d.Rbp >> 4); ++cg) {
-        uint32_t v[16];
-        tcv_ld16(taddr + (uint32_t)cg * 16u, v);
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tc::sts128(z2 + (uint32_t)(2 * cg + h) * plz2 + (uint32_t)row * 16u,
-                     tcv_pack(__uint_as_float(v[8 * h]), __uint_as_float(v[8 * h + 1])),
-                     tcv_pack(__uint_as_float(v[8 * h + 2]), __uint_as_float(v[8 * h + 3])),
-                     tcv_pack(__uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5])),
-                     tcv_pack(__uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7])));
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(empty0 + 8 * buf);
-    }
-  }
-  if (warp > 4) tile_ctr += d.T;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // =============================== stage 3: Y = Z2 . A_out^T + bias -> NCHW ===============================
-  if (warp == 4) {
-    const uint32_t idesc = tc::umma_idesc_bf16(d.Coutp);
-    const uint32_t plo = (uint32_t)d.Coutp * 16u;
-    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
-      const int buf = tile_ctr & 1;
-      if (tile_ctr >= 2) tc::mbar_wait(empty0 + 8 * buf, (uint32_t)(((tile_ctr >> 1) - 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tc::elect_one()) {
-        for (int k2 = 0; k2 < (d.Rbp >> 4); ++k2)
-          tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(z2 + (uint32_t)(2 * k2) * plz2 + (uint32_t)t * 2048u, plz2),
-                        tcv_desc(wo + (uint32_t)(2 * k2) * plo, plo), idesc, k2 ? 1u : 0u);
-        tc::umma_commit(full0 + 8 * buf);
-      }
-      __syncwarp();
-    }
-  } else if (warp < 4) {
+  if (warp < 8) {
+    // =============================== loaders ===============================
+    const int groups = d.Cinp >> 3;
     const int64_t hw = (int64_t)d.H * d.W;
-    for (int t = 0; t < d.T; ++t, ++tile_ctr) {
-      const int buf = tile_ctr & 1;
-      tc::mbar_wait(full0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * d.nb);
-      const long long g = c0 + t * 128 + warp * 32 + lane;
-      bool valid = g < d.total;
-      float* yp = y;
-      if (valid) {
-        const int b = (int)(g / d.Gp);
-        const int rem = (int)(g - (long long)b * d.Gp);
-        const int py = rem / d.Wp, px = rem - py * d.Wp;
-        valid = py >= 1 && py <= d.H && px >= 1 && px <= d.W;
-        yp = y + (int64_t)b * d.Cout * hw + (int64_t)(py - 1) * d.W + (px - 1);
-      }
-      for (int cg = 0; cg < (d.Coutp >> 4); ++cg) {
-        uint32_t v[16];
-        tcv_ld16(taddr + (uint32_t)cg * 16u, v);
-        if (valid) {
+    int it_ = 0;
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it_) {
+      const int xb = it_ & 1;
+      if (it_ >= 2) tc::mbar_wait(xempty0 + 8 * xb, (uint32_t)(((it_ >> 1) - 1) & 1));
+      const uint32_t xs = smem + d.o_x + (uint32_t)xb * xbytes;
+      const int e0 = (int)(ch * d.T * 128) - d.halo;           // position of row 0 of the planes
+      // four (position, channel group) items per thread in flight: 32 independent loads before the first conversion
+      for (int it0 = tid; it0 < groups * PE; it0 += 4 * kTcvLoaders) {
+        float v[4][8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int co = cg * 16 + j;
-            if (co < d.Cout) yp[(int64_t)co * hw] = __uint_as_float(v[j]) + bias_s[co];
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+          const int it = it0 + u * kTcvLoaders;
+          if (it < groups * PE) {
+            const int row = it % PE, kg = it / PE;
+            const int g = e0 + row;
+            if (g >= 0 && g < (int)d.total) {
+              const int b = g / d.Gp;
+              const int rem = g - b * d.Gp;
+              const int py = rem / d.Wp, px = rem - py * d.Wp;
+              if (py >= 1 && py <= d.H && px >= 1 && px <= d.W) {
+                const float* p = x + ((int64_t)b * d.Cin + kg * 8) * hw + (int64_t)(py - 1) * d.W + (px - 1);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (kg * 8 + e < d.Cin) v[u][e] = __ldg(p + e * hw);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int it = it0 + u * kTcvLoaders;
+          if (it < groups * PE) {
+            const int row = it % PE, kg = it / PE;
+            tc::sts128(xs + (uint32_t)kg * plx + (uint32_t)row * 16u, tcv_pack(v[u][0], v[u][1]), tcv_pack(v[u][2], v[u][3]),
+                       tcv_pack(v[u][4], v[u][5]), tcv_pack(v[u][6], v[u][7]));
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(empty0 + 8 * buf);
+      if (lane == 0) tc::mbar_arrive(xfull0 + 8 * xb);
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    tc::mbar_wait(wbar, 0);                                             // the weight image has landed
+    const uint32_t id1 = tc::umma_idesc_bf16(d.Rap), id2 = tc::umma_idesc_bf16(d.Rbp), id3 = tc::umma_idesc_bf16(d.Coutp);
+    const uint32_t pla = (uint32_t)d.Rap * 16u, plk = (uint32_t)d.Rbp * 16u, plo = (uint32_t)d.Coutp * 16u;
+    const uint32_t tapb = (uint32_t)(d.Rap * d.Rbp * 2);
+    int tile_ctr = 0, it_ = 0;
+    auto acquire = [&]() {      // accumulator of the next tile
+      const int buf = tile_ctr & 1;
+      if (tile_ctr >= 2) tc::mbar_wait(aempty0 + 8 * buf, (uint32_t)(((tile_ctr >> 1) - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      return buf;
+    };
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it_) {
+      const int xb = it_ & 1;
+      const uint32_t xs = smem + d.o_x + (uint32_t)xb * xbytes, z2 = xs;
+      tc::mbar_wait(xfull0 + 8 * xb, (uint32_t)((it_ >> 1) & 1));
+      // ---- stage 1: Z1 = X . A_in^T over the chunk and its halos ----
+      for (int e = 0; e < d.TE; ++e, ++tile_ctr) {
+        const int buf = acquire();
+        if (tc::elect_one()) {
+          for (int k2 = 0; k2 < (d.Cinp >> 4); ++k2)
+            tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(xs + (uint32_t)(2 * k2) * plx + (uint32_t)e * 2048u, plx),
+                          tcv_desc(wa + (uint32_t)(2 * k2) * pla, pla), id1, k2 ? 1u : 0u);
+          tc::umma_commit(afull0 + 8 * buf);
+        }
+        __syncwarp();
+      }
+      // ---- stage 2: Z2 = sum over taps of shifted Z1 . K_tap^T ----
+      tc::mbar_wait(z1done, (uint32_t)(it_ & 1));
+      for (int t = 0; t < d.T; ++t, ++tile_ctr) {
+        const int buf = acquire();
+        if (tc::elect_one()) {
+          uint32_t acc = 0;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int shift = (tap / 3 - 1) * d.Wp + (tap % 3 - 1);
+            const uint32_t arow = (uint32_t)(t * 128 + d.halo + shift) * 16u;
+            for (int k2 = 0; k2 < (d.Rap >> 4); ++k2) {
+              tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(z1 + (uint32_t)(2 * k2) * plx + arow, plx),
+                            tcv_desc(wk + (uint32_t)tap * tapb + (uint32_t)(2 * k2) * plk, plk), id2, acc);
+              acc = 1;
+            }
+          }
+          tc::umma_commit(afull0 + 8 * buf);
+        }
+        __syncwarp();
+      }
+      // ---- stage 3: Y = Z2 . A_out^T ----
+      tc::mbar_wait(z2done, (uint32_t)(it_ & 1));
+      for (int t = 0; t < d.T; ++t, ++tile_ctr) {
+        const int buf = acquire();
+        if (tc::elect_one()) {
+          for (int k2 = 0; k2 < (d.Rbp >> 4); ++k2)
+            tc::umma_bf16(tmem_base + (uint32_t)(buf * d.nb), tcv_desc(z2 + (uint32_t)(2 * k2) * plz2 + (uint32_t)t * 2048u, plz2),
+                          tcv_desc(wo + (uint32_t)(2 * k2) * plo, plo), id3, k2 ? 1u : 0u);
+          tc::umma_commit(afull0 + 8 * buf);
+          if (t == d.T - 1) tc::umma_commit(xempty0 + 8 * xb);        // X / Z2 of this chunk may be overwritten
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================== drain ===============================
+    const int quad = warp & 3;                                          // warps 9..12 -> quadrants 1, 2, 3, 0
+    const int64_t hw = (int64_t)d.H * d.W;
+    tc::mbar_wait(wbar, 0);                                             // bias
+    int tile_ctr = 0, it_ = 0;
+    auto pack_rows = [&](uint32_t dst_plane0, uint32_t plane_bytes, int row, int ngroups16, int buf) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * d.nb);
+      for (int cg = 0; cg < ngroups16; ++cg) {
+        uint32_t v[16];
+        tcv_ld16(taddr + (uint32_t)cg * 16u, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tc::sts128(dst_plane0 + (uint32_t)(2 * cg + h) * plane_bytes + (uint32_t)row * 16u,
+                     tcv_pack(__uint_as_float(v[8 * h]), __uint_as_float(v[8 * h + 1])),
+                     tcv_pack(__uint_as_float(v[8 * h + 2]), __uint_as_float(v[8 * h + 3])),
+                     tcv_pack(__uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5])),
+                     tcv_pack(__uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7])));
+      }
+    };
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it_) {
+      const int xb = it_ & 1;
+      const uint32_t z2 = smem + d.o_x + (uint32_t)xb * xbytes;
+      const int c0 = (int)(ch * d.T * 128);
+      for (int e = 0; e < d.TE; ++e, ++tile_ctr) {                      // stage 1 -> Z1
+        const int buf = tile_ctr & 1;
+        tc::mbar_wait(afull0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        pack_rows(z1, plx, e * 128 + quad * 32 + lane, d.Rap >> 4, buf);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (e == d.TE - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(aempty0 + 8 * buf);
+          if (e == d.TE - 1) tc::mbar_arrive(z1done);
+        }
+      }
+      for (int t = 0; t < d.T; ++t, ++tile_ctr) {                       // stage 2 -> Z2
+        const int buf = tile_ctr & 1;
+        tc::mbar_wait(afull0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        pack_rows(z2, plz2, t * 128 + quad * 32 + lane, d.Rbp >> 4, buf);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (t == d.T - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(aempty0 + 8 * buf);
+          if (t == d.T - 1) tc::mbar_arrive(z2done);
+        }
+      }
+      for (int t = 0; t < d.T; ++t, ++tile_ctr) {                       // stage 3 -> y
+        const int buf = tile_ctr & 1;
+        tc::mbar_wait(afull0 + 8 * buf, (uint32_t)((tile_ctr >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * d.nb);
+        const int g = c0 + t * 128 + quad * 32 + lane;
+        bool valid = g < (int)d.total;
+        float* yp = y;
+        if (valid) {
+          const int b = g / d.Gp;
+          const int rem = g - b * d.Gp;
+          const int py = rem / d.Wp, px = rem - py * d.Wp;
+          valid = py >= 1 && py <= d.H && px >= 1 && px <= d.W;
+          yp = y + (int64_t)b * d.Cout * hw + (int64_t)(py - 1) * d.W + (px - 1);
+        }
+        for (int cg = 0; cg < (d.Coutp >> 4); ++cg) {
+          uint32_t v[16];
+          tcv_ld16(taddr + (uint32_t)cg * 16u, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = cg * 16 + j;
+              if (co < d.Cout) yp[(int64_t)co * hw] = __uint_as_float(v[j]) + bias_s[co];
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(aempty0 + 8 * buf);
+      }
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * d.nb)) : "memory");
   }
@@ -356,7 +371,8 @@ static void tcv_layout(TcConvDesc& d, int T) {
   o = (o + 127) & ~127;
   d.wbytes = o;
   const int xb = d.Cinp * d.TE * 128 * 2, z2b = d.Rbp * T * 128 * 2;
-  d.o_x = o; o += xb > z2b ? xb : z2b;
+  d.xbytes = xb > z2b ? xb : z2b;
+  d.o_x = o; o += 2 * d.xbytes;
   d.o_z1 = o; o += d.Rap * d.TE * 128 * 2;
   d.smem = o + 128;
 }
@@ -374,15 +390,13 @@ static int tcv_prepare(TcConvDesc& d, int B, int Cin, int H, int W, int Ra, int 
   d.nb = (d.Rap > 32 || d.Rbp > 32 || d.Coutp > 32) ? 64 : 32;
   // chunk size: as many 128-position tiles per CTA as fit in shared memory (fewer halo positions are recomputed), as long
   // as every SM still gets a chunk
-  int T = 1;
+  // chunk size: tiles per chunk.  Small chunks keep the stage chain of a chunk short (the loads of the next chunk overlap
+  // it); every chunk recomputes its two halos in stage 1.  TTA_TTCONV_T overrides (measurements).
   static const int forced = [] { const char* e = getenv("TTA_TTCONV_T"); return e ? atoi(e) : 0; }();
-  for (int cand = forced > 0 ? forced : 8; cand >= 1; cand >>= 1) {
-    tcv_layout(d, cand);
-    const long long chunks = (d.total + (long long)cand * 128 - 1) / ((long long)cand * 128);
-    if (d.smem <= 220 * 1024 && (chunks >= kNumSMs || cand == 1 || forced > 0)) {
-      T = cand;
-      break;
-    }
+  int T = forced > 0 ? forced : 2;
+  for (; T > 1; T >>= 1) {
+    tcv_layout(d, T);
+    if (d.smem <= 220 * 1024) break;
   }
   tcv_layout(d, T);
   return d.smem <= 227 * 1024 ? TTA_OK : TTA_E_INVALID;
@@ -430,6 +444,10 @@ extern "C" int tta_ttconv_tc_fwd(const float* x, const void* blob, float* y, int
     set_error("ttconv_tc: working set %d B does not fit shared memory", d.smem);
     return TTA_E_INVALID;
   }
+  if (d.total >= (1ll << 31) - 4096) {
+    set_error("ttconv_tc: %lld padded positions exceed the 32-bit position space", d.total);
+    return TTA_E_INVALID;
+  }
   const long long chunks = (d.total + (long long)d.T * 128 - 1) / ((long long)d.T * 128);
   static int smem_set = 0;
   if (d.smem > 48 * 1024 && d.smem > smem_set) {
@@ -438,7 +456,14 @@ extern "C" int tta_ttconv_tc_fwd(const float* x, const void* blob, float* y, int
     if (rc) return rc;
     smem_set = d.smem;
   }
-  ttconv_tc_kernel<<<(unsigned)chunks, kTcThreads, d.smem, (cudaStream_t)stream>>>(x, reinterpret_cast<const uint8_t*>(blob), y, d);
+  // persistent: as many CTAs as fit at once (shared memory, 512 TMEM columns, 2048 threads per SM), each walks over chunks
+  int per_sm = (227 * 1024) / (d.smem + 1024);
+  if (per_sm > 512 / (2 * d.nb)) per_sm = 512 / (2 * d.nb);
+  if (per_sm > 2) per_sm = 2;                      // registers: __launch_bounds__(416, 2)
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)kNumSMs * per_sm;
+  if (grid > chunks) grid = chunks;
+  ttconv_tc_kernel<<<(unsigned)grid, kTcvThreads, d.smem, (cudaStream_t)stream>>>(x, reinterpret_cast<const uint8_t*>(blob), y, d);
   TTA_CHECK_LAUNCH("ttconv_tc launch");
   return TTA_OK;
 }

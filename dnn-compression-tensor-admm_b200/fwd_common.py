@@ -315,7 +315,12 @@ def lowrank2_apply(ws, x2d, w1, w2, bias):
         rt.cast_bf16(x32.reshape(-1), xb)
         out_dtype = torch.float32
     N1, N2 = w1.N, w2.N
-    ldy = N2 if out_dtype == torch.float32 or N2 % 8 == 0 else pad8(N2)
+    # the kernel stores 16-byte granules: the row pitch is a multiple of 4 (fp32) / 8 (bf16) elements, the pad columns
+    # are sliced off (e.g. a 10-class head)
+    if out_dtype == torch.float32:
+        ldy = N2 if N2 % 4 == 0 else (N2 + 3) // 4 * 4
+    else:
+        ldy = N2 if N2 % 8 == 0 else pad8(N2)
     y = torch.empty(R, ldy, dtype=out_dtype, device=dev)
     rt.lowrank2_fwd(xb, w1.mat, w2.mat, bias, y, R, K1, N1, N2, ldx=K1, ld1=w1.ld, ld2=w2.ld, ldy=ldy)
     return y if ldy == N2 else y[:, :N2]

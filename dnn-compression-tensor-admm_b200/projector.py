@@ -852,6 +852,26 @@ class EigBatch:
             out[q] = int(jac_sweeps[jj])
         return out
 
+    def snapshot_flags(self, *tabs_list):
+        """Device-side copy of what `results` would check (fp64 solver status words, Jacobi convergence words) for solves
+        whose buffers are about to be reused without a host synchronisation in between."""
+        snap = []
+        for tabs in tabs_list:
+            if tabs['symeig'].n:
+                snap.append(('status', tabs, tabs['status'][:tabs['symeig'].n].clone()))
+            if tabs['eig'].n and not tabs['big']:
+                snap.append(('jacobi', tabs, tabs['scratch'][:6 * tabs['eig'].n].clone()))
+        return snap
+
+    def check_flags(self, snapshots):
+        for snap in snapshots:
+            for kind, tabs, t in snap:
+                if kind == 'status':
+                    if bool(t.ne(0).any().item()):
+                        raise EigClusterFlag()
+                else:
+                    rt.jacobi_results_from_host(t.cpu().numpy(), tabs['eig'], self.max_sweeps)
+
     def results(self, tabs):
         if not tabs['eig'].n:
             return self._merge(tabs, [])
@@ -939,7 +959,7 @@ class TKProjectionPlan:
             w['e0'] = self.eig.buffers((li, 0), O, r0, max(KK * I, O), False)
             w['e1'] = self.eig.buffers((li, 1), I, r1, max(O * KK, I), False)
             self.ws.append(w)
-        self.norms = torch.zeros(2 * max(len(self.layers), 1), dtype=torch.float64, device=dev)
+        self.norms = torch.zeros(4 * max(len(self.layers), 1), dtype=torch.float64, device=dev)     # |X|^2, 3 sweeps of |core|^2
 
     # -- static per-layer task rows ---------------------------------------------------------------
     def bind(self, w_list, u_list, z_list):
@@ -1026,37 +1046,46 @@ class TKProjectionPlan:
         active = everyone
         it = 0
         ph.mark('hooi')
+        # tensorly's rule (`iteration > 1 and |err[-2] - err[-1]| < tol`) cannot fire before the third sweep: the first three
+        # sweeps are enqueued back to back (core norms into three device slots, eigensolver flags OR-ed on the device) and
+        # read back ONCE; from then on one host synchronisation per sweep decides which layers stop.
+        first = min(3, self.n_iter_max)
         while active and it < self.n_iter_max:
-            # one host synchronisation per HOOI sweep (the stopping rule needs the core norm on the host):
-            # both eigensolves are only enqueued, their sweep counts are read after the norm has arrived
+            batch = first if it == 0 else 1
             t0, t1 = self._eig_tabs('sweep0', active), self._eig_tabs('sweep1', active)
-            rt.gemm(self._tab('p0', active))
-            self.eig.enqueue(t0, warm=True)          # previous solve of the same mode: HOSVD init or the last sweep
-            rt.gemm(self._tab('p1', active))
-            self.eig.enqueue(t1, warm=True)
-            rt.gemm(self._tab('core', active))
-            out = self.norms[n:n + len(active)]
-            out.zero_()
-            rt.sqnorm(self._tab('nc', active), out)
-            norm_c2 = out.cpu().numpy()
+            slots = self.norms[n:n + batch * len(active)]
+            slots.zero_()
+            flags = []
+            for b in range(batch):
+                rt.gemm(self._tab('p0', active))
+                self.eig.enqueue(t0, warm=True)          # previous solve of the same mode: HOSVD init or the last sweep
+                rt.gemm(self._tab('p1', active))
+                self.eig.enqueue(t1, warm=True)
+                rt.gemm(self._tab('core', active))
+                rt.sqnorm(self._tab('nc', active), slots[b * len(active):(b + 1) * len(active)])
+                if b < batch - 1:                        # the flags of this sweep are overwritten by the next one
+                    flags.append(self.eig.snapshot_flags(t0, t1))
+            norm_c2 = slots.cpu().numpy().reshape(batch, len(active))      # the host synchronisation
+            self.eig.check_flags(flags)
             s0, s1 = self.eig.results(t0), self.eig.results(t1)
             stop = []
             for q, li in enumerate(active):
                 jac[self.layers[li].name] += [int(s0[q]), int(s1[q])]
                 nx = math.sqrt(float(norm_x2[li]))
-                err = math.sqrt(abs(float(norm_x2[li]) - float(norm_c2[q]))) / nx if nx > 0 else 0.0
-                errs[li].append(err)
-                if (it > 1 and abs(errs[li][-2] - errs[li][-1]) < self.hooi_tol) or it == self.n_iter_max - 1:
+                for b in range(batch):
+                    errs[li].append(math.sqrt(abs(float(norm_x2[li]) - float(norm_c2[b, q]))) / nx if nx > 0 else 0.0)
+                last = it + batch - 1
+                if (last > 1 and abs(errs[li][-2] - errs[li][-1]) < self.hooi_tol) or last == self.n_iter_max - 1:
                     stop.append(li)
+            it += batch
             if stop:
                 stop = tuple(stop)
                 rt.gemm(self._tab('rec1', stop))
                 rt.gemm(self._tab('rec2', stop))
                 rt.fold_store(self._tab('fold', stop))
                 for li in stop:
-                    self.hooi_sweeps[self.layers[li].name] = it + 1
+                    self.hooi_sweeps[self.layers[li].name] = it
                 active = tuple(li for li in active if li not in stop)
-            it += 1
         ph.finish()
         self.sweeps = jac
         self.errors = {L.name: errs[i] for i, L in enumerate(self.layers)}

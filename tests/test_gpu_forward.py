@@ -224,6 +224,25 @@ def test_tklinear_forward_matches_dense(variant):
             assert _rel(a, b_) <= 3e-2, _rel(a, b_)
 
 
+def test_tklinear_head_with_odd_output_width():
+    """A 10-class head: out_features is not a multiple of 4, the fused kernel's output pitch is padded and sliced."""
+    import hp_tables
+    import TKLinear
+    g = torch.Generator(device='cpu').manual_seed(21)
+    w = torch.randn(10, 64, generator=g) * 0.1
+    b = torch.randn(10, generator=g) * 0.1
+    hp = hp_tables.HpTable('tk_head', {'fc.weight': [8, 24]})
+    layer = TKLinear.TKLinearM(64, 10, bias=True, hp_dict=hp, name='fc.weight', dense_w=w, dense_b=b).to(DEV)
+    x = torch.randn(33, 64, generator=g).to(DEV)
+    with torch.no_grad():
+        y = layer(x)
+        ref = layer._forward_torch(x) if hasattr(layer, '_forward_torch') else torch.nn.functional.linear(
+            torch.nn.functional.linear(torch.nn.functional.linear(x, layer.first_factor), layer.core_tensor), layer.last_factor,
+            layer.bias)
+    assert tuple(y.shape) == (33, 10)
+    assert _rel(y, ref) <= FWD_TOL, _rel(y, ref)
+
+
 @pytest.mark.parametrize('B,Cin,H,W,Ra,Rb,Cout,KS,stride,pad', [
     (3, 16, 32, 32, 16, 16, 16, 3, 1, 1),      # ttm_resnet32 layer1
     (2, 16, 32, 32, 16, 32, 32, 3, 2, 1),      # stride-2 transition
