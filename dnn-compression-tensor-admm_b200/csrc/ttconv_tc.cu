@@ -100,13 +100,13 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_pack_kernel(const float*
 }
 
 // Persistent, warp-specialised: a CTA fetches the weight image once and walks over chunks blockIdx.x, blockIdx.x + gridDim.x, ...
-//   warps 0-7   loaders: x of chunk i + 1 -> bf16 planes in the other X buffer while chunk i is being multiplied
-//   warp 8      tcgen05.mma issuer (stage 1 -> stage 2 -> stage 3 of a chunk, two TMEM accumulators used alternately)
-//   warps 9-12  drain: TMEM -> bf16 -> Z1 / Z2 planes, and TMEM + bias -> y (warp & 3 selects the TMEM lane quadrant)
-constexpr int kTcvLoaders = 256;
+//   warps 0-3   loaders: x of chunk i + 1 -> bf16 planes in the other X buffer while chunk i is being multiplied
+//   warp 4      tcgen05.mma issuer (stage 1 -> stage 2 -> stage 3 of a chunk, two TMEM accumulators used alternately)
+//   warps 5-8   drain: TMEM -> bf16 -> Z1 / Z2 planes, and TMEM + bias -> y (warp & 3 selects the TMEM lane quadrant)
+constexpr int kTcvLoaders = 128;
 constexpr int kTcvThreads = kTcvLoaders + 32 + 128;
 
-__global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ blob,
+__global__ void __launch_bounds__(kTcvThreads, 3) ttconv_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ blob,
                                                                   float* __restrict__ y, const __grid_constant__ TcConvDesc d) {
   extern __shared__ __align__(128) uint8_t tcv_smem_raw[];
   const uint32_t smem = (tc::smem_u32(tcv_smem_raw) + 127u) & ~127u;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
                  "r"((uint32_t)d.wbytes), "r"(wbar)
                  : "memory");
   }
-  if (warp == 8) {
+  if (warp == kTcvLoaders / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base_smem)),
                  "r"((uint32_t)(2 * d.nb))
                  : "memory");
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
   const uint32_t xbytes = (uint32_t)d.xbytes;                // one X buffer (Z2 of the same chunk aliases it)
   const long long nchunks = (d.total + (long long)d.T * 128 - 1) / ((long long)d.T * 128);
 
-  if (warp < 8) {
+  if (warp < kTcvLoaders / 32) {
     // =============================== loaders ===============================
     const int groups = d.Cinp >> 3;
     const int64_t hw = (int64_t)d.H * d.W;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(xfull0 + 8 * xb);
     }
-  } else if (warp == 8) {
+  } else if (warp == kTcvLoaders / 32) {
     // =============================== MMA issuer ===============================
     tc::mbar_wait(wbar, 0);                                             // the weight image has landed
     const uint32_t id1 = tc::umma_idesc_bf16(d.Rap), id2 = tc::umma_idesc_bf16(d.Rbp), id3 = tc::umma_idesc_bf16(d.Coutp);
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
     }
   } else {
     // =============================== drain ===============================
-    const int quad = warp & 3;                                          // warps 9..12 -> quadrants 1, 2, 3, 0
+    const int quad = warp & 3;                                          // warps 5..8 -> quadrants 1, 2, 3, 0
     const int64_t hw = (int64_t)d.H * d.W;
     tc::mbar_wait(wbar, 0);                                             // bias
     int tile_ctr = 0, it_ = 0;
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kTcvLoaders / 32) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * d.nb)) : "memory");
   }
@@ -459,7 +459,7 @@ extern "C" int tta_ttconv_tc_fwd(const float* x, const void* blob, float* y, int
   // persistent: as many CTAs as fit at once (shared memory, 512 TMEM columns, 2048 threads per SM), each walks over chunks
   int per_sm = (227 * 1024) / (d.smem + 1024);
   if (per_sm > 512 / (2 * d.nb)) per_sm = 512 / (2 * d.nb);
-  if (per_sm > 2) per_sm = 2;                      // registers: __launch_bounds__(416, 2)
+  if (per_sm > 3) per_sm = 3;                      // registers: __launch_bounds__(288, 3)
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)kNumSMs * per_sm;
   if (grid > chunks) grid = chunks;

@@ -9,14 +9,20 @@ import sys, os
 sys.path[:0] = [%r, %r]
 import torch, tta_runtime as rt
 dev = 'cuda:0'
-def t(fn, iters=30, warm=5):
-    for _ in range(warm): fn()
-    torch.cuda.synchronize()
+def t(fn, reps=20, iters=5):
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3): fn()
+    torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps): fn()
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters): fn()
+    for _ in range(iters): g.replay()
     e1.record(); e1.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3
+    return e0.elapsed_time(e1) / iters / reps * 1e3
 out = []
 for (cin, hw, ra, rb, cout) in ((16, 32, 16, 16, 16), (32, 16, 32, 32, 32), (64, 8, 64, 64, 64), (64, 56, 40, 40, 64)):
     x = torch.randn(128, cin, hw, hw, device=dev); y = torch.empty(128, cout, hw, hw, device=dev)
