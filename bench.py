@@ -647,8 +647,15 @@ def forward_bench(dev, peaks):
             for layer, x in lin:
                 layer(xs_bf[x.shape[1]])
 
+    def lin_chain_bf16():
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+            for layer, x in lin:
+                import fwd_common as fc
+                fc.tt_apply_torch(x, list(layer.tt_cores)[layer.out_tt_order:], list(layer.tt_cores)[:layer.out_tt_order])
+
     ms_f, ms_c = _time_cuda(lin_fused, iters=3, warm=1), _time_cuda(lin_chain, iters=3, warm=1)
     ms_fb = _time_cuda(lin_fused_bf16, iters=3, warm=1)
+    ms_cb = _time_cuda(lin_chain_bf16, iters=3, warm=1)
     # training step of the same layers (forward + backward with a random upstream gradient): fused path
     # (fwd_common.LowRank2Fn: forward and dX on the two-factor kernel) vs the torch op chain
     gys = {}
@@ -682,6 +689,7 @@ def forward_bench(dev, peaks):
         macs_exec += layer.in_features * layer.out_features if dense else chain
     out['deit_small_ttlinear_layers'] = {'batch': 256, 'tokens': tokens, 'fused_img_s': 256 / (ms_f / 1e3), 'fused_ms': ms_f,
                                          'torch_op_chain_img_s': 256 / (ms_c / 1e3), 'torch_op_chain_ms': ms_c,
+                                         'torch_op_chain_bf16_autocast_ms': ms_cb,
                                          'fused_bf16_activations_ms': ms_fb,
                                          'fused_bf16_activations_img_s': 256 / (ms_fb / 1e3),
                                          'train_step_fused_ms': ms_tf, 'train_step_torch_op_chain_ms': ms_tc,

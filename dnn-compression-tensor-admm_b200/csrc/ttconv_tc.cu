@@ -100,13 +100,13 @@ __global__ void __launch_bounds__(kTcThreads) ttconv_tc_pack_kernel(const float*
 }
 
 // Persistent, warp-specialised: a CTA fetches the weight image once and walks over chunks blockIdx.x, blockIdx.x + gridDim.x, ...
-//   warps 0-3   loaders: x of chunk i + 1 -> bf16 planes in the other X buffer while chunk i is being multiplied
-//   warp 4      tcgen05.mma issuer (stage 1 -> stage 2 -> stage 3 of a chunk, two TMEM accumulators used alternately)
-//   warps 5-8   drain: TMEM -> bf16 -> Z1 / Z2 planes, and TMEM + bias -> y (warp & 3 selects the TMEM lane quadrant)
-constexpr int kTcvLoaders = 128;
+//   warps 0-7   loaders: x of chunk i + 1 -> bf16 planes in the other X buffer while chunk i is being multiplied
+//   warp 8      tcgen05.mma issuer (stage 1 -> stage 2 -> stage 3 of a chunk, two TMEM accumulators used alternately)
+//   warps 9-12  drain: TMEM -> bf16 -> Z1 / Z2 planes, and TMEM + bias -> y (warp & 3 selects the TMEM lane quadrant)
+constexpr int kTcvLoaders = 256;
 constexpr int kTcvThreads = kTcvLoaders + 32 + 128;
 
-__global__ void __launch_bounds__(kTcvThreads, 3) ttconv_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ blob,
+__global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ blob,
                                                                   float* __restrict__ y, const __grid_constant__ TcConvDesc d) {
   extern __shared__ __align__(128) uint8_t tcv_smem_raw[];
   const uint32_t smem = (tc::smem_u32(tcv_smem_raw) + 127u) & ~127u;
@@ -163,38 +163,40 @@ __global__ void __launch_bounds__(kTcvThreads, 3) ttconv_tc_kernel(const float* 
       if (it_ >= 2) tc::mbar_wait(xempty0 + 8 * xb, (uint32_t)(((it_ >> 1) - 1) & 1));
       const uint32_t xs = smem + d.o_x + (uint32_t)xb * xbytes;
       const int e0 = (int)(ch * d.T * 128) - d.halo;           // position of row 0 of the planes
-      // four (position, channel group) items per thread in flight: 32 independent loads before the first conversion
-      for (int it0 = tid; it0 < groups * PE; it0 += 4 * kTcvLoaders) {
-        float v[4][8];
+      // a thread owns two rows (positions) per pass: the position is decoded once, then every channel group of both rows
+      // is fetched with 16 independent loads in flight before the first conversion
+      const bool full8 = (d.Cin & 7) == 0;
+      for (int r0 = tid; r0 < PE; r0 += 2 * kTcvLoaders) {
+        const float* src[2];
+        int rowi[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
-          const int it = it0 + u * kTcvLoaders;
-          if (it < groups * PE) {
-            const int row = it % PE, kg = it / PE;
-            const int g = e0 + row;
-            if (g >= 0 && g < (int)d.total) {
-              const int b = g / d.Gp;
-              const int rem = g - b * d.Gp;
-              const int py = rem / d.Wp, px = rem - py * d.Wp;
-              if (py >= 1 && py <= d.H && px >= 1 && px <= d.W) {
-                const float* p = x + ((int64_t)b * d.Cin + kg * 8) * hw + (int64_t)(py - 1) * d.W + (px - 1);
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (kg * 8 + e < d.Cin) v[u][e] = __ldg(p + e * hw);
-              }
-            }
+        for (int u = 0; u < 2; ++u) {
+          const int row = r0 + u * kTcvLoaders;
+          rowi[u] = row;
+          src[u] = nullptr;
+          const int g = e0 + row;
+          if (row < PE && g >= 0 && g < (int)d.total) {
+            const int b = g / d.Gp;
+            const int rem = g - b * d.Gp;
+            const int py = rem / d.Wp, px = rem - py * d.Wp;
+            if (py >= 1 && py <= d.H && px >= 1 && px <= d.W)
+              src[u] = x + (int64_t)b * d.Cin * hw + (int64_t)(py - 1) * d.W + (px - 1);
           }
         }
+        for (int kg = 0; kg < groups; ++kg) {
+          float v[2][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int it = it0 + u * kTcvLoaders;
-          if (it < groups * PE) {
-            const int row = it % PE, kg = it / PE;
-            tc::sts128(xs + (uint32_t)kg * plx + (uint32_t)row * 16u, tcv_pack(v[u][0], v[u][1]), tcv_pack(v[u][2], v[u][3]),
-                       tcv_pack(v[u][4], v[u][5]), tcv_pack(v[u][6], v[u][7]));
+          for (int u = 0; u < 2; ++u) {
+            const float* p = src[u] + (int64_t)kg * 8 * hw;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[u][e] = (src[u] != nullptr && (full8 || kg * 8 + e < d.Cin)) ? __ldg(p + e * hw) : 0.f;
           }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (rowi[u] < PE)
+              tc::sts128(xs + (uint32_t)kg * plx + (uint32_t)rowi[u] * 16u, tcv_pack(v[u][0], v[u][1]), tcv_pack(v[u][2], v[u][3]),
+                         tcv_pack(v[u][4], v[u][5]), tcv_pack(v[u][6], v[u][7]));
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kTcvThreads, 3) ttconv_tc_kernel(const float* 
     }
   } else {
     // =============================== drain ===============================
-    const int quad = warp & 3;                                          // warps 5..8 -> quadrants 1, 2, 3, 0
+    const int quad = warp & 3;                                          // warps 9..12 -> quadrants 1, 2, 3, 0
     const int64_t hw = (int64_t)d.H * d.W;
     tc::mbar_wait(wbar, 0);                                             // bias
     int tile_ctr = 0, it_ = 0;
@@ -459,7 +461,7 @@ extern "C" int tta_ttconv_tc_fwd(const float* x, const void* blob, float* y, int
   // persistent: as many CTAs as fit at once (shared memory, 512 TMEM columns, 2048 threads per SM), each walks over chunks
   int per_sm = (227 * 1024) / (d.smem + 1024);
   if (per_sm > 512 / (2 * d.nb)) per_sm = 512 / (2 * d.nb);
-  if (per_sm > 3) per_sm = 3;                      // registers: __launch_bounds__(288, 3)
+  if (per_sm > 2) per_sm = 2;                      // registers: __launch_bounds__(416, 2)
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)kNumSMs * per_sm;
   if (grid > chunks) grid = chunks;
