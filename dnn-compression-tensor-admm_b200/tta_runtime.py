@@ -163,6 +163,11 @@ def _load():
                         'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_gram_enable_tc',
                         'tta_ttconv_tc_blob_bytes'):
             getattr(lib, name).restype = ci
+    # measurement switches: the production defaults are the tensor-core paths
+    if os.environ.get('TTA_GRAM_TC') is not None:
+        lib.tta_gram_enable_tc(int(os.environ['TTA_GRAM_TC']))
+    if os.environ.get('TTA_GEMM_TC') is not None:
+        lib.tta_gemm_enable_tc(int(os.environ['TTA_GEMM_TC']))
     _LIB = lib
     return lib
 
