@@ -21,6 +21,9 @@ per-layer FLOP model and the projected Z tensors are exchanged with one all-gath
 from __future__ import annotations
 
 import numpy as np
+import os
+import time
+
 import torch
 
 import projector
@@ -61,6 +64,15 @@ class _PenaltyFn(torch.autograd.Function):
             grads.append(flat[off:off + p.numel()].view(p.shape))
             off += p.numel()
         return (grad_out, None) + tuple(grads)
+
+
+def _priority_range():
+    """(lowest, highest) stream priority of the device; numerically the highest priority is the smallest number."""
+    try:
+        lo, hi = torch.cuda.Stream.priority_range()
+        return int(lo), int(hi)
+    except Exception:
+        return 0, -1
 
 
 class ADMM:
@@ -231,11 +243,18 @@ class ADMM:
         if len(async_plans) > 1 and not rt.backend_is_emulated() and all(pl.profile is None for pl, _ in async_plans):
             dev = self._state_device()
             if self._streams is None or len(self._streams) != len(async_plans):
-                self._streams = [torch.cuda.Stream(device=dev, priority=-1 if i < 2 else 0)
+                # descending priorities in the order of the groups (most critical first): when SMs free up, the block
+                # scheduler serves the pending CTAs of the critical chain before those of the shorter chains
+                lo, hi = _priority_range()
+                prios = os.environ.get('TTA_GROUP_PRIOS')
+                prios = [int(v) for v in prios.split(',')] if prios else list(range(hi, lo + 1))
+                self._streams = [torch.cuda.Stream(device=dev, priority=max(hi, min(lo, prios[min(i, len(prios) - 1)])))
                                  for i in range(len(async_plans))]
             main = torch.cuda.current_stream(dev)
             fork = torch.cuda.Event()
             fork.record(main)
+            t_host = time.perf_counter()
+            self.enqueue_ms_per_group = []
             for (plan, names), st in zip(async_plans, self._streams):
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
@@ -249,6 +268,7 @@ class ADMM:
                     done = torch.cuda.Event()
                     done.record(st)
                 main.wait_event(done)
+                self.enqueue_ms_per_group.append((time.perf_counter() - t_host) * 1e3)     # diagnostics: host time so far
             for plan, names in self._plans:
                 if hasattr(plan, 'enqueue'):
                     plan.collect()

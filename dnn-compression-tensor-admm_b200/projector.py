@@ -335,6 +335,7 @@ class TTProjectionPlan:
         # whose trd solve reports inseparable eigenvalues (exactly repeated singular values) switches to 'jacobi'.
         self.solver = default_solver() if refine else 'jacobi'
         self.gram_in_place = os.environ.get('TTA_GRAM_IN_PLACE', '1') != '0'
+        self._flags_ev = self._flags_host = self._flags_dev = None
         self._last = None
         self._warm_valid = False
         self._warm_used = False      # the update being collected was warm-started
@@ -642,8 +643,33 @@ class TTProjectionPlan:
         ph.mark('fold')
         if self.t_fold.n:
             rt.fold_store(self.t_fold)
+        self._enqueue_flag_readback()
         mark('end')
         ph.finish()
+
+    def _flag_parts(self):
+        parts = []
+        for w in self.waves:
+            if w['eig'].n or w['symeig'].n:
+                parts.append(w['scratch'][:6 * w['eig'].n])
+                parts.append(w['status'][:w['symeig'].n])
+        return parts
+
+    def _enqueue_flag_readback(self):
+        """Sweep counts / status words of every wave -> pinned host memory, on the plan's stream right behind its last
+        kernel: collect() then only waits for an event instead of issuing a cat + D2H copy per plan after the join."""
+        parts = self._flag_parts()
+        if not parts or rt.backend_is_emulated():
+            self._flags_ev = None
+            return
+        n = sum(int(p.numel()) for p in parts)
+        if self._flags_host is None or self._flags_host.numel() != n:
+            self._flags_dev = torch.empty(n, dtype=torch.int32, device=self.device)
+            self._flags_host = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        torch.cat(parts, out=self._flags_dev)
+        self._flags_host.copy_(self._flags_dev, non_blocking=True)
+        self._flags_ev = torch.cuda.Event()
+        self._flags_ev.record()
 
     def collect(self):
         """The one host synchronisation of an update: sweep counts / convergence status of every wave."""
@@ -651,11 +677,12 @@ class TTProjectionPlan:
         live = [w for w in self.waves if w['eig'].n or w['symeig'].n]
         if not live:
             return
-        parts = []
-        for w in live:
-            parts.append(w['scratch'][:6 * w['eig'].n])
-            parts.append(w['status'][:w['symeig'].n])
-        flat = torch.cat(parts).cpu().numpy()     # one D2H copy per plan
+        if self._flags_ev is not None:
+            self._flags_ev.synchronize()              # the copy was enqueued behind the last kernel of the plan
+            flat = self._flags_host.numpy()
+            self._flags_ev = None
+        else:
+            flat = torch.cat(self._flag_parts()).cpu().numpy()     # one D2H copy per plan
         off = 0
         flagged = False
         for wi, wave in enumerate(self.waves):
