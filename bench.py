@@ -588,9 +588,9 @@ def forward_bench(dev, peaks):
                                      'fused_fp32_cuda_core_kernel_ms': ms_cc,
                                      'torch_op_chain_img_s': 128 / (ms_c / 1e3), 'torch_op_chain_ms': ms_c,
                                      'torch_op_chain_bf16_autocast_ms': ms_cb,
-                                     'kernel': 'ttconv_tc_kernel (bf16 tcgen05, csrc/ttconv_tc.cu) for the {} stride-1 layers, '
-                                               'ttconv_fused_kernel (fp32 CUDA cores) for the {} stride-2 layers'
-                                               .format(n_tc, len(layers) - n_tc),
+                                     'kernel': 'ttconv_tc_kernel (bf16 tcgen05, csrc/ttconv_tc.cu) for all {} layers ({} of them '
+                                               'stride 2: stride-1 result at every position, odd positions dropped)'
+                                               .format(len(layers), len(layers) - n_tc),
                                      'roofline': {'bound': 'hbm', 'algorithmic_bytes': act_bytes,
                                                   'achieved': act_bytes / (best / 1e3) / 1e9, 'peak': peaks['hbm_gbs'],
                                                   'unit': 'GB/s', 'frac': act_bytes / (best / 1e3) / 1e9 / peaks['hbm_gbs'],

@@ -1,5 +1,5 @@
 // Fused forward of the factorised 3x3 convolutions on the 5th-generation tensor cores (bf16 tcgen05, fp32 TMEM
-// accumulators):  1x1 (C_in -> r_a)  ->  3x3 (r_a -> r_b, stride 1, zero padding 1)  ->  1x1 (r_b -> C_out) + bias,
+// accumulators):  1x1 (C_in -> r_a)  ->  3x3 (r_a -> r_b, stride 1 or 2, zero padding 1)  ->  1x1 (r_b -> C_out) + bias,
 // ONE kernel, both intermediates stay in shared memory as bf16.
 //
 // This is the contraction of TTConv2dM.forward (TTConv.py:130-153: in-core chain, F.conv2d with core_kernel, out-core
@@ -30,6 +30,7 @@ constexpr int kTcThreads = 256;      // pack kernel
 
 struct TcConvDesc {
   int B, Cin, H, W, Ra, Rb, Cout;
+  int stride, Ho, Wo;             // stride 2: the stride-1 result is formed at every position, the odd ones are dropped
   int Cinp, Rap, Rbp, Coutp;      // padded to multiples of 16 (MMA K step / N granularity)
   int Wp, Gp, halo;               // padded row, padded grid size, Wp + 1
   int T, TE;                      // output tiles per chunk, stage-1 tiles per chunk (chunk + both halos)
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
   } else {
     // =============================== drain ===============================
     const int quad = warp & 3;                                          // warps 9..12 -> quadrants 1, 2, 3, 0
-    const int64_t hw = (int64_t)d.H * d.W;
+    const int64_t hw = (int64_t)d.Ho * d.Wo;                            // output plane
     tc::mbar_wait(wbar, 0);                                             // bias
     int tile_ctr = 0, it_ = 0;
     auto pack_rows = [&](uint32_t dst_plane0, uint32_t plane_bytes, int row, int ngroups16, int buf) {
@@ -327,7 +328,13 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
           const int rem = g - b * d.Gp;
           const int py = rem / d.Wp, px = rem - py * d.Wp;
           valid = py >= 1 && py <= d.H && px >= 1 && px <= d.W;
-          yp = y + (int64_t)b * d.Cout * hw + (int64_t)(py - 1) * d.W + (px - 1);
+          int oy = py - 1, ox = px - 1;
+          if (d.stride == 2) {
+            valid = valid && !(oy & 1) && !(ox & 1);
+            oy >>= 1;
+            ox >>= 1;
+          }
+          yp = y + (int64_t)b * d.Cout * hw + (int64_t)oy * d.Wo + ox;
         }
         for (int cg = 0; cg < (d.Coutp >> 4); ++cg) {
           uint32_t v[16];
@@ -357,9 +364,9 @@ __global__ void __launch_bounds__(kTcvThreads, 2) ttconv_tc_kernel(const float* 
 
 static int tcv_round16(int v) { return (v + 15) & ~15; }
 
-// geometry this kernel serves: 3x3, stride 1, padding 1, channel counts and ranks <= 64
+// geometry this kernel serves: 3x3, stride 1 or 2, padding 1, channel counts and ranks <= 64
 bool ttconv_tc_supported(int Cin, int Ra, int Rb, int Cout, int KS, int stride, int pad) {
-  return KS == 3 && stride == 1 && pad == 1 && Cin <= 64 && Ra <= 64 && Rb <= 64 && Cout <= 64;
+  return KS == 3 && (stride == 1 || stride == 2) && pad == 1 && Cin <= 64 && Ra <= 64 && Rb <= 64 && Cout <= 64;
 }
 
 static void tcv_layout(TcConvDesc& d, int T) {
@@ -382,7 +389,10 @@ static void tcv_layout(TcConvDesc& d, int T) {
 }  // namespace tta
 
 namespace tta {
-static int tcv_prepare(TcConvDesc& d, int B, int Cin, int H, int W, int Ra, int Rb, int Cout) {
+static int tcv_prepare(TcConvDesc& d, int B, int Cin, int H, int W, int Ra, int Rb, int Cout, int stride = 1) {
+  d.stride = stride;
+  d.Ho = (H + 2 - 3) / stride + 1;
+  d.Wo = (W + 2 - 3) / stride + 1;
   d.B = B; d.Cin = Cin; d.H = H; d.W = W; d.Ra = Ra; d.Rb = Rb; d.Cout = Cout;
   d.Cinp = tcv_round16(Cin); d.Rap = tcv_round16(Ra); d.Rbp = tcv_round16(Rb); d.Coutp = tcv_round16(Cout);
   d.Wp = W + 2;
@@ -442,7 +452,7 @@ extern "C" int tta_ttconv_tc_fwd(const float* x, const void* blob, float* y, int
     return TTA_E_INVALID;
   }
   TcConvDesc d;
-  if (tcv_prepare(d, B, Cin, H, W, Ra, Rb, Cout) != TTA_OK) {
+  if (tcv_prepare(d, B, Cin, H, W, Ra, Rb, Cout, stride) != TTA_OK) {
     set_error("ttconv_tc: working set %d B does not fit shared memory", d.smem);
     return TTA_E_INVALID;
   }

@@ -368,7 +368,9 @@ int tta_ttconv_fused_fwd(const float* x, const float* a_in, const float* kern, c
 /* Same contraction on the tensor cores (bf16 tcgen05.mma, fp32 TMEM accumulators, both intermediates in shared memory
  * as bf16; csrc/ttconv_tc.cu): pixel-major implicit GEMM over the zero-padded position space, the nine taps of the
  * 3 x 3 stage are row-shifted views of the stage-1 result (un-swizzled K-major operands: a shift is a descriptor start
- * address).  Serves k = 3, stride 1, pad 1, channel counts and ranks <= 64 (tta_ttconv_tc_supported); other geometries
+ * address).  Serves k = 3, stride 1 or 2 (the stride-1 result is formed at every position and the odd ones are dropped:
+ * the three contractions are cheap next to the activation traffic), pad 1, channel counts and ranks <= 64
+ * (tta_ttconv_tc_supported); other geometries
  * return TTA_E_INVALID -- the callers fall back to tta_ttconv_fused_fwd.  The weights are packed once per weight change
  * into the shared-memory image of the kernel (tta_ttconv_tc_pack: bf16 planes of a_in, the nine taps of kern, a_out,
  * fp32 bias; tta_ttconv_tc_blob_bytes bytes) and fetched by every CTA with one bulk copy.  Output within 1e-2 relative

@@ -31,3 +31,11 @@ for _ in range(n):
     ts.append(a.elapsed_time(b))
 print('chain-only update ms:', ' '.join('{:.2f}'.format(t) for t in ts))
 print('jacobi sweeps per TT step:', {n: v for n, v in admm.sweeps.items()})
+# timeline of one more update (CUDA events recorded by the plan, ms after the start)
+plan = admm._plans[0][0]
+plan.trace = []
+t0 = torch.cuda.Event(enable_timing=True)
+t0.record()
+admm.update()
+torch.cuda.synchronize()
+print('timeline:', ' '.join('{}@{:.2f}'.format(lbl, t0.elapsed_time(ev)) for lbl, ev in plan.trace))

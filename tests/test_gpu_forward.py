@@ -274,6 +274,29 @@ def test_ttconv_fused_kernel_matches_conv_chain(B, Cin, H, W, Ra, Rb, Cout, KS, 
 
 
 @pytest.mark.parametrize('B,Cin,H,W,Ra,Rb,Cout', [
+    (3, 16, 32, 32, 16, 32, 32),       # ttm_resnet32 stride-2 transition
+    (2, 32, 16, 16, 29, 31, 64),
+    (2, 9, 13, 10, 5, 6, 11),          # odd sizes
+])
+def test_ttconv_tensor_core_kernel_stride2(B, Cin, H, W, Ra, Rb, Cout):
+    import torch.nn.functional as F
+    assert rt.ttconv_tc_supported(Cin, Ra, Rb, Cout, 3, 2, 1)
+    g = torch.Generator(device='cpu').manual_seed(B * 7 + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+    a_in = (torch.randn(Ra, Cin, generator=g) / Cin ** 0.5).to(DEV)
+    kern = (torch.randn(Rb, Ra, 3, 3, generator=g) / (Ra * 9) ** 0.5).to(DEV)
+    a_out = (torch.randn(Cout, Rb, generator=g) / Rb ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    ref = F.conv2d(F.conv2d(F.conv2d(x.double(), a_in.double()[:, :, None, None]), kern.double(), None, 2, 1),
+                   a_out.double()[:, :, None, None], bias.double())
+    y = torch.full(tuple(ref.shape), float('nan'), device=DEV)
+    rt.ttconv_tc_fwd(x, rt.ttconv_tc_pack(a_in, kern, a_out, bias), y, B, Cin, H, W, Ra, Rb, Cout, 3, 2, 1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert _rel(y, ref) <= 1e-2, _rel(y, ref)
+
+
+@pytest.mark.parametrize('B,Cin,H,W,Ra,Rb,Cout', [
     (3, 16, 32, 32, 16, 16, 16),       # ttm_resnet32 layer1
     (5, 32, 16, 16, 20, 24, 32),       # layer2, ranks not multiples of 16
     (4, 64, 8, 8, 27, 29, 64),         # layer3 ranks
@@ -287,7 +310,7 @@ def test_ttconv_tensor_core_kernel_matches_conv_chain(B, Cin, H, W, Ra, Rb, Cout
     in fp64, within the 1e-2 bar of the decomposed-layer forwards (three bf16 roundings: ~4e-3)."""
     import torch.nn.functional as F
     assert rt.ttconv_tc_supported(Cin, Ra, Rb, Cout, 3, 1, 1)
-    assert not rt.ttconv_tc_supported(Cin, Ra, Rb, Cout, 3, 2, 1) and not rt.ttconv_tc_supported(128, Ra, Rb, Cout, 3, 1, 1)
+    assert not rt.ttconv_tc_supported(Cin, Ra, Rb, Cout, 3, 1, 0) and not rt.ttconv_tc_supported(128, Ra, Rb, Cout, 3, 1, 1)
     g = torch.Generator(device='cpu').manual_seed(B * 131 + Cin * 17 + H)
     x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
     a_in = (torch.randn(Ra, Cin, generator=g) / Cin ** 0.5).to(DEV)
