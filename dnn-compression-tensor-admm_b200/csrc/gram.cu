@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_partial_big(const tta_gr
 
 // G = sum over slices of the partial tiles (fp64, fixed order), mirrored; stored as the eigensolver's column state
 // x[col*ld + row] (fp32, zero padded to ld x kpad) and / or as the k x k fp64 matrix g64.
-// Eight lanes share one element of the lower triangle (i >= j, consecutive lanes groups take consecutive j: the
-// partial rows are read contiguously) and split the slices between them; both partial kernels store the tiles that
+// One or eight lanes per element of the lower triangle (i >= j, consecutive lanes / lane groups take consecutive j: the
+// partial rows are read contiguously); eight lanes split the slices between them; both partial kernels store the tiles that
 // hold the lower triangle, and the tensor-core tiles on the diagonal are not bitwise symmetric (lo*hi and hi*lo swap
 // roles across the diagonal), so the lower triangle is the one that is taken.
 __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restrict__ tasks,
@@ -291,11 +291,16 @@ __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restri
   const tta_gram_task tk = tasks[blockIdx.y];
   const bool tcp = flags.tc[blockIdx.y] != 0;
   const int64_t kk2 = (int64_t)tk.k * tk.k;
-  const int sub = threadIdx.x & 7;
+  // lanes per element: 8 when there are many slices to add up (k <= 32 problems with reductions of 73 728: 144 slices),
+  // 1 otherwise (consecutive threads then read consecutive elements of a slice: coalesced)
+  const int lpe = tk.nsplit >= 24 ? 8 : 1;
+  const int lsh = lpe == 8 ? 3 : 0;
+  const int sub = threadIdx.x & (lpe - 1);
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int grp = (threadIdx.x & 31) >> 3;
-  for (int64_t e0 = (gtid >> 5) * 4; e0 < kk2; e0 += nthr >> 3) {       // warp-uniform trip count (full-mask shuffles)
+  const int grp = (threadIdx.x & 31) >> lsh;
+  const int per_warp = 32 >> lsh;
+  for (int64_t e0 = (gtid >> 5) * per_warp; e0 < kk2; e0 += nthr >> lsh) {       // warp-uniform trip count (full-mask shuffles)
     const int64_t e = e0 + grp;
     const int i = (int)(e / tk.k);
     const int j = (int)(e - (int64_t)i * tk.k);
@@ -304,15 +309,17 @@ __global__ void __launch_bounds__(256) gram_finish(const tta_gram_task* __restri
     if (lower) {
       if (tcp) {
         const float* p = reinterpret_cast<const float*>(tk.part) + e;
-        for (int sidx = sub; sidx < tk.nsplit; sidx += 8) s += (double)p[(int64_t)sidx * kk2];
+        for (int sidx = sub; sidx < tk.nsplit; sidx += lpe) s += (double)p[(int64_t)sidx * kk2];
       } else {
         const double* p = tk.part + e;
-        for (int sidx = sub; sidx < tk.nsplit; sidx += 8) s += p[(int64_t)sidx * kk2];
+        for (int sidx = sub; sidx < tk.nsplit; sidx += lpe) s += p[(int64_t)sidx * kk2];
       }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (lpe == 8) {
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+    }
     if (lower && sub == 0) {
       if (tk.g64) {
         tk.g64[(int64_t)i * tk.k + j] = s;
@@ -362,7 +369,7 @@ extern "C" int tta_gram_batched(const tta_gram_task* tasks_dev, const tta_gram_t
                   tk.nc, tk.nsplit, tk.ld, tk.kpad);
         return TTA_E_INVALID;
       }
-      const int64_t el = (int64_t)tk.k * tk.k * 8;     // eight lanes per element (gram_finish)
+      const int64_t el = (int64_t)tk.k * tk.k * (tk.nsplit >= 24 ? 8 : 1);     // lanes per element (gram_finish)
       max_elems = el > max_elems ? el : max_elems;
     }
     // tensor-core route: TMA-addressable tasks are computed by gram_tc_kernel (fp32 partials)
