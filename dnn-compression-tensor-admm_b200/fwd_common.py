@@ -346,6 +346,18 @@ def _mm_f32(a, b):
         return (a @ b).float()
 
 
+def _grad_tn(a, b, M, N, K, lda, ldb):
+    """a^T b (fp32) for a (K x lda), b (K x ldb) bf16: own tcgen05 kernel (csrc/gemm_tn.cu); TTA_GRAD_MM=torch keeps the
+    round-1 torch.mm path (cuBLAS) for comparison."""
+    if _GRAD_TORCH or rt.backend_is_emulated():
+        return _mm_f32(a[:, :M].t(), b[:, :N])
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    return rt.gemm_bf16_tn(a, b, out, M, N, K, lda=lda, ldb=ldb, ldc=N)
+
+
+_GRAD_TORCH = os.environ.get('TTA_GRAD_MM', '') == 'torch'
+
+
 class LowRank2Fn(torch.autograd.Function):
     """Training path of the two-factor layers (backward of the fused forwards):
     y = (x W1^T) W2^T + bias with the forward AND the input gradient on the fused TMA + tcgen05 kernel.
@@ -395,10 +407,10 @@ class LowRank2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             v = torch.zeros(R, n1p, dtype=torch.bfloat16, device=dev)
             rt.gemm_bf16_tc(xb, w1b, v, R, N1, K1, lda=K1, ldb=ld1, ldc=n1p)          # V = x W1^T
-            dw2 = _mm_f32(dyb.t(), v[:, :N1]).to(w2dt)
+            dw2 = _grad_tn(dyb, v, N2, N1, R, N2, n1p).to(w2dt)                       # dW2 = dY^T V
             dv = torch.zeros(R, n1p, dtype=torch.bfloat16, device=dev)
             rt.gemm_bf16_tc(dyb, w2t, dv, R, N1, N2, lda=N2, ldb=N2, ldc=n1p)         # dV = dY W2
-            dw1 = _mm_f32(dv[:, :N1].t(), xb).to(w1dt)
+            dw1 = _grad_tn(dv, xb, N1, K1, R, n1p, K1).to(w1dt)                       # dW1 = dV^T X
         db = dy.sum(0).to(bdt) if has_bias and ctx.needs_input_grad[3] else None
         return dx, dw1, dw2, db
 

@@ -63,7 +63,7 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_jacobi_scratch_bytes', 'tta_jacobi_read_results', 'tta_select_batched', 'tta_gemm_batched', 'tta_sqnorm_batched',
            'tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
-           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd', 'tta_ttconv_tc_fwd', 'tta_ttconv_tc_supported', 'tta_ttconv_tc_pack', 'tta_ttconv_tc_blob_bytes',
+           'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd', 'tta_ttconv_tc_fwd', 'tta_ttconv_tc_supported', 'tta_ttconv_tc_pack', 'tta_ttconv_tc_blob_bytes', 'tta_gemm_bf16_tn', 'tta_gemm_bf16_tn_workspace_bytes',
            'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k',
            'tta_symeig_profile_enable', 'tta_symeig_profile_read', 'tta_orth_penalty_fwd_batched',
            'tta_orth_penalty_bwd_batched']
@@ -155,13 +155,16 @@ def _load():
     lib.tta_ttconv_tc_pack.argtypes = [vp] * 5 + [ci] * 4 + [vp]
     lib.tta_ttconv_tc_blob_bytes.argtypes = [ci] * 4
     lib.tta_ttconv_tc_blob_bytes.restype = ctypes.c_int64
+    lib.tta_gemm_bf16_tn_workspace_bytes.argtypes = [ci] * 3
+    lib.tta_gemm_bf16_tn_workspace_bytes.restype = ctypes.c_int64
+    lib.tta_gemm_bf16_tn.argtypes = [vp, i64, vp, i64, vp, i64, ci, ci, ci, vp, i64, vp]
     lib.tta_lowrank2_fwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, ci, i64, ci, ci, ci, vp]
     for name in EXPORTS:
         if name not in ('tta_last_error', 'tta_jacobi_scratch_bytes', 'tta_launch_count', 'tta_symeig_work_doubles',
                         'tta_symeig_profile_enable', 'tta_symeig_profile_read',
                         'tta_jacobi_profile_enable', 'tta_jacobi_profile_read', 'tta_jacobi_force_multilaunch',
                         'tta_jacobi_enable_gra', 'tta_jacobi_set_stop_rel', 'tta_gemm_enable_tc', 'tta_gram_enable_tc',
-                        'tta_ttconv_tc_blob_bytes'):
+                        'tta_ttconv_tc_blob_bytes', 'tta_gemm_bf16_tn_workspace_bytes'):
             getattr(lib, name).restype = ci
     # measurement switches: the production defaults are the tensor-core paths
     if os.environ.get('TTA_GRAM_TC') is not None:
@@ -426,6 +429,22 @@ def ttconv_tc_supported(Cin, Ra, Rb, Cout, KS, stride, pad):
     if _FAKE is not None:
         return False
     return bool(lib().tta_ttconv_tc_supported(int(Cin), int(Ra), int(Rb), int(Cout), int(KS), int(stride), int(pad)))
+
+
+_TN_WS = {}
+
+
+def gemm_bf16_tn(a, b, out, M, N, K, lda=None, ldb=None, ldc=None):
+    """out[M, N] (fp32) = a^T b with a (K x M), b (K x N) bf16 row-major: the weight-gradient products of the fused
+    training path on the tcgen05 kernel of csrc/gemm_tn.cu (TMA boxes as MN-major operands, split-K)."""
+    need = int(lib().tta_gemm_bf16_tn_workspace_bytes(int(M), int(N), int(K)))
+    ws = _TN_WS.get(a.device)
+    if ws is None or ws.numel() < need:
+        ws = _TN_WS[a.device] = torch.empty(need, dtype=torch.uint8, device=a.device)
+    _check(lib().tta_gemm_bf16_tn(_p(a), lda if lda is not None else M, _p(b), ldb if ldb is not None else N, _p(out),
+                                  ldc if ldc is not None else N, int(M), int(N), int(K), _p(ws), ws.numel(), stream_handle()),
+           'tta_gemm_bf16_tn')
+    return out
 
 
 def ttconv_tc_pack(a_in, kern, a_out, bias):

@@ -398,6 +398,17 @@ int tta_lowrank2_fwd(const void* x, int64_t ldx, const void* w1, int64_t ld1, co
                      const float* bias, void* y, int64_t ldy, int out_fp32, int64_t M, int K1, int N1, int N2,
                      void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Weight-gradient GEMM of the fused training path (fwd_common.LowRank2Fn.backward; replaces torch.mm / cuBLAS):
+ *     c[M, N] (fp32, row pitch ldc) = a^T b,   a (K x M) and b (K x N) bf16 row-major (pitches lda, ldb: multiples of 8,
+ *     16-byte aligned bases) -- the reduction index K (tokens) is the slow index of both operands.
+ * TMA boxes land as MN-major SWIZZLE_128B operands of tcgen05.mma (no transposition), split-K over CTAs, partial
+ * tiles in `workspace` (tta_gemm_bf16_tn_workspace_bytes), summed in a fixed order.
+ * ------------------------------------------------------------------------------------------- */
+int64_t tta_gemm_bf16_tn_workspace_bytes(int M, int N, int K);
+int tta_gemm_bf16_tn(const void* a, int64_t lda, const void* b, int64_t ldb, float* c, int64_t ldc, int M, int N, int K,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

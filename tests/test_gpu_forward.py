@@ -363,6 +363,25 @@ def test_lowrank2_fused_forward_matches_torch(M, K1, N1, N2, out_f32):
     assert float((y[:, n2p:].float() - 7.0).abs().max()) == 0.0      # nothing written past the granule that holds N2
 
 
+@pytest.mark.parametrize('M,N,K,lda,ldb', [(128, 128, 64, 128, 128), (1152, 256, 50432, 1152, 256), (256, 384, 3000, 256, 384),
+                                           (40, 72, 777, 48, 72), (320, 1536, 4097, 320, 1536), (129, 65, 130, 136, 72)])
+def test_gemm_bf16_tn_weight_gradient_kernel(M, N, K, lda, ldb):
+    """tta_gemm_bf16_tn: c = a^T b with the reduction index slow in both operands (TMA boxes as MN-major tcgen05 operands,
+    split-K) against torch in fp64; bf16 inputs, fp32 accumulation -> 1e-5 grade of the fp32 result."""
+    g = torch.Generator(device='cpu').manual_seed(M + N + K)
+    a = torch.randn(K, lda, generator=g).to(torch.bfloat16).to(DEV)
+    b = torch.randn(K, ldb, generator=g).to(torch.bfloat16).to(DEV)
+    out = torch.full((M, N), float('nan'), device=DEV)
+    rt.gemm_bf16_tn(a, b, out, M, N, K, lda=lda, ldb=ldb, ldc=N)
+    torch.cuda.synchronize()
+    ref = a[:, :M].double().t() @ b[:, :N].double()
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) <= 2e-5, _rel(out, ref)
+    out2 = torch.empty_like(out)
+    rt.gemm_bf16_tn(a, b, out2, M, N, K, lda=lda, ldb=ldb, ldc=N)
+    assert torch.equal(out, out2)                      # fixed summation order: bit-reproducible
+
+
 def test_lowrank2_rejects_bad_arguments():
     x = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
     w1 = torch.zeros(400, 64, device=DEV, dtype=torch.bfloat16)
