@@ -10,8 +10,10 @@
 // The output is small (M, N <= 1536) and the reduction long: split-K over CTAs, fp32 partial tiles in a workspace,
 // summed in a fixed order by a second kernel (deterministic).
 //   warp 0     TMA producer (one elected lane): four boxes per 64-row k-block, 4-stage ring, mbarrier expect_tx.
-//   warp 1     TMEM allocator (128 columns) + tcgen05.mma issuer (kind::f16, bf16 operands, fp32 accumulation).
+//   warp 1     TMEM allocator (256 columns) + tcgen05.mma issuer (kind::f16, bf16 operands, fp32 accumulation).
 //   warps 2-5  epilogue: tcgen05.ld -> partial tile.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace tta {
@@ -22,13 +24,14 @@ using namespace tta::tc;
 constexpr int kThreads = 192;
 constexpr int kStages = 4;
 constexpr int kBoxBytes = 64 * 128;            // 64 reduction rows x 128 bytes
-constexpr int kStageBytes = 4 * kBoxBytes;     // A: two 64-column boxes, B: two
-constexpr int kSmem = kStages * kStageBytes + 1024;
+constexpr int kMaxStageBytes = 6 * kBoxBytes;  // A: two 64-column boxes, B: two (BN = 128) or four (BN = 256)
+constexpr int kSmem = kStages * kMaxStageBytes + 1024;
 
 struct Params {
   int M, N, K;
   int nsplit, kb_per_split, nkb;
   int tiles_m, tiles_n;
+  int bn;         // tile width: 128 or 256 (each CTA re-reads its A and B rows from L2: wider tiles, less traffic)
   float* ws;      // partials [nsplit][M][N]
 };
 
@@ -59,7 +62,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   item /= p.tiles_n;
   const int tm = item % p.tiles_m;
   const int split = item / p.tiles_m;
-  const int m0 = tm * 128, n0 = tn * 128;
+  const int m0 = tm * 128, n0 = tn * p.bn;
+  const int nbb = p.bn >> 6;                                  // B boxes per stage
+  const uint32_t stage_bytes = (uint32_t)(2 + nbb) * kBoxBytes;
   const int kb0 = split * p.kb_per_split;
   int kb1 = kb0 + p.kb_per_split;
   if (kb1 > p.nkb) kb1 = p.nkb;
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(128u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(256u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -91,25 +96,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int s = i % kStages;
         if (i >= kStages) mbar_wait(empty0 + 8 * s, (uint32_t)(((i / kStages) - 1) & 1));
         const uint32_t bar = full0 + 8 * s;
-        mbar_expect_tx(bar, (uint32_t)kStageBytes);
-        const uint32_t base = smem0 + (uint32_t)s * kStageBytes;
+        mbar_expect_tx(bar, stage_bytes);
+        const uint32_t base = smem0 + (uint32_t)s * stage_bytes;
         const int kr = (kb0 + i) * 64;
         tma_load_2d(base, &tm_a, bar, m0, kr);
         tma_load_2d(base + kBoxBytes, &tm_a, bar, m0 + 64, kr);
-        tma_load_2d(base + 2 * kBoxBytes, &tm_b, bar, n0, kr);
-        tma_load_2d(base + 3 * kBoxBytes, &tm_b, bar, n0 + 64, kr);
+        for (int bb = 0; bb < nbb; ++bb) tma_load_2d(base + (uint32_t)(2 + bb) * kBoxBytes, &tm_b, bar, n0 + 64 * bb, kr);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // D = fp32, A = B = bf16, both MN-major (bits 15 / 16), M = 128, N = 128
-    const uint32_t idesc = umma_idesc_bf16(128) | (1u << 15) | (1u << 16);
+    // D = fp32, A = B = bf16, both MN-major (bits 15 / 16), M = 128, N = bn
+    const uint32_t idesc = umma_idesc_bf16(p.bn) | (1u << 15) | (1u << 16);
     for (int i = 0; i < nk; ++i) {
       const int s = i % kStages;
       mbar_wait(full0 + 8 * s, (uint32_t)((i / kStages) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        const uint32_t base = smem0 + (uint32_t)s * kStageBytes;
+        const uint32_t base = smem0 + (uint32_t)s * stage_bytes;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)       // 16 reduction rows = two 8-row atoms = 2048 bytes
           umma_bf16(tmem_base, desc_mn_sw128(base + (uint32_t)ks * 2048u), desc_mn_sw128(base + 2 * kBoxBytes + (uint32_t)ks * 2048u),
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     float* prow = p.ws + ((int64_t)split * p.M + gm) * p.N + n0;
     const bool vec = (p.N & 3) == 0;
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
       uint32_t v[32];
       if (nk > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
@@ -174,12 +178,17 @@ __global__ void __launch_bounds__(256) gemm_tn_reduce(const float* __restrict__ 
   }
 }
 
-static void plan(int M, int N, int K, int& tiles_m, int& tiles_n, int& nkb, int& nsplit, int& kb_per_split) {
+static void plan(int M, int N, int K, int& tiles_m, int& tiles_n, int& nkb, int& nsplit, int& kb_per_split, int& bn) {
+  static const int env_bn = [] { const char* e = getenv("TTA_TN_BN"); return e ? atoi(e) : 0; }();
+  static const int env_ctas = [] { const char* e = getenv("TTA_TN_CTAS"); return e ? atoi(e) : 0; }();
+  bn = env_bn ? env_bn : (N > 128 ? 256 : 128);
   tiles_m = (M + 127) / 128;
-  tiles_n = (N + 127) / 128;
+  tiles_n = (N + bn - 1) / bn;
   nkb = (K + 63) / 64;
   const int tiles = tiles_m * tiles_n;
-  nsplit = (2 * kNumSMs + tiles - 1) / tiles;          // about two CTAs per SM in total
+  // about 1.5 CTAs per SM in total (measured best of 1 / 1.5 / 2 / 3 on the DeiT-small shapes: the kernel is bound by the
+  // L2 -> shared-memory traffic of the re-read operand rows, 6-7 TB/s, not by the split)
+  nsplit = ((env_ctas ? env_ctas : 3 * kNumSMs / 2) + tiles - 1) / tiles;
   if (nsplit > nkb) nsplit = nkb;
   if (nsplit > 64) nsplit = 64;
   if (nsplit < 1) nsplit = 1;
@@ -192,8 +201,8 @@ static void plan(int M, int N, int K, int& tiles_m, int& tiles_n, int& nkb, int&
 }  // namespace tta
 
 extern "C" int64_t tta_gemm_bf16_tn_workspace_bytes(int M, int N, int K) {
-  int tm, tn, nkb, ns, per;
-  tta::gtn::plan(M, N, K, tm, tn, nkb, ns, per);
+  int tm, tn, nkb, ns, per, bn;
+  tta::gtn::plan(M, N, K, tm, tn, nkb, ns, per, bn);
   return (int64_t)ns * M * N * 4;
 }
 
@@ -211,7 +220,7 @@ extern "C" int tta_gemm_bf16_tn(const void* a, int64_t lda, const void* b, int64
   }
   Params p;
   p.M = M; p.N = N; p.K = K;
-  plan(M, N, K, p.tiles_m, p.tiles_n, p.nkb, p.nsplit, p.kb_per_split);
+  plan(M, N, K, p.tiles_m, p.tiles_n, p.nkb, p.nsplit, p.kb_per_split, p.bn);
   if (workspace_bytes < (int64_t)p.nsplit * M * N * 4) {
     set_error("gemm_bf16_tn: workspace of %lld bytes is too small", (long long)workspace_bytes);
     return TTA_E_INVALID;
