@@ -767,6 +767,11 @@ static int trd_launch_reduce(const tta_symeig_task* tasks_dev, int first, int co
 static bool g_trd_prof = false;
 struct TrdProfRec { cudaEvent_t a, b; };
 static std::vector<TrdProfRec> g_trd_recs;
+// mode 2 (scripts/trace_symeig_stages.py): five events per tta_symeig_top_batched call on the caller's stream --
+// before the reduction, after it, after the eigenvalues, after the vectors, after the back-transformation
+static int g_trd_stage_prof = 0;
+struct TrdStageRec { cudaEvent_t e[5]; int kmax, n_tasks; };
+static std::vector<TrdStageRec> g_trd_stage_recs;
 
 static int trd_reduce_dispatch(int nr, const tta_symeig_task* tasks_dev, int first, int count, int P, size_t smem,
                                cudaStream_t st) {
@@ -819,7 +824,34 @@ size_t tta_symeig_work_doubles(int k, int r) {
 
 int tta_symeig_max_k(void) { return tta::kTrdMaxK; }
 
-void tta_symeig_profile_enable(int on) { tta::g_trd_prof = on != 0; }
+void tta_symeig_profile_enable(int on) {
+  tta::g_trd_prof = on == 1;
+  tta::g_trd_stage_prof = on == 2 ? 1 : 0;
+}
+
+/* mode 2 readback: per call (in call order) kmax, n_tasks, and the milliseconds of the four stages relative to a common
+ * origin event `origin` recorded by the caller (cudaEvent_t handle) -- start of reduce, end of reduce, end of eigenvalues,
+ * end of vectors, end of back-transformation.  Returns the number of records written (7 doubles each). */
+int tta_symeig_stage_profile_read(void* origin, double* out, int max_records) {
+  using namespace tta;
+  int n = 0;
+  for (TrdStageRec& r : g_trd_stage_recs) {
+    if (n < max_records) {
+      out[7 * n] = r.kmax;
+      out[7 * n + 1] = r.n_tasks;
+      for (int i = 0; i < 5; ++i) {
+        float t = 0.f;
+        cudaEventSynchronize(r.e[i]);
+        cudaEventElapsedTime(&t, (cudaEvent_t)origin, r.e[i]);
+        out[7 * n + 2 + i] = t;
+      }
+      ++n;
+    }
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(r.e[i]);
+  }
+  g_trd_stage_recs.clear();
+  return n;
+}
 
 void tta_symeig_profile_read(double* reduce_ms, unsigned long long* reduce_launches) {
   using namespace tta;
@@ -874,6 +906,14 @@ int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_ta
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
+  TrdStageRec srec;
+  const bool stage_prof = g_trd_stage_prof != 0;
+  auto stage_mark = [&](int i) {
+    if (stage_prof && cudaEventCreate(&srec.e[i]) == cudaSuccess) cudaEventRecord(srec.e[i], st);
+  };
+  srec.kmax = kmax;
+  srec.n_tasks = n_tasks;
+  stage_mark(0);
   StreamPool* pool = runs.size() > 1 ? pool_for(dev, st) : nullptr;
   if (runs.size() > 1 && !pool) {
     set_error("symeig: cannot create internal streams");
@@ -919,11 +959,13 @@ int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_ta
       if (rc) return rc;
     }
   }
+  stage_mark(1);
   const int kpmax = (kmax + 31) & ~31;
   const size_t smem = (size_t)2 * kpmax * sizeof(double);
   // grid.x = eigenvalues of the widest task + one CTA per group of four reflectors of the largest task
   trd_eigval_kernel<<<dim3((unsigned)(rmax + (kmax + 1) / 4), (unsigned)n_tasks), kTrdEvalThreads, smem, st>>>(tasks_dev);
   TTA_CHECK_LAUNCH("symeig eigenvalue launch");
+  stage_mark(2);
   const size_t smem_vec = ((size_t)3 * kpmax + (size_t)2 * kmax * kTrdEvecPer) * sizeof(double);
   static size_t smem_vec_set = 48 * 1024;
   if (smem_vec > smem_vec_set) {
@@ -935,10 +977,13 @@ int tta_symeig_top_batched(const tta_symeig_task* tasks_dev, const tta_symeig_ta
   trd_eigvec_kernel<<<dim3((unsigned)((rmax + kTrdEvecPer - 1) / kTrdEvecPer), (unsigned)n_tasks), kTrdEvecThreads,
                       smem_vec, st>>>(tasks_dev);
   TTA_CHECK_LAUNCH("symeig eigenvector launch");
+  stage_mark(3);
   for (const Run& rn : runs) {
     rc = trd_backtransform_dispatch(rn.nr, tasks_dev, rn.first, rn.count, rn.rmax, st);
     if (rc) return rc;
   }
+  stage_mark(4);
+  if (stage_prof) g_trd_stage_recs.push_back(srec);
   return TTA_OK;
 }
 }

@@ -65,7 +65,7 @@ EXPORTS = ['tta_last_error', 'tta_version', 'tta_launch_count', 'tta_check_devic
            'tta_refine_finalize_batched', 'tta_gemm_bf16_tc', 'tta_small_gemm', 'tta_cast_bf16',
            'tta_nchw_to_nhwc_bf16', 'tta_nhwc_to_nchw_f32', 'tta_im2col_bf16', 'tta_ttconv_fused_fwd', 'tta_ttconv_tc_fwd', 'tta_ttconv_tc_supported', 'tta_ttconv_tc_pack', 'tta_ttconv_tc_blob_bytes', 'tta_gemm_bf16_tn', 'tta_gemm_bf16_tn_workspace_bytes',
            'tta_lowrank2_fwd', 'tta_symeig_top_batched', 'tta_symeig_work_doubles', 'tta_symeig_max_k',
-           'tta_symeig_profile_enable', 'tta_symeig_profile_read', 'tta_orth_penalty_fwd_batched',
+           'tta_symeig_profile_enable', 'tta_symeig_profile_read', 'tta_symeig_stage_profile_read', 'tta_orth_penalty_fwd_batched',
            'tta_orth_penalty_bwd_batched']
 
 
@@ -139,6 +139,7 @@ def _load():
     lib.tta_symeig_profile_enable.restype = None
     lib.tta_symeig_profile_read.argtypes = [vp, vp]
     lib.tta_symeig_profile_read.restype = None
+    lib.tta_symeig_stage_profile_read.argtypes = [vp, vp, ci]
     for nm in ('tta_gemm_f64_batched', 'tta_refine_prepare_batched', 'tta_refine_coeff_batched',
                'tta_refine_finalize_batched', 'tta_symeig_top_batched'):
         getattr(lib, nm).argtypes = [vp, vp, ci, vp]

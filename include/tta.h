@@ -315,6 +315,10 @@ int tta_symeig_max_k(void);
  * device time / number of launches since the last read and clears them. */
 void tta_symeig_profile_enable(int on);
 void tta_symeig_profile_read(double* reduce_ms, unsigned long long* reduce_launches);
+/* tta_symeig_profile_enable(2): five events per tta_symeig_top_batched call on the caller's stream (before the reduction,
+ * after it, after the eigenvalues, after the vectors, after the back-transformation).  Readback, in call order, 7 doubles
+ * per call: largest k, number of tasks, and the five times in ms after `origin` (a cudaEvent_t the caller recorded). */
+int tta_symeig_stage_profile_read(void* origin, double* out, int max_records);
 
 /* out[t] = sum of squares of n floats (fp64): tensorly `tl.norm(core, 2)**2` in the HOOI stopping rule. */
 typedef struct {
