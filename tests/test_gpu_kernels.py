@@ -116,7 +116,8 @@ def test_gram_row_and_col(m, n, nsplit):
 
 
 @pytest.mark.parametrize('m,n,nsplit', [(8, 4608, 9), (32, 73728, 48), (64, 576, 2), (75, 512, 1), (130, 512, 3),
-                                        (480, 4608, 18), (512, 948, 4), (300, 100, 1), (1680, 32, 3), (96, 36, 1)])
+                                        (480, 4608, 18), (512, 948, 4), (300, 100, 1), (1680, 32, 3), (96, 36, 1),
+                                        (64, 200, 4)])     # last: more slices than 128-index chunks (empty slices)
 @pytest.mark.parametrize('with_u', [False, True])
 def test_gram_tensor_core(m, n, nsplit, with_u):
     """tcgen05 3xTF32 Gram (csrc/gram_tc.cu), TMA-fed, the optional second addend summed in shared memory: row and
