@@ -11,8 +11,14 @@ every contraction of a TT / Tucker chain is one kernel of libtta.so:
 Weights are re-packed to bf16 (K padded to a multiple of 8, TT cores permuted so each chain step is a
 plain K-major GEMM) once and cached until a parameter's version counter changes.
 
-Training path (autograd enabled and something requires grad): the reference's own op chain restated
-with torch ops -- the fused backward is SURVEY 8(f) "next".
+Fused kernels on top of that: `tta_lowrank2_fwd` (two-factor linear layers, intermediate in TMEM), `tta_ttconv_tc_fwd`
+(bf16 tcgen05 fused 1x1 -> 3x3 -> 1x1 convolution, weights packed once per weight change: FoldedConv.blob) with
+`tta_ttconv_fused_fwd` (fp32 CUDA cores) for the geometries the tensor-core kernel does not serve.
+
+Training path (autograd enabled and something requires grad): the linear layers go through `LowRank2Fn` when
+`layer.fused_training` is set or autocast is active -- forward and dX on the fused two-factor kernel, V / dV on the
+TMA GEMM, the weight gradients dW1 / dW2 on `tta_gemm_bf16_tn` (csrc/gemm_tn.cu); otherwise, and for the convolution
+layers, the reference's own op chain restated with torch ops.
 """
 from __future__ import annotations
 
