@@ -207,6 +207,12 @@ def tucker_sweep(channels, frac):
     return HpTable('tk_sweep_C{}_r{}'.format(channels, r), {'weight': [r, r]})
 
 
+def tucker_sweep_all(channels=(64, 128, 256, 512, 1024, 2048), fracs=(0.25, 0.5)):
+    """Config 5 as one table: names as in workloads.tucker_sweep_weights."""
+    return HpTable('tk_sweep_all', {'c{}_r{}.weight'.format(c, int(c * f)): [int(c * f), int(c * f)]
+                                    for c in channels for f in fracs})
+
+
 ALL = {
     'tt_resnet50_general_3x': tt_resnet50_general_3x,
     'tt_resnet50_special_3x': tt_resnet50_special_3x,

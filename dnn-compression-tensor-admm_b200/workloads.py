@@ -80,6 +80,17 @@ def tucker_sweep_weight(channels, seed=0):
     return OrderedDict(weight=_normal((channels, channels, 3, 3), math.sqrt(2.0 / (channels * 9)), g))
 
 
+def tucker_sweep_weights(seed=0, channels=(64, 128, 256, 512, 1024, 2048), fracs=(0.25, 0.5)):
+    """BASELINE config 5 as ONE model: a C x C x 3 x 3 weight per (C, rank fraction) of the sweep -- independent tensors,
+    so the sweep shards over GPUs like the layers of a network (sharding.LayerSharding)."""
+    out = OrderedDict()
+    for c in channels:
+        for f in fracs:
+            g = _gen(seed + c)
+            out['c{}_r{}.weight'.format(c, int(c * f))] = _normal((c, c, 3, 3), math.sqrt(2.0 / (c * 9)), g)
+    return out
+
+
 class ParamBag(torch.nn.Module):
     """Minimal stand-in for a model: exposes `named_parameters()` with the given names.
 
