@@ -382,6 +382,37 @@ def test_gemm_bf16_tn_weight_gradient_kernel(M, N, K, lda, ldb):
     assert torch.equal(out, out2)                      # fixed summation order: bit-reproducible
 
 
+def test_tensor_core_kernels_stay_inside_their_outputs():
+    """Sentinel guards around the outputs of the round-2 tensor-core kernels (no memcheck tool on the GPU pool): nothing
+    outside the output tensor may change."""
+    g = torch.Generator(device='cpu').manual_seed(77)
+    guard = 4096
+    # fused convolution: ragged sizes, stride 1 and 2
+    for (B, Cin, H, W, Ra, Rb, Cout, stride) in ((2, 7, 13, 9, 5, 6, 11, 1), (3, 16, 15, 15, 16, 24, 32, 2), (1, 64, 8, 8, 27, 29, 64, 1)):
+        x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+        blob = rt.ttconv_tc_pack(torch.randn(Ra, Cin, generator=g).to(DEV), torch.randn(Rb, Ra, 3, 3, generator=g).to(DEV),
+                                 torch.randn(Cout, Rb, generator=g).to(DEV), None)
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        n = B * Cout * Ho * Wo
+        buf = torch.full((n + 2 * guard,), 12345.0, device=DEV)
+        y = buf[guard:guard + n].view(B, Cout, Ho, Wo)
+        rt.ttconv_tc_fwd(x, blob, y, B, Cin, H, W, Ra, Rb, Cout, 3, stride, 1)
+        torch.cuda.synchronize()
+        assert bool((buf[:guard] == 12345.0).all()) and bool((buf[guard + n:] == 12345.0).all())
+        assert not bool((y == 12345.0).any())
+    # weight-gradient GEMM: output pitch wider than N
+    for (M, N, K) in ((40, 72, 777), (129, 65, 130)):
+        a = torch.randn(K, (M + 7) // 8 * 8, generator=g).to(torch.bfloat16).to(DEV)
+        b = torch.randn(K, (N + 7) // 8 * 8, generator=g).to(torch.bfloat16).to(DEV)
+        ldc = N + 5
+        buf = torch.full((guard + M * ldc + guard,), 12345.0, device=DEV)
+        out = buf[guard:guard + M * ldc].view(M, ldc)
+        rt.gemm_bf16_tn(a, b, out, M, N, K, lda=a.shape[1], ldb=b.shape[1], ldc=ldc)
+        torch.cuda.synchronize()
+        assert bool((buf[:guard] == 12345.0).all()) and bool((buf[guard + M * ldc:] == 12345.0).all())
+        assert bool((out[:, N:] == 12345.0).all()) and not bool((out[:, :N] == 12345.0).any())
+
+
 def test_lowrank2_rejects_bad_arguments():
     x = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
     w1 = torch.zeros(400, 64, device=DEV, dtype=torch.bfloat16)

@@ -148,6 +148,7 @@ def test_gram_tensor_core(m, n, nsplit, with_u):
         rt.gram(tab)
         torch.cuda.synchronize()
         assert rt.launch_count() - n0 == 2            # gram_tc_kernel + gram_finish: no CUDA-core partial pass
+        assert bool((a == _t(A)).all())               # operands untouched (TMA reads only)
         got = g64.cpu().numpy().reshape(k, k)
         scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
         err = np.abs(got - G) / scale
