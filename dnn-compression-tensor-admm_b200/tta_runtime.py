@@ -19,7 +19,7 @@ import torch
 os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtta.so')
+LIB_PATH = os.environ.get('TTA_LIB') or os.path.join(_HERE, 'libtta.so')      # TTA_LIB: another build of the same library (A/B measurements)
 
 # ---- struct layouts (must mirror include/tta.h; checked by tests/test_abi.py against the header) ----
 P = np.uint64  # pointers
