@@ -676,7 +676,7 @@ def forward_bench(dev, peaks):
             layer.zero_grad(set_to_none=True)
             layer.fused_training = False
 
-    ms_tf = _time_cuda(lambda: lin_train(True), iters=2, warm=1)
+    ms_tf = _time_cuda(lambda: lin_train(True), iters=5, warm=2)
     ms_tc = _time_cuda(lambda: lin_train(False), iters=2, warm=1)
     gys.clear()
     macs = 0
