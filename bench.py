@@ -299,6 +299,17 @@ def run_ours(args):
     for n in admm._shard.local_names:      # every rank downloads the Z of the layers it projected
         if not torch.equal(host_z[n], admm.z[n].cpu()):
             raise SystemExit('bench.py: host Z of {} differs from the device tensor'.format(n))
+    if world > 1:
+        # the weights of the layers other ranks project must arrive by the NVLink all-gather: wipe them on the device,
+        # run one more end-to-end step, compare every parameter with the host copy
+        local = set(admm._shard.local_names)
+        for n in admm._names:
+            if n not in local:
+                params[n].data.zero_()
+        e2e_step()
+        for n in admm._names:
+            if not torch.equal(params[n].data.cpu(), host_w[n]):
+                raise SystemExit('bench.py: device W of {} differs from the host tensor after update_from_host'.format(n))
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -109,6 +109,8 @@ class ADMM:
         self._plans = None
         self._ew_cache = None
         self.sweeps = {}
+        self._xw_stream = None
+        self._xw_done = None
         self._shard = None
         self._streams = None
         self._copy_stream = None
@@ -213,10 +215,22 @@ class ADMM:
         with torch.no_grad():
             local = set(self._shard.local_names)
             remote = [n for n in self._names if n not in local]
-            self._run_plans(_host_in, _host_out)
+            # W of the layers other ranks project: one all-gather of the weight slabs (NVLink), no PCIe traffic.
+            # Up to four ranks it is issued inside _run_plans, right after the uploads of the local layers, on a side stream,
+            # and overlaps the projection (only the dual update needs the result): e2e 5.64 -> 5.34 ms at N = 2, 5.21 ->
+            # 4.92 ms at N = 4.  With 8 ranks that was measured slower (5.25 -> 6.7 ms: the NCCL CTAs spin until the slowest
+            # rank has uploaded, scattered over the GPCs, and a 16-CTA eigensolver cluster needs 16 free SMs of ONE GPC), so
+            # there the exchange follows the all-gather of Z as in round 1.  TTA_XW_OVERLAP=0 / 1 overrides.  The order of
+            # the two collectives is the same on every rank in either mode.
+            need_w = self._shard.world > 1 and _host_in is not None      # every rank takes part, whatever it owns
+            env = os.environ.get('TTA_XW_OVERLAP')
+            overlap = need_w and ((env == '1') if env in ('0', '1') else self._shard.world <= 4)
+            self._xw_done = None
+            self._run_plans(_host_in, _host_out, remote if overlap else None)
             self._shard.exchange(self.z)
-            if remote and _host_in is not None:
-                # W of the layers other ranks project: one all-gather of the weight slabs (NVLink), no PCIe traffic
+            if self._xw_done is not None:
+                torch.cuda.current_stream(self._state_device()).wait_event(self._xw_done)
+            if need_w and not overlap:
                 self._shard.exchange_weights(self._params, self._shard.local_names, remote)
             if remote and _host_out is not None and _gather_host_z:
                 self._copy(_host_out, remote, False)
@@ -232,7 +246,24 @@ class ADMM:
                         if self.verbose:
                             print('*INFO: {} in ADMM, norm(w-z)={}'.format(n, v))
 
-    def _run_plans(self, host_in=None, host_out=None):
+    def _exchange_weights(self, remote, after_events=None):
+        """All-gather of W (sharding.exchange_weights); on a side stream behind `after_events` when given."""
+        if remote is None:
+            return
+        if after_events is None:
+            self._shard.exchange_weights(self._params, self._shard.local_names, remote)
+            return
+        dev = self._state_device()
+        if self._xw_stream is None:
+            self._xw_stream = torch.cuda.Stream(device=dev)
+        for ev in after_events:
+            self._xw_stream.wait_event(ev)
+        with torch.cuda.stream(self._xw_stream):
+            self._shard.exchange_weights(self._params, self._shard.local_names, remote)
+            self._xw_done = torch.cuda.Event()
+            self._xw_done.record(self._xw_stream)
+
+    def _run_plans(self, host_in=None, host_out=None, remote=None):
         """Z-update of the local layers.  Several TT plans (layer groups) are enqueued on side streams -- the
         first two on high-priority streams -- forked from and joined back into the current stream, so that
         the Gram / refinement kernels of one group overlap the eigensolves of another and short chains do not
@@ -255,12 +286,17 @@ class ADMM:
             fork.record(main)
             t_host = time.perf_counter()
             self.enqueue_ms_per_group = []
+            uploaded = []
             for (plan, names), st in zip(async_plans, self._streams):
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
                     if host_in is not None:
                         for n in names:
                             self._params[n].data.copy_(host_in[n], non_blocking=True)
+                        if remote is not None:
+                            ev = torch.cuda.Event()
+                            ev.record(st)
+                            uploaded.append(ev)
                     plan.enqueue(*args(names))
                     if host_out is not None:
                         for n in names:
@@ -269,17 +305,27 @@ class ADMM:
                     done.record(st)
                 main.wait_event(done)
                 self.enqueue_ms_per_group.append((time.perf_counter() - t_host) * 1e3)     # diagnostics: host time so far
+            sync_plans = [(pl, nm) for pl, nm in self._plans if not hasattr(pl, 'enqueue')]
+            for plan, names in sync_plans:
+                self._copy(host_in, names, True)
+            if remote is not None:
+                if sync_plans:          # their uploads are on the current stream
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    uploaded.append(ev)
+                self._exchange_weights(remote, uploaded)
             for plan, names in self._plans:
                 if hasattr(plan, 'enqueue'):
                     plan.collect()
                 else:
-                    self._copy(host_in, names, True)
                     plan.run(*args(names))
                     self._copy(host_out, names, False)
                 self.sweeps.update(plan.sweeps)
             return
         for plan, names in self._plans:
             self._copy(host_in, names, True)
+        self._exchange_weights(remote)
+        for plan, names in self._plans:
             plan.run(*args(names))
             self._copy(host_out, names, False)
             self.sweeps.update(plan.sweeps)
