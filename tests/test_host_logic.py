@@ -404,3 +404,39 @@ def test_wave_makespan_with_whole_gpu_problems():
     t_small = projector.wave_makespan_ms([512, 256])
     assert projector.wave_makespan_ms([640]) == pytest.approx(projector.eig_time_ms(640))
     assert projector.wave_makespan_ms([512, 256, 640]) == pytest.approx(t_small + projector.eig_time_ms(640))
+
+
+def test_first_step_gram_reads_w_and_u_in_place(emulated_backend):
+    """The Gram task of the first TT step points at the parameter and the dual tensor themselves (tta_gram_task.a / a2)
+    whenever its rows are made of whole output channels; later steps, and first steps that are column Grams of a k x k
+    convolution, read the plan's own buffers."""
+    import tta_runtime as rt
+    hp = hp_tables.tt_resnet50_general_3x()
+    names = ['layer3.1.conv2.weight', 'layer3.0.conv1.weight']       # a 3 x 3 (first step truncates) and a 1 x 1 convolution
+    w = {n: t for n, t in workloads.resnet50_weights(seed=0).items() if n in names}
+    layers = [projector.TTLayer(n, tuple(w[n].shape), hp.tt_shapes[n], list(hp.ranks[n])) for n in names]
+    plan = projector.TTProjectionPlan(layers, 'cpu')
+    ws = [w[n].clone() for n in names]
+    us = [torch.randn_like(t) * 0.01 for t in ws]
+    zs = [torch.empty_like(t) for t in ws]
+    plan.bind(ws, us, zs)
+    seen = 0
+    for wave in plan.waves:
+        tab = wave['gram'].host
+        for q, li in enumerate(wave['idx']):
+            row = tab[q]
+            if int(row['a']) == ws[li].data_ptr():
+                assert int(row['a2']) == us[li].data_ptr()
+                seen += 1
+            else:
+                assert int(row['a2']) == 0
+    assert seen == len(names)          # exactly the first real step of every layer
+
+
+@pytest.mark.parametrize('k,red', [(8, 40), (32, 73728), (480, 4608), (512, 1024), (2048, 18432), (100, 7)])
+def test_gram_splits_bounds(k, red):
+    n = projector.gram_splits(k, red)
+    tiles = (k + 127) // 128
+    assert 1 <= n <= 148
+    assert n == 1 or n * 256 <= red + 255                       # at least 256 reduction indices per slice
+    assert n * tiles * (tiles + 1) // 2 <= 148 + tiles * (tiles + 1) // 2      # about one CTA per SM
